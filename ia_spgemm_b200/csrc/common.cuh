@@ -1,0 +1,117 @@
+// common.cuh -- engine context, error handling and small device helpers shared by all kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "../../include/iaspgemm.h"
+
+namespace ias {
+
+struct Ctx {
+    bool ready = false;
+    int device = 0;
+    int sm_count = 148;
+    size_t smem_optin = 227 * 1024;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;      // stream every engine kernel is launched on
+    cudaMemPool_t pool = nullptr;
+    cudaEvent_t ev[8] = {};
+    long long launches = 0;             // engine kernels launched since ias_init
+    char err[512] = {0};
+    // pinned host arena for ias_csr_mul_csr_host results (grow only)
+    void *h_arena = nullptr;
+    size_t h_arena_bytes = 0;
+    // small pinned scratch for scalar read-backs
+    long long *h_scalars = nullptr;     // 64 entries
+};
+
+Ctx &ctx();
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line);
+int fail(int code, const char *fmt, ...);
+int ensure_init();
+
+#define IAS_CUDA(x)                                                         \
+    do {                                                                    \
+        cudaError_t e__ = (x);                                              \
+        if (e__ != cudaSuccess) return ias::fail_cuda(e__, #x, __FILE__, __LINE__); \
+    } while (0)
+
+#define IAS_TRY(x)                 \
+    do {                           \
+        int rc__ = (x);            \
+        if (rc__ != IAS_OK) return rc__; \
+    } while (0)
+
+// launch bookkeeping: every engine kernel goes through this so gpu_launches is a count, not a guess
+#define IAS_LAUNCH(kernel, grid, block, smem, ...)                                   \
+    do {                                                                             \
+        kernel<<<(grid), (block), (smem), ias::ctx().stream>>>(__VA_ARGS__);         \
+        ias::ctx().launches++;                                                       \
+        cudaError_t le__ = cudaGetLastError();                                       \
+        if (le__ != cudaSuccess) return ias::fail_cuda(le__, #kernel, __FILE__, __LINE__); \
+    } while (0)
+
+// stream-ordered allocation from the engine pool (no cudaMalloc+cudaMemset per call like DevMalloc)
+template <class T>
+inline int dalloc(T **p, size_t n)
+{
+    *p = nullptr;
+    if (n == 0) n = 1;
+    cudaError_t e = cudaMallocFromPoolAsync((void **)p, n * sizeof(T), ctx().pool, ctx().stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(IAS_E_NOMEM, "device allocation of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
+    }
+    return IAS_OK;
+}
+template <class T>
+inline void dfree(T *p)
+{
+    if (p) cudaFreeAsync((void *)p, ctx().stream);
+}
+
+// RAII holder for temporaries inside one API call
+template <class T>
+struct DBuf {
+    T *p = nullptr;
+    ~DBuf() { dfree(p); }
+    int alloc(size_t n) { dfree(p); return dalloc(&p, n); }
+    T *release() { T *q = p; p = nullptr; return q; }
+    operator T *() const { return p; }
+};
+
+inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// ---------------------------------------------------------------- device helpers
+__device__ __forceinline__ unsigned hash_col(int k) { return (unsigned)k * 0x9E3779B1u; }
+
+__device__ __forceinline__ uint64_t mix64(uint64_t x)
+{
+    x ^= x >> 30; x *= 0xBF58476D1CE4E5B9ull;
+    x ^= x >> 27; x *= 0x94D049BB133111EBull;
+    x ^= x >> 31;
+    return x;
+}
+
+__device__ __forceinline__ int warp_sum(int v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ long long warp_sum(long long v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+}  // namespace ias

@@ -1,0 +1,210 @@
+// context.cu -- engine context, transfers, checksums (C ABI part 1).
+#include <stdarg.h>
+#include <stdlib.h>
+
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace ias {
+
+static Ctx g_ctx;
+Ctx &ctx() { return g_ctx; }
+
+int fail_cuda(cudaError_t e, const char *what, const char *file, int line)
+{
+    snprintf(g_ctx.err, sizeof g_ctx.err, "CUDA error %d (%s) in %s at %s:%d", (int)e, cudaGetErrorString(e), what, file, line);
+    cudaGetLastError();
+    return IAS_E_CUDA;
+}
+
+int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_ctx.err, sizeof g_ctx.err, fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+int ensure_init()
+{
+    if (g_ctx.ready) return IAS_OK;
+    return ias_init(0);
+}
+
+}  // namespace ias
+
+using namespace ias;
+
+extern "C" {
+
+const char *ias_version(void) { return "ia-spgemm-b200 0.1 (sm_100a)"; }
+const char *ias_last_error(void) { return ctx().err; }
+long long ias_kernel_launches(void) { return ctx().launches; }
+
+int ias_init(int device)
+{
+    Ctx &c = ctx();
+    if (c.ready && c.device == device) return IAS_OK;
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) {
+        cudaGetLastError();
+        return fail(IAS_E_CUDA, "no CUDA device available (%s): the engine has no CPU fallback", cudaGetErrorString(e));
+    }
+    if (device < 0 || device >= n) return fail(IAS_E_ARG, "device %d out of range (have %d)", device, n);
+    IAS_CUDA(cudaSetDevice(device));
+    c.device = device;
+    cudaDeviceProp p;
+    IAS_CUDA(cudaGetDeviceProperties(&p, device));
+    c.sm_count = p.multiProcessorCount;
+    c.smem_optin = p.sharedMemPerBlockOptin;
+    if (!c.own_stream) IAS_CUDA(cudaStreamCreateWithFlags(&c.own_stream, cudaStreamNonBlocking));
+    c.stream = c.own_stream;
+    IAS_CUDA(cudaDeviceGetDefaultMemPool(&c.pool, device));
+    unsigned long long keep = ~0ull;     // keep freed blocks in the pool: allocation cost is paid once
+    IAS_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    for (int i = 0; i < 8; ++i)
+        if (!c.ev[i]) IAS_CUDA(cudaEventCreate(&c.ev[i]));
+    if (!c.h_scalars) IAS_CUDA(cudaMallocHost((void **)&c.h_scalars, 64 * sizeof(long long)));
+    c.ready = true;
+    return IAS_OK;
+}
+
+int ias_set_stream(void *s)
+{
+    IAS_TRY(ensure_init());
+    ctx().stream = s ? (cudaStream_t)s : ctx().own_stream;
+    return IAS_OK;
+}
+
+int ias_sync(void)
+{
+    IAS_TRY(ensure_init());
+    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
+    return IAS_OK;
+}
+
+int ias_device_info(int *sm_count, size_t *smem_optin, size_t *free_bytes, size_t *total_bytes)
+{
+    IAS_TRY(ensure_init());
+    if (sm_count) *sm_count = ctx().sm_count;
+    if (smem_optin) *smem_optin = ctx().smem_optin;
+    size_t f = 0, t = 0;
+    IAS_CUDA(cudaMemGetInfo(&f, &t));
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return IAS_OK;
+}
+
+// ---------------------------------------------------------------- transfers
+int ias_upload_csr(const IasCsrMatrix *h, IasCsrMatrixDev *d)
+{
+    IAS_TRY(ensure_init());
+    if (!h || !d || h->row < 0 || h->nnz < 0) return fail(IAS_E_ARG, "ias_upload_csr: bad argument");
+    d->choice = true; d->row = h->row; d->col = h->col; d->nnz = h->nnz;
+    IAS_TRY(dalloc(&d->row_ind_dev, (size_t)h->row + 1));
+    IAS_TRY(dalloc(&d->col_ind_dev, (size_t)h->nnz));
+    IAS_TRY(dalloc(&d->values_dev, (size_t)h->nnz));
+    cudaStream_t s = ctx().stream;
+    IAS_CUDA(cudaMemcpyAsync(d->row_ind_dev, h->row_ind, sizeof(int) * ((size_t)h->row + 1), cudaMemcpyHostToDevice, s));
+    if (h->nnz) {
+        IAS_CUDA(cudaMemcpyAsync(d->col_ind_dev, h->col_ind, sizeof(int) * (size_t)h->nnz, cudaMemcpyHostToDevice, s));
+        IAS_CUDA(cudaMemcpyAsync(d->values_dev, h->values, sizeof(double) * (size_t)h->nnz, cudaMemcpyHostToDevice, s));
+    }
+    IAS_CUDA(cudaStreamSynchronize(s));
+    return IAS_OK;
+}
+
+int ias_free_csr_dev(IasCsrMatrixDev *m)
+{
+    if (!m) return IAS_OK;
+    dfree(m->row_ind_dev); dfree(m->col_ind_dev); dfree(m->values_dev);
+    m->row_ind_dev = nullptr; m->col_ind_dev = nullptr; m->values_dev = nullptr;
+    return IAS_OK;
+}
+
+int ias_free_csr64_dev(IasCsr64Dev *m)
+{
+    if (!m) return IAS_OK;
+    dfree(m->row_ptr_dev); dfree(m->col_ind_dev); dfree(m->values_dev);
+    m->row_ptr_dev = nullptr; m->col_ind_dev = nullptr; m->values_dev = nullptr;
+    return IAS_OK;
+}
+
+int ias_download_csr64(const IasCsr64Dev *d, long long *rp, int *ci, double *v)
+{
+    IAS_TRY(ensure_init());
+    if (!d) return fail(IAS_E_ARG, "ias_download_csr64: NULL");
+    cudaStream_t s = ctx().stream;
+    if (rp) IAS_CUDA(cudaMemcpyAsync(rp, d->row_ptr_dev, sizeof(long long) * ((size_t)d->row + 1), cudaMemcpyDeviceToHost, s));
+    if (ci && d->nnz) IAS_CUDA(cudaMemcpyAsync(ci, d->col_ind_dev, sizeof(int) * (size_t)d->nnz, cudaMemcpyDeviceToHost, s));
+    if (v && d->nnz) IAS_CUDA(cudaMemcpyAsync(v, d->values_dev, sizeof(double) * (size_t)d->nnz, cudaMemcpyDeviceToHost, s));
+    IAS_CUDA(cudaStreamSynchronize(s));
+    return IAS_OK;
+}
+
+int ias_download_csr(const IasCsrMatrixDev *d, int *rp, int *ci, double *v)
+{
+    IAS_TRY(ensure_init());
+    if (!d) return fail(IAS_E_ARG, "ias_download_csr: NULL");
+    cudaStream_t s = ctx().stream;
+    if (rp) IAS_CUDA(cudaMemcpyAsync(rp, d->row_ind_dev, sizeof(int) * ((size_t)d->row + 1), cudaMemcpyDeviceToHost, s));
+    if (ci && d->nnz) IAS_CUDA(cudaMemcpyAsync(ci, d->col_ind_dev, sizeof(int) * (size_t)d->nnz, cudaMemcpyDeviceToHost, s));
+    if (v && d->nnz) IAS_CUDA(cudaMemcpyAsync(v, d->values_dev, sizeof(double) * (size_t)d->nnz, cudaMemcpyDeviceToHost, s));
+    IAS_CUDA(cudaStreamSynchronize(s));
+    return IAS_OK;
+}
+
+// ---------------------------------------------------------------- verified_sum (csr_dev:258-273)
+// Deterministic: cub's reduction tree is fixed for a given n.
+int ias_checksum(const double *v, long long n, double *sum)
+{
+    IAS_TRY(ensure_init());
+    if (!sum || n < 0) return fail(IAS_E_ARG, "ias_checksum: bad argument");
+    *sum = 0.0;
+    if (n == 0) return IAS_OK;
+    DBuf<double> out;
+    IAS_TRY(out.alloc(1));
+    size_t tb = 0;
+    IAS_CUDA(cub::DeviceReduce::Sum(nullptr, tb, v, out.p, n, ctx().stream));
+    DBuf<char> tmp;
+    IAS_TRY(tmp.alloc(tb));
+    IAS_CUDA(cub::DeviceReduce::Sum(tmp.p, tb, v, out.p, n, ctx().stream));
+    ctx().launches += 2;
+    IAS_CUDA(cudaMemcpyAsync(sum, out.p, sizeof(double), cudaMemcpyDeviceToHost, ctx().stream));
+    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
+    return IAS_OK;
+}
+
+__global__ void k_is_canonical(int rows, const int *__restrict__ rp, const int *__restrict__ ci, int *bad)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    int b = 0;
+    for (int p = rp[i] + 1; p < rp[i + 1]; ++p) b |= (ci[p] <= ci[p - 1]);
+    if (b) *bad = 1;
+}
+
+int ias_csr_is_canonical(const IasCsrMatrixDev *m, int *canonical)
+{
+    IAS_TRY(ensure_init());
+    if (!m || !canonical) return fail(IAS_E_ARG, "ias_csr_is_canonical: NULL");
+    DBuf<int> bad;
+    IAS_TRY(bad.alloc(1));
+    IAS_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), ctx().stream));
+    if (m->row > 0) IAS_LAUNCH(k_is_canonical, grid_for(m->row, 256), 256, 0, m->row, m->row_ind_dev, m->col_ind_dev, bad.p);
+    int h = 0;
+    IAS_CUDA(cudaMemcpyAsync(&h, bad.p, sizeof(int), cudaMemcpyDeviceToHost, ctx().stream));
+    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
+    *canonical = !h;
+    return IAS_OK;
+}
+
+double ias_sizeof_csr(int rows, long long nnz) { return 4.0 * ((double)rows + 1 + (double)nnz + 3) + 8.0 * (double)nnz; }
+double ias_sizeof_dia(int rows, int cols, int nd) { return 4.0 * ((double)rows + cols - 1 + nd + 3) + 8.0 * ((double)rows * nd); }
+double ias_sizeof_ell(int rows, int w) { return 4.0 * ((double)rows + (double)rows * w + 4) + 8.0 * ((double)rows * w); }
+double ias_sizeof_coo(int rows, long long nnz) { return 4.0 * ((double)rows + 1 + 2.0 * (double)nnz + 3) + 8.0 * (double)nnz; }
+
+}  // extern "C"

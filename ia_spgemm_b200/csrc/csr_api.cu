@@ -1,0 +1,315 @@
+// csr_api.cu -- C ABI of the CSR hot path (Algorithm 2 and the library calls it replaces).
+#include <stdlib.h>
+
+#include "spgemm_host.cuh"
+
+using namespace ias;
+
+namespace {
+
+int check_operands(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1)
+{
+    if (!A || !B) return fail(IAS_E_ARG, "NULL operand");
+    if (A->row < 0 || A->col < 0 || B->row < 0 || B->col < 0) return fail(IAS_E_ARG, "negative dimension");
+    if (A->col > B->row) return fail(IAS_E_ARG, "shape mismatch: A is %dx%d, B is %dx%d", A->row, A->col, B->row, B->col);
+    if (r0 < 0 || r1 > A->row || r0 > r1) return fail(IAS_E_ARG, "row range [%d,%d) outside A (%d rows)", r0, r1, A->row);
+    return IAS_OK;
+}
+
+CsrView view(const IasCsrMatrixDev *M) { return CsrView{M->row_ind_dev, M->col_ind_dev, M->values_dev}; }
+
+// rows [r0,r1) of C = A*B, materialised
+int mul_rows(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, IasCsr64Dev *C, IasSpgemmStats *st)
+{
+    IAS_TRY(ensure_init());
+    IAS_TRY(check_operands(A, B, r0, r1));
+    if (!C) return fail(IAS_E_ARG, "NULL result");
+    double avg = A->row ? (double)A->nnz / A->row : 0.0;
+    return spgemm_materialise(view(A), view(B), avg, B->col, r0, r1, C, st);
+}
+
+__global__ void k_narrow_rp(int n, const long long *in, int *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int)in[i];
+}
+
+}  // namespace
+
+extern "C" {
+
+int ias_csr_mul_csr_rows_dev64(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, IasCsr64Dev *C,
+                               IasSpgemmStats *st)
+{
+    return mul_rows(A, B, r0, r1, C, st);
+}
+
+int ias_csr_mul_csr_dev64(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, IasCsr64Dev *C, IasSpgemmStats *st)
+{
+    if (!A) return fail(IAS_E_ARG, "NULL operand");
+    return mul_rows(A, B, 0, A->row, C, st);
+}
+
+int ias_csr_mul_csr_dev(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, IasCsrMatrixDev *C, double *elapsed_ms)
+{
+    if (!A || !C) return fail(IAS_E_ARG, "NULL operand");
+    IasCsr64Dev c64;
+    IasSpgemmStats st;
+    IAS_TRY(mul_rows(A, B, 0, A->row, &c64, &st));
+    if (c64.nnz >= 0x7fffffffLL) {
+        ias_free_csr64_dev(&c64);
+        return fail(IAS_E_OVERFLOW, "nnz(C) = %lld does not fit the int32 CsrMatrixDev layout; use ias_csr_mul_csr_dev64", c64.nnz);
+    }
+    C->choice = true; C->row = c64.row; C->col = c64.col; C->nnz = (int)c64.nnz;
+    IAS_TRY(dalloc(&C->row_ind_dev, (size_t)c64.row + 1));
+    IAS_LAUNCH(k_narrow_rp, grid_for(c64.row + 1, 256), 256, 0, c64.row + 1, c64.row_ptr_dev, C->row_ind_dev);
+    C->col_ind_dev = c64.col_ind_dev; C->values_dev = c64.values_dev;
+    dfree(c64.row_ptr_dev);
+    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (elapsed_ms) *elapsed_ms = st.ms_total;
+    return IAS_OK;
+}
+
+int ias_csr_mul_csr_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, size_t budget_bytes,
+                           int *row_nnz_dev, IasSpgemmStats *st)
+{
+    IAS_TRY(ensure_init());
+    IAS_TRY(check_operands(A, B, r0, r1));
+    Ctx &c = ctx();
+    long long l0 = c.launches;
+    IasSpgemmStats local;
+    memset(&local, 0, sizeof local);
+    int nrows = r1 - r0;
+
+    IAS_CUDA(cudaEventRecord(c.ev[0], c.stream));
+    IAS_CUDA(cudaEventRecord(c.ev[1], c.stream));
+    RangeWork rw;
+    CsrView av = view(A), bv = view(B);
+    double avg = A->row ? (double)A->nnz / A->row : 0.0;
+    IAS_TRY(symbolic_range(av, bv, r0, r1, B->col, avg, rw, &local));
+    IAS_CUDA(cudaEventRecord(c.ev[2], c.stream));
+    DBuf<long long> rp;
+    IAS_TRY(rp.alloc((size_t)nrows + 1));
+    IAS_TRY(scan_row_ptr(rw.nnz_row.p, nrows, rp.p));
+    if (row_nnz_dev && nrows) IAS_LAUNCH(k_copy_counts, grid_for(nrows, 256), 256, 0, nrows, rw.nnz_row.p, row_nnz_dev);
+    IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 32, rp.p + nrows, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    long long nnz = c.h_scalars[32];
+
+    // batch capacity in entries (12 B each): the budget, but never less than the largest row
+    if (budget_bytes == 0) {
+        size_t f = 0, t = 0;
+        IAS_CUDA(cudaMemGetInfo(&f, &t));
+        budget_bytes = (size_t)(0.6 * (double)f);
+    }
+    long long cap = (long long)(budget_bytes / 12);
+    cap = std::max<long long>(cap, (long long)B->col);       // nnz(C_i) <= cols: one row always fits
+    cap = std::min<long long>(cap, std::max<long long>(nnz, 1));
+    const int MAXB = 4096;
+    DBuf<int> bounds, nb;
+    IAS_TRY(bounds.alloc(MAXB + 1));
+    IAS_TRY(nb.alloc(1));
+    IAS_LAUNCH(k_batch_bounds, 1, 1, 0, nrows, rp.p, cap, MAXB, bounds.p, nb.p);
+    int h_nb = 0;
+    static int h_bounds[MAXB + 1];
+    IAS_CUDA(cudaMemcpyAsync(&h_nb, nb.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaMemcpyAsync(h_bounds, bounds.p, sizeof(int) * (MAXB + 1), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    if (h_nb < 0) return fail(IAS_E_NOMEM, "streaming budget of %zu bytes needs more than %d batches", budget_bytes, MAXB);
+
+    DBuf<int> ci;
+    DBuf<double> cv;
+    IAS_TRY(ci.alloc((size_t)cap));
+    IAS_TRY(cv.alloc((size_t)cap));
+    DBuf<unsigned long long> d_hash;
+    DBuf<double> d_sum;
+    IAS_TRY(d_hash.alloc(1));
+    IAS_TRY(d_sum.alloc(1));
+    IAS_CUDA(cudaMemsetAsync(d_hash.p, 0, sizeof(unsigned long long), c.stream));
+    IAS_CUDA(cudaMemsetAsync(d_sum.p, 0, sizeof(double), c.stream));
+    IAS_CUDA(cudaEventRecord(c.ev[3], c.stream));
+
+    for (int b = 0; b < h_nb; ++b) {
+        int b0 = h_bounds[b], b1 = h_bounds[b + 1];
+        IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 40, rp.p + b0, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+        IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 41, rp.p + b1, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+        IAS_CUDA(cudaStreamSynchronize(c.stream));
+        long long e0 = c.h_scalars[40], e1 = c.h_scalars[41];
+        if (e1 == e0) continue;
+        OutMap out{rp.p, e0, nullptr, 0};
+        IAS_TRY(numeric_rows(av, bv, rw, b0, b1, B->col, out, ci.p, cv.p, &local));
+        long long threads = (e1 - e0 + 15) / 16;
+        IAS_LAUNCH(k_consume, grid_for(threads, 256), 256, 0, b1 - b0, r0 + b0, rp.p + b0, e0, ci.p, cv.p, d_hash.p, d_sum.p);
+    }
+    IAS_CUDA(cudaEventRecord(c.ev[4], c.stream));
+    IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 42, d_hash.p, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 43, d_sum.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+
+    local.nnz = nnz;
+    local.batches = h_nb;
+    local.structure_hash = (unsigned long long)c.h_scalars[42];
+    memcpy(&local.checksum, c.h_scalars + 43, sizeof(double));
+    local.ms_analyze = ias::ev_ms(0, 1); local.ms_symbolic = ias::ev_ms(1, 2); local.ms_scan = ias::ev_ms(2, 3);
+    local.ms_numeric = ias::ev_ms(3, 4); local.ms_total = ias::ev_ms(0, 4);
+    for (int b = 0; b < 8; ++b) local.num_bin_rows[b] = b < NBINS ? rw.num_hist[b] : 0;
+    local.kernel_launches = (int)(c.launches - l0);
+    if (st) *st = local;
+    return IAS_OK;
+}
+
+int ias_structure_hash(const IasCsr64Dev *C, int row_base, unsigned long long *hash)
+{
+    IAS_TRY(ensure_init());
+    if (!C || !hash) return fail(IAS_E_ARG, "NULL");
+    Ctx &c = ctx();
+    *hash = 0;
+    if (C->nnz == 0) return IAS_OK;
+    DBuf<unsigned long long> d_hash;
+    DBuf<double> d_sum;
+    IAS_TRY(d_hash.alloc(1));
+    IAS_TRY(d_sum.alloc(1));
+    IAS_CUDA(cudaMemsetAsync(d_hash.p, 0, sizeof(unsigned long long), c.stream));
+    IAS_CUDA(cudaMemsetAsync(d_sum.p, 0, sizeof(double), c.stream));
+    long long threads = (C->nnz + 15) / 16;
+    IAS_LAUNCH(k_consume, grid_for(threads, 256), 256, 0, C->row, row_base, C->row_ptr_dev, 0LL, C->col_ind_dev, C->values_dev, d_hash.p, d_sum.p);
+    IAS_CUDA(cudaMemcpyAsync(hash, d_hash.p, sizeof(unsigned long long), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    return IAS_OK;
+}
+
+// ---------------------------------------------------------------- host operands (the e2e path)
+static int host_arena(size_t bytes, void **p)
+{
+    Ctx &c = ctx();
+    if (c.h_arena_bytes < bytes) {
+        if (c.h_arena) cudaFreeHost(c.h_arena);
+        c.h_arena = nullptr; c.h_arena_bytes = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMallocHost(&c.h_arena, want);
+        if (e != cudaSuccess) { cudaGetLastError(); return fail(IAS_E_NOMEM, "pinned host allocation of %zu bytes failed", want); }
+        c.h_arena_bytes = want;
+    }
+    *p = c.h_arena;
+    return IAS_OK;
+}
+
+int ias_release_host(void)
+{
+    Ctx &c = ctx();
+    if (c.h_arena) cudaFreeHost(c.h_arena);
+    c.h_arena = nullptr; c.h_arena_bytes = 0;
+    return IAS_OK;
+}
+
+int ias_csr_mul_csr_host(const IasCsrMatrix *A, const IasCsrMatrix *B, long long **c_rp, int **c_ci, double **c_v,
+                         long long *c_nnz, IasSpgemmStats *st, double *ms_h2d, double *ms_d2h)
+{
+    IAS_TRY(ensure_init());
+    if (!A || !B || !c_rp || !c_ci || !c_v || !c_nnz) return fail(IAS_E_ARG, "NULL");
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    bool alias = (A == B) || (A->row_ind == B->row_ind && A->col_ind == B->col_ind && A->values == B->values &&
+                              A->row == B->row && A->col == B->col);
+    IasCsrMatrixDev dA = {}, dB = {};
+    IAS_CUDA(cudaEventRecord(c.ev[5], s));
+    IAS_TRY(ias_upload_csr(A, &dA));
+    if (alias) dB = dA; else IAS_TRY(ias_upload_csr(B, &dB));
+    IAS_CUDA(cudaEventRecord(c.ev[6], s));
+    IasCsr64Dev dC = {};
+    int rc = mul_rows(&dA, &dB, 0, dA.row, &dC, st);
+    if (rc == IAS_OK) {
+        IAS_CUDA(cudaEventRecord(c.ev[7], s));
+        size_t b_rp = sizeof(long long) * ((size_t)dC.row + 1), b_ci = sizeof(int) * (size_t)dC.nnz, b_v = sizeof(double) * (size_t)dC.nnz;
+        size_t o_v = (b_rp + 255) / 256 * 256, o_ci = o_v + (b_v + 255) / 256 * 256;
+        void *base = nullptr;
+        rc = host_arena(o_ci + b_ci + 256, &base);
+        if (rc == IAS_OK) {
+            *c_rp = (long long *)base;
+            *c_v = (double *)((char *)base + o_v);
+            *c_ci = (int *)((char *)base + o_ci);
+            rc = ias_download_csr64(&dC, *c_rp, *c_ci, *c_v);
+            *c_nnz = dC.nnz;
+        }
+        cudaEventRecord(c.ev[0], s);           // mul_rows is done with ev[0]: reuse it as end of download
+        cudaStreamSynchronize(s);
+        if (ms_h2d) { float ms = 0; cudaEventElapsedTime(&ms, c.ev[5], c.ev[6]); *ms_h2d = ms; }
+        if (ms_d2h) { float ms = 0; cudaEventElapsedTime(&ms, c.ev[7], c.ev[0]); *ms_d2h = ms; }
+    }
+    ias_free_csr64_dev(&dC);
+    ias_free_csr_dev(&dA);
+    if (!alias) ias_free_csr_dev(&dB);
+    return rc;
+}
+
+// ---------------------------------------------------------------- GetFlop and work-balanced row blocks
+namespace {
+__global__ void __launch_bounds__(256) k_row_products(int nrows, CsrView A, CsrView B, long long *__restrict__ out)
+{
+    int lane = threadIdx.x & 31;
+    int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (i >= nrows) return;
+    long long ub = 0;
+    int pe = A.end(i);
+    for (int p = A.begin(i) + lane; p < pe; p += 32) ub += B.len(__ldg(A.ci + p));
+    ub = warp_sum(ub);
+    if (lane == 0) out[i] = ub;
+}
+__global__ void k_split(int nrows, const long long *__restrict__ incl, int parts, int *__restrict__ bounds)
+{
+    int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p > parts) return;
+    if (p == 0) { bounds[0] = 0; return; }
+    if (p == parts) { bounds[parts] = nrows; return; }
+    long long total = nrows ? incl[nrows - 1] : 0;
+    long long target = (long long)((double)total * p / parts);
+    int lo = 0, hi = nrows;                     // first row whose inclusive prefix exceeds the target
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (incl[mid] <= target) lo = mid + 1; else hi = mid; }
+    bounds[p] = lo;
+}
+}  // namespace
+
+static int row_products_scan(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, DBuf<long long> &incl)
+{
+    IAS_TRY(incl.alloc((size_t)A->row + 1));
+    if (A->row == 0) return IAS_OK;
+    IAS_LAUNCH(k_row_products, grid_for((long long)A->row * 32, 256), 256, 0, A->row, view(A), view(B), incl.p);
+    size_t tb = 0;
+    IAS_CUDA(cub::DeviceScan::InclusiveSum(nullptr, tb, incl.p, incl.p, A->row, ctx().stream));
+    DBuf<char> tmp;
+    IAS_TRY(tmp.alloc(tb));
+    IAS_CUDA(cub::DeviceScan::InclusiveSum(tmp.p, tb, incl.p, incl.p, A->row, ctx().stream));
+    ctx().launches += 2;
+    return IAS_OK;
+}
+
+int ias_getflop(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, long long *products)
+{
+    IAS_TRY(ensure_init());
+    IAS_TRY(check_operands(A, B, 0, A ? A->row : 0));
+    if (!products) return fail(IAS_E_ARG, "NULL");
+    *products = 0;
+    if (A->row == 0) return IAS_OK;
+    DBuf<long long> incl;
+    IAS_TRY(row_products_scan(A, B, incl));
+    IAS_CUDA(cudaMemcpyAsync(products, incl.p + A->row - 1, sizeof(long long), cudaMemcpyDeviceToHost, ctx().stream));
+    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
+    return IAS_OK;
+}
+
+int ias_partition_rows(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int parts, int *bounds)
+{
+    IAS_TRY(ensure_init());
+    IAS_TRY(check_operands(A, B, 0, A ? A->row : 0));
+    if (parts < 1 || !bounds) return fail(IAS_E_ARG, "bad partition request");
+    DBuf<long long> incl;
+    IAS_TRY(row_products_scan(A, B, incl));
+    DBuf<int> d_bounds;
+    IAS_TRY(d_bounds.alloc((size_t)parts + 1));
+    IAS_LAUNCH(k_split, grid_for(parts + 1, 64), 64, 0, A->row, incl.p, parts, d_bounds.p);
+    IAS_CUDA(cudaMemcpyAsync(bounds, d_bounds.p, sizeof(int) * ((size_t)parts + 1), cudaMemcpyDeviceToHost, ctx().stream));
+    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
+    return IAS_OK;
+}
+
+}  // extern "C"

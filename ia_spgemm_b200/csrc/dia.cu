@@ -1,0 +1,273 @@
+// dia.cu -- DIA format: converter and the DIA x DIA kernel (Algorithm 3).
+//
+// Replaces CSRtoDIA (CPU/detail/dia/common_dia.h:29-96), DIA_mul_DIA (dia:101-195) and the
+// never-called DIA_MUL_DIA_DEV chain (GPU/detail/dia_dev/common_dia_dev.h:27-182: phase1 flags
+// diagonals with a row loop, DIA_sum<<<1,1>>> compacts serially, phase3 walks row-major values with
+// a stride of num_diagonals).  Here:
+//   - values are DIAGONAL-MAJOR on device (values[slot*rows + i]) so a warp reads/writes 256
+//     contiguous bytes per diagonal;
+//   - the set of output diagonals is a function of the offsets and the matrix bounds alone
+//     (dia:104-140 never looks at values), so it is computed on the host in O(dA*dB);
+//   - one pass writes every output diagonal once, accumulating all contributing (a,b) pairs in a
+//     register: HBM traffic = 8*n*(dA + dB + dC) bytes, the algorithmic minimum.
+#include <algorithm>
+#include <vector>
+
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+using namespace ias;
+
+namespace {
+
+__global__ void __launch_bounds__(256) k_flag_diagonals(int rows, const int *__restrict__ rp, const int *__restrict__ ci,
+                                                        int *__restrict__ flags /* rows+cols, index (rows-i)+j */)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    int pe = rp[i + 1];
+    for (int p = rp[i]; p < pe; ++p) {
+        int m = (rows - i) + ci[p];
+        if (!flags[m]) flags[m] = 1;
+    }
+}
+
+// slot_of = exclusive scan of flags.  offsets[slot] = m - rows; diagonal_ind[m-1] = slot (0 when absent)
+__global__ void __launch_bounds__(256) k_number_diagonals(int span, int rows, const int *__restrict__ flags,
+                                                          const int *__restrict__ slot_of, int *__restrict__ offsets,
+                                                          int *__restrict__ diag_ind)
+{
+    int m = blockIdx.x * blockDim.x + threadIdx.x;
+    if (m >= span) return;
+    int present = flags[m];
+    if (present) offsets[slot_of[m]] = m - rows;
+    if (m >= 1) diag_ind[m - 1] = present ? slot_of[m] : 0;
+}
+
+__global__ void __launch_bounds__(256) k_fill_dia(int rows, const int *__restrict__ rp, const int *__restrict__ ci,
+                                                  const double *__restrict__ v, const int *__restrict__ slot_of,
+                                                  double *__restrict__ values /* diagonal-major */)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows) return;
+    int pe = rp[i + 1];
+    for (int p = rp[i]; p < pe; ++p) {           // in order: a duplicate (i,j) overwrites, as dia:75-90 does
+        int slot = slot_of[(rows - i) + ci[p]];
+        values[(size_t)slot * rows + i] = v[p];
+    }
+}
+
+// C[d][i] = sum over pairs (a,b) of diagonal d:  A[a][i] * B[b][i + offA[a]]   (dia:162-193)
+// pair tables live in shared memory; one thread per row, all diagonals of the row in one pass.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_dia_mul_dia(int rows, int a_cols, int b_cols, int a_nd, int b_nd, int c_nd,
+                                                       const int *__restrict__ a_off, const int *__restrict__ b_off,
+                                                       const double *__restrict__ a_val, const double *__restrict__ b_val,
+                                                       const int *__restrict__ pair_start /* c_nd+1 */,
+                                                       const unsigned *__restrict__ pairs /* a<<16 | b */, int npairs,
+                                                       double *__restrict__ c_val)
+{
+    extern __shared__ int sm[];
+    int *s_start = sm;                         // c_nd + 1
+    int *s_aoff = s_start + c_nd + 1;          // a_nd
+    int *s_boff = s_aoff + a_nd;               // b_nd
+    unsigned *s_pairs = reinterpret_cast<unsigned *>(s_boff + b_nd);   // npairs
+    for (int t = threadIdx.x; t <= c_nd; t += BLOCK) s_start[t] = pair_start[t];
+    for (int t = threadIdx.x; t < a_nd; t += BLOCK) s_aoff[t] = a_off[t];
+    for (int t = threadIdx.x; t < b_nd; t += BLOCK) s_boff[t] = b_off[t];
+    for (int t = threadIdx.x; t < npairs; t += BLOCK) s_pairs[t] = pairs[t];
+    __syncthreads();
+    const int b_rows = a_cols;
+    for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < rows; i += (long long)gridDim.x * BLOCK) {
+        for (int d = 0; d < c_nd; ++d) {
+            double acc = 0.0;
+            int pe = s_start[d + 1];
+            for (int p = s_start[d]; p < pe; ++p) {
+                unsigned ab = s_pairs[p];
+                int a = ab >> 16, b = ab & 0xffff;
+                long long j = i + s_aoff[a];
+                long long k = j + s_boff[b];
+                if (j >= 0 && j < a_cols && k >= 0 && k < b_cols)
+                    acc += __ldg(a_val + (size_t)a * rows + i) * __ldg(b_val + (size_t)b * b_rows + j);
+            }
+            c_val[(size_t)d * rows + i] = acc;
+        }
+    }
+}
+
+// diagonal-major -> the reference's row-major [i*nd + slot] (for downloads / parity checks)
+__global__ void __launch_bounds__(256) k_dia_to_row_major(int rows, int nd, const double *__restrict__ in, double *__restrict__ out)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)rows * nd;
+    if (t >= n) return;
+    size_t i = t / nd, s = t % nd;
+    out[t] = in[s * rows + i];
+}
+
+int diag_census(const IasCsrMatrixDev *A, DBuf<int> &flags, DBuf<int> &slot_of, int *nd)
+{
+    Ctx &c = ctx();
+    int span = A->row + A->col;                     // map index (rows - i) + j lies in [1, rows+cols-1]
+    IAS_TRY(flags.alloc((size_t)span + 1));
+    IAS_TRY(slot_of.alloc((size_t)span + 1));
+    IAS_CUDA(cudaMemsetAsync(flags.p, 0, sizeof(int) * ((size_t)span + 1), c.stream));
+    if (A->row) IAS_LAUNCH(k_flag_diagonals, grid_for(A->row, 256), 256, 0, A->row, A->row_ind_dev, A->col_ind_dev, flags.p);
+    size_t tb = 0;
+    IAS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flags.p, slot_of.p, span + 1, c.stream));
+    DBuf<char> tmp;
+    IAS_TRY(tmp.alloc(tb));
+    IAS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags.p, slot_of.p, span + 1, c.stream));
+    c.launches += 2;
+    IAS_CUDA(cudaMemcpyAsync(nd, slot_of.p + span, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    return IAS_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int ias_count_diagonals(const IasCsrMatrixDev *A, int *num_diagonals)
+{
+    IAS_TRY(ensure_init());
+    if (!A || !num_diagonals) return fail(IAS_E_ARG, "NULL");
+    DBuf<int> flags, slot_of;
+    return diag_census(A, flags, slot_of, num_diagonals);
+}
+
+int ias_csr_to_dia(const IasCsrMatrixDev *A, double gate, IasDiaDev *out)
+{
+    IAS_TRY(ensure_init());
+    if (!A || !out) return fail(IAS_E_ARG, "NULL");
+    Ctx &c = ctx();
+    memset(out, 0, sizeof *out);
+    out->row = A->row; out->col = A->col;
+    DBuf<int> flags, slot_of;
+    int nd = 0;
+    IAS_TRY(diag_census(A, flags, slot_of, &nd));
+    out->num_diagonals = nd;
+    // size gate of the reference (dia:56 uses 50x on the CPU, GPU/detail/dia/common_dia.h:51 uses 20x)
+    if (!(ias_sizeof_dia(A->row, A->col, nd) < gate * ias_sizeof_csr(A->row, A->nnz))) {
+        out->choice = false;
+        return IAS_OK;
+    }
+    if (nd > 65535) { out->choice = false; return IAS_OK; }   // pair tables index diagonals with 16 bits
+    out->choice = true;
+    int span = A->row + A->col;
+    DBuf<int> di, off;
+    DBuf<double> val;
+    IAS_TRY(di.alloc((size_t)std::max(span - 1, 1)));
+    IAS_TRY(off.alloc((size_t)std::max(nd, 1)));
+    IAS_TRY(val.alloc((size_t)A->row * nd));
+    IAS_CUDA(cudaMemsetAsync(val.p, 0, sizeof(double) * (size_t)A->row * nd, c.stream));
+    IAS_LAUNCH(k_number_diagonals, grid_for(span, 256), 256, 0, span, A->row, flags.p, slot_of.p, off.p, di.p);
+    if (A->row) IAS_LAUNCH(k_fill_dia, grid_for(A->row, 256), 256, 0, A->row, A->row_ind_dev, A->col_ind_dev, A->values_dev, slot_of.p, val.p);
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    out->diagonal_ind_dev = di.release(); out->diagonal_offsets_dev = off.release(); out->values_dev = val.release();
+    return IAS_OK;
+}
+
+int ias_free_dia_dev(IasDiaDev *m)
+{
+    if (!m) return IAS_OK;
+    dfree(m->diagonal_ind_dev); dfree(m->diagonal_offsets_dev); dfree(m->values_dev);
+    m->diagonal_ind_dev = nullptr; m->diagonal_offsets_dev = nullptr; m->values_dev = nullptr;
+    return IAS_OK;
+}
+
+int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, double *elapsed_ms)
+{
+    IAS_TRY(ensure_init());
+    if (!A || !B || !C) return fail(IAS_E_ARG, "NULL");
+    if (!A->choice || !B->choice) return fail(IAS_E_GATE, "DIA operand was rejected by the size gate (choice == false)");
+    if (A->col > B->row) return fail(IAS_E_ARG, "shape mismatch: A is %dx%d, B is %dx%d", A->row, A->col, B->row, B->col);
+    Ctx &c = ctx();
+    cudaStream_t s = c.stream;
+    memset(C, 0, sizeof *C);
+    C->row = A->row; C->col = B->col; C->choice = true;
+    IAS_CUDA(cudaEventRecord(c.ev[0], s));
+
+    // offsets are tiny: fetch them and enumerate the reachable output diagonals on the host.
+    // (a,b) reaches diagonal oA+oB iff some row i has 0 <= i+oA < a_cols and 0 <= i+oA+oB < b_cols (dia:110-131)
+    std::vector<int> ao(A->num_diagonals), bo(B->num_diagonals);
+    if (!ao.empty()) IAS_CUDA(cudaMemcpyAsync(ao.data(), A->diagonal_offsets_dev, sizeof(int) * ao.size(), cudaMemcpyDeviceToHost, s));
+    if (!bo.empty()) IAS_CUDA(cudaMemcpyAsync(bo.data(), B->diagonal_offsets_dev, sizeof(int) * bo.size(), cudaMemcpyDeviceToHost, s));
+    IAS_CUDA(cudaStreamSynchronize(s));
+    struct Pair { long long off; unsigned ab; };
+    std::vector<Pair> pairs;
+    pairs.reserve(ao.size() * bo.size());
+    for (size_t a = 0; a < ao.size(); ++a)
+        for (size_t b = 0; b < bo.size(); ++b) {
+            long long oa = ao[a], ob = bo[b];
+            long long lo = std::max<long long>(0, std::max(-oa, -oa - ob));
+            long long hi = std::min<long long>(A->row, std::min<long long>((long long)A->col - oa, (long long)B->col - oa - ob));
+            if (lo < hi) pairs.push_back({oa + ob, (unsigned)((a << 16) | b)});
+        }
+    std::stable_sort(pairs.begin(), pairs.end(), [](const Pair &x, const Pair &y) { return x.off < y.off; });
+    std::vector<int> c_off, pstart;
+    std::vector<unsigned> pab(pairs.size());
+    for (size_t p = 0; p < pairs.size(); ++p) {
+        if (p == 0 || pairs[p].off != pairs[p - 1].off) { c_off.push_back((int)pairs[p].off); pstart.push_back((int)p); }
+        pab[p] = pairs[p].ab;
+    }
+    pstart.push_back((int)pairs.size());
+    int c_nd = (int)c_off.size();
+    C->num_diagonals = c_nd;
+
+    int span = A->row + B->col - 1;
+    std::vector<int> h_di((size_t)std::max(span, 1), 0);
+    for (int d = 0; d < c_nd; ++d) h_di[(size_t)c_off[d] + A->row - 1] = d;     // dia:150-158
+    DBuf<int> di, off, d_pstart;
+    DBuf<unsigned> d_pairs;
+    DBuf<double> val;
+    IAS_TRY(di.alloc(h_di.size()));
+    IAS_TRY(off.alloc((size_t)std::max(c_nd, 1)));
+    IAS_TRY(d_pstart.alloc(pstart.size()));
+    IAS_TRY(d_pairs.alloc(std::max<size_t>(pab.size(), 1)));
+    IAS_TRY(val.alloc((size_t)A->row * c_nd));
+    IAS_CUDA(cudaMemcpyAsync(di.p, h_di.data(), sizeof(int) * h_di.size(), cudaMemcpyHostToDevice, s));
+    if (c_nd) IAS_CUDA(cudaMemcpyAsync(off.p, c_off.data(), sizeof(int) * c_nd, cudaMemcpyHostToDevice, s));
+    IAS_CUDA(cudaMemcpyAsync(d_pstart.p, pstart.data(), sizeof(int) * pstart.size(), cudaMemcpyHostToDevice, s));
+    if (!pab.empty()) IAS_CUDA(cudaMemcpyAsync(d_pairs.p, pab.data(), sizeof(unsigned) * pab.size(), cudaMemcpyHostToDevice, s));
+
+    size_t sm = sizeof(int) * ((size_t)c_nd + 1 + ao.size() + bo.size() + pab.size());
+    if (sm > c.smem_optin) return fail(IAS_E_NOMEM, "DIA pair table (%zu bytes) exceeds shared memory", sm);
+    if (A->row && c_nd) {
+        constexpr int BLOCK = 256;
+        auto k = k_dia_mul_dia<BLOCK>;
+        if (sm > 48 * 1024) IAS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        unsigned grid = (unsigned)std::min<long long>(grid_for(A->row, BLOCK), (long long)c.sm_count * 8 * 64);
+        IAS_LAUNCH(k, grid, BLOCK, sm, A->row, A->col, B->col, (int)ao.size(), (int)bo.size(), c_nd, A->diagonal_offsets_dev,
+                   B->diagonal_offsets_dev, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p, (int)pab.size(), val.p);
+    }
+    IAS_CUDA(cudaEventRecord(c.ev[1], s));
+    IAS_CUDA(cudaStreamSynchronize(s));
+    if (elapsed_ms) { float ms = 0; cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]); *elapsed_ms = ms; }
+    C->diagonal_ind_dev = di.release(); C->diagonal_offsets_dev = off.release(); C->values_dev = val.release();
+    return IAS_OK;
+}
+
+int ias_download_dia(const IasDiaDev *d, int *diagonal_ind, int *diagonal_offsets, double *values_row_major)
+{
+    IAS_TRY(ensure_init());
+    if (!d) return fail(IAS_E_ARG, "NULL");
+    if (!d->choice) return fail(IAS_E_GATE, "DIA matrix was rejected by the size gate");
+    Ctx &c = ctx();
+    int span = d->row + d->col - 1;
+    if (diagonal_ind && span > 0) IAS_CUDA(cudaMemcpyAsync(diagonal_ind, d->diagonal_ind_dev, sizeof(int) * span, cudaMemcpyDeviceToHost, c.stream));
+    if (diagonal_offsets && d->num_diagonals) IAS_CUDA(cudaMemcpyAsync(diagonal_offsets, d->diagonal_offsets_dev, sizeof(int) * d->num_diagonals, cudaMemcpyDeviceToHost, c.stream));
+    size_t n = (size_t)d->row * d->num_diagonals;
+    if (values_row_major && n) {
+        DBuf<double> rm;
+        IAS_TRY(rm.alloc(n));
+        IAS_LAUNCH(k_dia_to_row_major, grid_for((long long)n, 256), 256, 0, d->row, d->num_diagonals, d->values_dev, rm.p);
+        IAS_CUDA(cudaMemcpyAsync(values_row_major, rm.p, sizeof(double) * n, cudaMemcpyDeviceToHost, c.stream));
+        IAS_CUDA(cudaStreamSynchronize(c.stream));
+    }
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    return IAS_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,292 @@
+// spgemm_host.cuh -- host orchestration of the Gustavson pipeline for one row range of C.
+// Templated on the operand views so that the CSR, ELL and COO entry points share it.
+#pragma once
+#include <algorithm>
+
+#include <thrust/iterator/transform_iterator.h>
+
+#include "spgemm_kernels.cuh"
+
+namespace ias {
+
+constexpr int TINY_BLOCK = 128;
+constexpr int G_BLOCK = 512;
+
+// row lists grouped by bin: list == nullptr means "identity" (every row of the range is in `only_bin`)
+struct BinLists {
+    DBuf<int> list;
+    DBuf<unsigned char> keys_sorted;
+    DBuf<int> iota;
+    DBuf<char> tmp;
+    long long count[8] = {0};
+    long long offset[8] = {0};
+    int only_bin = -1;
+    const int *rows_of(int bin) const { return only_bin >= 0 ? nullptr : list.p + offset[bin]; }
+};
+
+inline int build_bin_lists(int nrows, const unsigned char *bin_dev, const long long *hist, BinLists &bl)
+{
+    bl.only_bin = -1;
+    long long run = 0;
+    for (int b = 0; b < NBINS; ++b) {
+        bl.count[b] = hist[b];
+        bl.offset[b] = run;
+        run += hist[b];
+        if (hist[b] == nrows) bl.only_bin = b;
+    }
+    if (bl.only_bin >= 0 || nrows == 0) return IAS_OK;
+    IAS_TRY(bl.list.alloc(nrows));
+    IAS_TRY(bl.keys_sorted.alloc(nrows));
+    IAS_TRY(bl.iota.alloc(nrows));
+    IAS_LAUNCH(k_iota, grid_for(nrows, 256), 256, 0, nrows, bl.iota.p);
+    size_t tb = 0;
+    IAS_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tb, bin_dev, bl.keys_sorted.p, bl.iota.p, bl.list.p, nrows, 0, 3, ctx().stream));
+    IAS_TRY(bl.tmp.alloc(tb));
+    IAS_CUDA(cub::DeviceRadixSort::SortPairs(bl.tmp.p, tb, bin_dev, bl.keys_sorted.p, bl.iota.p, bl.list.p, nrows, 0, 3, ctx().stream));
+    ctx().launches += 3;       // histogram + onesweep passes of the 3-bit stable sort
+    return IAS_OK;
+}
+
+template <class K>
+inline int opt_in_smem(K kernel, size_t bytes)
+{
+    if (bytes > 32 * 1024) IAS_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    return IAS_OK;
+}
+
+// state of one row range [r0, r1) after analysis + symbolic
+struct RangeWork {
+    int r0 = 0, nrows = 0;
+    DBuf<int> ub;                  // nrows
+    DBuf<int> nnz_row;             // nrows + 1 (last = 0, so that the scan yields the total)
+    DBuf<unsigned char> bin;       // nrows
+    DBuf<unsigned long long> hist; // 16 counters
+    DBuf<unsigned> gwork;          // global-row workspace slots
+    DBuf<int> cursor;
+    int gslots = 0;
+    long long products = 0;
+    long long sym_hist[8] = {0};
+    long long num_hist[8] = {0};
+    int max_tiny_nnz = 0, max_nnz = 0;
+};
+
+inline int read_hist(RangeWork &rw, int n, long long *out)
+{
+    Ctx &c = ctx();
+    IAS_CUDA(cudaMemcpyAsync(c.h_scalars, rw.hist.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    for (int i = 0; i < n; ++i) out[i] = c.h_scalars[i];
+    return IAS_OK;
+}
+
+inline int ensure_gwork(RangeWork &rw, int ncols, long long nrows_g)
+{
+    if (nrows_g <= 0) return IAS_OK;
+    GLayout L = GLayout::make(ncols);
+    int slots = (int)std::min<long long>(nrows_g, 2LL * ctx().sm_count);
+    if (rw.gslots >= slots && rw.gwork.p) return IAS_OK;
+    IAS_TRY(rw.gwork.alloc((size_t)slots * L.slot_words));
+    IAS_CUDA(cudaMemsetAsync(rw.gwork.p, 0, (size_t)slots * L.slot_words * sizeof(unsigned), ctx().stream));
+    if (!rw.cursor.p) IAS_TRY(rw.cursor.alloc(1));
+    rw.gslots = slots;
+    return IAS_OK;
+}
+
+// analysis + symbolic over [r0, r1): fills rw.ub, rw.nnz_row (exact nnz(C_i)), products
+template <class AV, class BV>
+int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double avg_a_row, RangeWork &rw, IasSpgemmStats *st)
+{
+    Ctx &c = ctx();
+    int nrows = r1 - r0;
+    rw.r0 = r0; rw.nrows = nrows;
+    IAS_TRY(rw.ub.alloc(nrows));
+    IAS_TRY(rw.nnz_row.alloc((size_t)nrows + 1));
+    IAS_TRY(rw.bin.alloc(nrows));
+    IAS_TRY(rw.hist.alloc(16));
+    IAS_CUDA(cudaMemsetAsync(rw.hist.p, 0, 16 * sizeof(unsigned long long), c.stream));
+    IAS_CUDA(cudaMemsetAsync(rw.nnz_row.p, 0, sizeof(int) * ((size_t)nrows + 1), c.stream));
+    if (nrows == 0) return IAS_OK;
+    if (avg_a_row > 8.0)
+        IAS_LAUNCH((k_row_ub_warp<AV, BV>), grid_for((long long)nrows * 32, 256), 256, 0, nrows, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p);
+    else
+        IAS_LAUNCH((k_row_ub_thread<AV, BV>), grid_for(nrows, 256), 256, 0, nrows, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p);
+    long long h[NBINS + 1];
+    IAS_TRY(read_hist(rw, NBINS + 1, h));
+    rw.products = h[NBINS];
+    for (int b = 0; b < NBINS; ++b) rw.sym_hist[b] = h[b];
+    IAS_CUDA(cudaEventRecord(c.ev[1], c.stream));
+
+    BinLists bl;
+    IAS_TRY(build_bin_lists(nrows, rw.bin.p, h, bl));
+    if (bl.count[BIN_T]) {
+        int n = (int)bl.count[BIN_T];
+        IAS_LAUNCH((k_sym_tiny<AV, BV, TINY_BLOCK>), grid_for(n, TINY_BLOCK), TINY_BLOCK, 0, bl.rows_of(BIN_T), n, r0, A, B, rw.nnz_row.p);
+    }
+    if (bl.count[BIN_W]) {
+        int n = (int)bl.count[BIN_W];
+        auto k = k_sym_hash<AV, BV, 32, 256, SYM_W_TSIZE>;
+        size_t sm = (size_t)8 * SYM_W_TSIZE * sizeof(int);
+        IAS_TRY(opt_in_smem(k, sm));
+        IAS_LAUNCH(k, grid_for(n, 8), 256, sm, bl.rows_of(BIN_W), n, r0, A, B, rw.nnz_row.p);
+    }
+    if (bl.count[BIN_B1]) {
+        int n = (int)bl.count[BIN_B1];
+        auto k = k_sym_hash<AV, BV, 256, 256, SYM_B1_TSIZE>;
+        size_t sm = (size_t)SYM_B1_TSIZE * sizeof(int);
+        IAS_TRY(opt_in_smem(k, sm));
+        IAS_LAUNCH(k, n, 256, sm, bl.rows_of(BIN_B1), n, r0, A, B, rw.nnz_row.p);
+    }
+    if (bl.count[BIN_B2]) {
+        int n = (int)bl.count[BIN_B2];
+        auto k = k_sym_hash<AV, BV, 1024, 1024, SYM_B2_TSIZE>;
+        size_t sm = (size_t)SYM_B2_TSIZE * sizeof(int);
+        IAS_TRY(opt_in_smem(k, sm));
+        IAS_LAUNCH(k, n, 1024, sm, bl.rows_of(BIN_B2), n, r0, A, B, rw.nnz_row.p);
+    }
+    if (bl.count[BIN_G]) {
+        int n = (int)bl.count[BIN_G];
+        IAS_TRY(ensure_gwork(rw, ncols_b, n));
+        IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
+        IAS_LAUNCH((k_sym_global<AV, BV, G_BLOCK>), rw.gslots, G_BLOCK, 0, bl.rows_of(BIN_G), n, r0, A, B, rw.nnz_row.p, rw.gwork.p,
+                   GLayout::make(ncols_b), rw.cursor.p);
+    }
+    if (st) {
+        st->products = rw.products;
+        for (int b = 0; b < 8; ++b) st->sym_bin_rows[b] = b < NBINS ? rw.sym_hist[b] : 0;
+    }
+    return IAS_OK;
+}
+
+// numeric bins of local rows [b0, b1) of the range
+template <class AV, class BV>
+int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int ncols_b, const OutMap &out_in,
+                 int *c_ci, double *c_v, IasSpgemmStats *st)
+{
+    Ctx &c = ctx();
+    int n = b1 - b0;
+    if (n <= 0) return IAS_OK;
+    IAS_CUDA(cudaMemsetAsync(rw.hist.p, 0, 16 * sizeof(unsigned long long), c.stream));
+    IAS_LAUNCH(k_classify_num, grid_for(n, 256), 256, 0, n, rw.ub.p + b0, rw.nnz_row.p + b0, rw.bin.p + b0, rw.hist.p);
+    long long h[NBINS + 2];
+    IAS_TRY(read_hist(rw, NBINS + 2, h));
+    for (int b = 0; b < NBINS; ++b) rw.num_hist[b] += h[b];
+    BinLists bl;
+    IAS_TRY(build_bin_lists(n, rw.bin.p + b0, h, bl));
+    int r0 = rw.r0 + b0;                         // lists hold indices local to [b0, b1)
+    OutMap out = out_in;
+    if (out.rp) out.rp += b0;
+    if (out.nnz_row) out.nnz_row += b0;
+    if (bl.count[BIN_T]) {
+        int m = (int)bl.count[BIN_T];
+        int cap = std::max(1, (int)h[NBINS]);
+        auto k = k_num_tiny<AV, BV, TINY_BLOCK>;
+        size_t sm = (size_t)TINY_BLOCK * cap * (sizeof(double) + sizeof(int));
+        IAS_TRY(opt_in_smem(k, sm));
+        IAS_LAUNCH(k, grid_for(m, TINY_BLOCK), TINY_BLOCK, sm, bl.rows_of(BIN_T), m, r0, A, B, out, c_ci, c_v, cap);
+    }
+    if (bl.count[BIN_W]) {
+        int m = (int)bl.count[BIN_W];
+        auto k = k_num_hash<AV, BV, 32, 256, NUM_W_TSIZE>;
+        size_t sm = (size_t)8 * NUM_W_TSIZE * 12;
+        IAS_TRY(opt_in_smem(k, sm));
+        IAS_LAUNCH(k, grid_for(m, 8), 256, sm, bl.rows_of(BIN_W), m, r0, A, B, out, c_ci, c_v);
+    }
+    if (bl.count[BIN_B1]) {
+        int m = (int)bl.count[BIN_B1];
+        auto k = k_num_hash<AV, BV, 256, 256, NUM_B1_TSIZE>;
+        size_t sm = (size_t)NUM_B1_TSIZE * 12;
+        IAS_TRY(opt_in_smem(k, sm));
+        IAS_LAUNCH(k, m, 256, sm, bl.rows_of(BIN_B1), m, r0, A, B, out, c_ci, c_v);
+    }
+    if (bl.count[BIN_B2]) {
+        int m = (int)bl.count[BIN_B2];
+        auto k = k_num_hash<AV, BV, 1024, 1024, NUM_B2_TSIZE>;
+        size_t sm = (size_t)NUM_B2_TSIZE * 12;
+        IAS_TRY(opt_in_smem(k, sm));
+        IAS_LAUNCH(k, m, 1024, sm, bl.rows_of(BIN_B2), m, r0, A, B, out, c_ci, c_v);
+    }
+    if (bl.count[BIN_G]) {
+        int m = (int)bl.count[BIN_G];
+        IAS_TRY(ensure_gwork(rw, ncols_b, m));
+        IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
+        IAS_LAUNCH((k_num_global<AV, BV, G_BLOCK>), rw.gslots, G_BLOCK, 0, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
+                   GLayout::make(ncols_b), rw.cursor.p);
+    }
+    (void)st;
+    return IAS_OK;
+}
+
+// 64-bit exclusive scan of nnz_row[0..nrows] (nrows+1 items; the last input is 0) -> rp[0..nrows]
+struct CastI64 {
+    __host__ __device__ long long operator()(int x) const { return (long long)x; }
+};
+inline int scan_row_ptr(const int *nnz_row, int nrows, long long *rp)
+{
+    auto in = thrust::make_transform_iterator(nnz_row, CastI64());
+    size_t tb = 0;
+    IAS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, in, rp, nrows + 1, ctx().stream));
+    DBuf<char> tmp;
+    IAS_TRY(tmp.alloc(tb));
+    IAS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, in, rp, nrows + 1, ctx().stream));
+    ctx().launches += 2;
+    return IAS_OK;
+}
+
+inline double ev_ms(int a, int b)
+{
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ctx().ev[a], ctx().ev[b]);
+    return (double)ms;
+}
+
+// rows [r0,r1) of C = A*B as a materialised CSR with 64-bit row pointers and column-sorted rows.
+// Timed region (ev[0]..ev[4]) mirrors CUSPARSE_MUL_CUSPARSE (cusparse:74-93): symbolic pass, allocation
+// of C, numeric pass, sort; operands already resident.
+template <class AV, class BV>
+int spgemm_materialise(const AV &av, const BV &bv, double avg_a_row, int ncols_b, int r0, int r1, IasCsr64Dev *C,
+                       IasSpgemmStats *st)
+{
+    Ctx &c = ctx();
+    long long l0 = c.launches;
+    IasSpgemmStats local;
+    memset(&local, 0, sizeof local);
+    int nrows = r1 - r0;
+    C->row = nrows; C->col = ncols_b; C->nnz = 0;
+    C->row_ptr_dev = nullptr; C->col_ind_dev = nullptr; C->values_dev = nullptr;
+
+    IAS_CUDA(cudaEventRecord(c.ev[0], c.stream));
+    IAS_CUDA(cudaEventRecord(c.ev[1], c.stream));
+    RangeWork rw;
+    IAS_TRY(symbolic_range(av, bv, r0, r1, ncols_b, avg_a_row, rw, &local));
+    IAS_CUDA(cudaEventRecord(c.ev[2], c.stream));
+
+    DBuf<long long> rp;
+    IAS_TRY(rp.alloc((size_t)nrows + 1));
+    IAS_TRY(scan_row_ptr(rw.nnz_row.p, nrows, rp.p));
+    IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 32, rp.p + nrows, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    long long nnz = c.h_scalars[32];
+    DBuf<int> ci;
+    DBuf<double> cv;
+    IAS_TRY(ci.alloc((size_t)nnz));
+    IAS_TRY(cv.alloc((size_t)nnz));
+    IAS_CUDA(cudaEventRecord(c.ev[3], c.stream));
+
+    OutMap out{rp.p, 0, nullptr, 0};
+    IAS_TRY(numeric_rows(av, bv, rw, 0, nrows, ncols_b, out, ci.p, cv.p, &local));
+    IAS_CUDA(cudaEventRecord(c.ev[4], c.stream));
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+
+    C->nnz = nnz;
+    C->row_ptr_dev = rp.release(); C->col_ind_dev = ci.release(); C->values_dev = cv.release();
+    local.nnz = nnz;
+    local.batches = 1;
+    local.ms_analyze = ev_ms(0, 1); local.ms_symbolic = ev_ms(1, 2); local.ms_scan = ev_ms(2, 3);
+    local.ms_numeric = ev_ms(3, 4); local.ms_total = ev_ms(0, 4);
+    for (int b = 0; b < 8; ++b) local.num_bin_rows[b] = b < NBINS ? rw.num_hist[b] : 0;
+    local.kernel_launches = (int)(c.launches - l0);
+    if (st) *st = local;
+    return IAS_OK;
+}
+
+}  // namespace ias

@@ -1,0 +1,635 @@
+// spgemm_kernels.cuh -- device side of the Gustavson pipeline (shared by the CSR, ELL and COO entry points).
+//
+// Replaces: CSR_MUL_CSR (CPU/detail/csr/common_csr.h:85-193), the thrust ESC chain of
+// CSR_MUL_CSR_DEV (GPU/detail/csr_dev/common_csr_dev.h:134-254), cusp::multiply (GPU/main.cu:482),
+// cusparseXcsrgemmNnz + cusparseDcsrgemm (GPU/detail/cusparse/common_cusparse.h:78-91) and the
+// Gustavson loops of ELL_MUL_ELL / COO_MUL_COO (ell:80-189, coo:72-161).
+//
+// Pipeline (one row range [r0, r1) of C at a time):
+//   analyze   k_row_ub_*      ub[i] = sum of B row lengths over A(i,:) (= the row's share of GetFlop),
+//                             symbolic bin of the row, histogram of bins, total products
+//   symbolic  k_sym_tiny      ub <= 32       one thread per row, private list in shared memory
+//             k_sym_hash      ub <= 24576    warp / CTA per row, shared-memory hash of column keys
+//             k_sym_global    larger         persistent CTA per row, column bitmap in global memory (L2)
+//   scan      cub ExclusiveSum over nnz(C_i) -> 64-bit row pointers
+//   numeric   k_num_tiny      ub <= 32       one thread per row, sorted private list, coalesced copy-out
+//             k_num_hash      nnz <= 12288   warp / CTA per row, shared-memory hash SPA (key,value),
+//                                            in-place compaction + bitonic sort -> column-sorted row
+//             k_num_global    larger         bitmap + rank: mark columns, prefix-popcount, emit sorted
+//                                            columns, accumulate values with RED.F64 at the ranked slot
+// No intermediate product is ever materialised in global memory (the reference's ESC chain writes
+// 24 B per product, csr_dev:170,190-194).
+#pragma once
+#include <cub/cub.cuh>
+
+#include "common.cuh"
+
+namespace ias {
+
+enum { BIN_EMPTY = 0, BIN_T = 1, BIN_W = 2, BIN_B1 = 3, BIN_B2 = 4, BIN_G = 5, NBINS = 6 };
+
+// symbolic bins by upper bound (hash tables hold <= 50 % load)
+constexpr int T_MAX = 32;
+constexpr int SYM_W_UB = 512, SYM_W_TSIZE = 1024;
+constexpr int SYM_B1_UB = 4096, SYM_B1_TSIZE = 8192;
+constexpr int SYM_B2_UB = 24576, SYM_B2_TSIZE = 49152;
+// numeric bins by exact nnz(C_i)
+constexpr int NUM_W_NNZ = 512, NUM_W_TSIZE = 1024;
+constexpr int NUM_B1_NNZ = 4096, NUM_B1_TSIZE = 8192;
+constexpr int NUM_B2_NNZ = 12288, NUM_B2_TSIZE = 16384;
+
+__host__ __device__ __forceinline__ int sym_bin_of(long long ub)
+{
+    if (ub == 0) return BIN_EMPTY;
+    if (ub <= T_MAX) return BIN_T;
+    if (ub <= SYM_W_UB) return BIN_W;
+    if (ub <= SYM_B1_UB) return BIN_B1;
+    if (ub <= SYM_B2_UB) return BIN_B2;
+    return BIN_G;
+}
+__host__ __device__ __forceinline__ int num_bin_of(int ub, int nnz)
+{
+    if (nnz == 0) return BIN_EMPTY;
+    if (ub <= T_MAX) return BIN_T;
+    if (nnz <= NUM_W_NNZ) return BIN_W;
+    if (nnz <= NUM_B1_NNZ) return BIN_B1;
+    if (nnz <= NUM_B2_NNZ) return BIN_B2;
+    return BIN_G;
+}
+
+// ---------------------------------------------------------------- operand views
+struct CsrView {                       // CsrMatrixDev, GPU/detail/format.h:59-69
+    const int *rp; const int *ci; const double *v;
+    typedef int off_t;
+    __device__ __forceinline__ off_t begin(int i) const { return __ldg(rp + i); }
+    __device__ __forceinline__ off_t end(int i) const { return __ldg(rp + i + 1); }
+    __device__ __forceinline__ int len(int i) const { return __ldg(rp + i + 1) - __ldg(rp + i); }
+};
+struct Csr64View {                     // CSR with 64-bit row offsets (IasCooDev::row_offset_dev)
+    const long long *rp; const int *ci; const double *v;
+    typedef long long off_t;
+    __device__ __forceinline__ off_t begin(int i) const { return __ldg(rp + i); }
+    __device__ __forceinline__ off_t end(int i) const { return __ldg(rp + i + 1); }
+    __device__ __forceinline__ int len(int i) const { return (int)(__ldg(rp + i + 1) - __ldg(rp + i)); }
+};
+struct EllView {                       // EllMatrixDev, GPU/detail/format.h:108-119 (row-major, fixed width)
+    const int *nr; const int *ci; const double *v; int w;
+    typedef long long off_t;
+    __device__ __forceinline__ off_t begin(int i) const { return (long long)i * w; }
+    __device__ __forceinline__ off_t end(int i) const { return (long long)i * w + __ldg(nr + i); }
+    __device__ __forceinline__ int len(int i) const { return __ldg(nr + i); }
+};
+
+// where row li of the current range goes in the output arrays
+struct OutMap {
+    const long long *rp;     // CSR: 64-bit row pointers of the range (rp[li] - rp0 = start)
+    long long rp0;
+    const int *nnz_row;      // ELL: per-row counts, start = li * stride
+    long long stride;
+    __device__ __forceinline__ long long start(int li) const { return rp ? rp[li] - rp0 : (long long)li * stride; }
+    __device__ __forceinline__ int count(int li) const { return rp ? (int)(rp[li + 1] - rp[li]) : nnz_row[li]; }
+};
+
+// ---------------------------------------------------------------- analyze
+// one thread per row (short A rows)
+template <class AV, class BV>
+__global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, BV B, int *__restrict__ ub_out,
+                                                       unsigned char *__restrict__ bin_out,
+                                                       unsigned long long *__restrict__ g_hist /*NBINS + 1*/)
+{
+    __shared__ unsigned long long s_hist[NBINS + 1];
+    if (threadIdx.x <= NBINS) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    int li = blockIdx.x * blockDim.x + threadIdx.x;
+    long long ub = 0;
+    int bin = -1;
+    if (li < nrows) {
+        int i = r0 + li;
+        typename AV::off_t pe = A.end(i);
+        for (typename AV::off_t p = A.begin(i); p < pe; ++p) ub += B.len(__ldg(A.ci + p));
+        bin = sym_bin_of(ub);
+        ub_out[li] = ub > 0x7fffffffLL ? 0x7fffffff : (int)ub;
+        bin_out[li] = (unsigned char)bin;
+    }
+    long long wsum = warp_sum(ub);
+    if ((threadIdx.x & 31) == 0 && wsum) atomicAdd(&s_hist[NBINS], (unsigned long long)wsum);
+    if (bin >= 0) atomicAdd(&s_hist[bin], 1ull);
+    __syncthreads();
+    if (threadIdx.x <= NBINS && s_hist[threadIdx.x]) atomicAdd(&g_hist[threadIdx.x], s_hist[threadIdx.x]);
+}
+
+// one warp per row (long / skewed A rows)
+template <class AV, class BV>
+__global__ void __launch_bounds__(256) k_row_ub_warp(int nrows, int r0, AV A, BV B, int *__restrict__ ub_out,
+                                                     unsigned char *__restrict__ bin_out,
+                                                     unsigned long long *__restrict__ g_hist)
+{
+    __shared__ unsigned long long s_hist[NBINS + 1];
+    if (threadIdx.x <= NBINS) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31;
+    int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (li < nrows) {
+        int i = r0 + li;
+        long long ub = 0;
+        typename AV::off_t pe = A.end(i);
+        for (typename AV::off_t p = A.begin(i) + lane; p < pe; p += 32) ub += B.len(__ldg(A.ci + p));
+        ub = warp_sum(ub);
+        if (lane == 0) {
+            int bin = sym_bin_of(ub);
+            ub_out[li] = ub > 0x7fffffffLL ? 0x7fffffff : (int)ub;
+            bin_out[li] = (unsigned char)bin;
+            atomicAdd(&s_hist[bin], 1ull);
+            if (ub) atomicAdd(&s_hist[NBINS], (unsigned long long)ub);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x <= NBINS && s_hist[threadIdx.x]) atomicAdd(&g_hist[threadIdx.x], s_hist[threadIdx.x]);
+}
+
+// numeric bins from exact counts; also the largest nnz(C_i) among tiny rows (sizes k_num_tiny's smem)
+static __global__ void __launch_bounds__(256) k_classify_num(int nrows, const int *__restrict__ ub, const int *__restrict__ nnz_row,
+                                                      unsigned char *__restrict__ bin_out,
+                                                      unsigned long long *__restrict__ g_hist /*NBINS+2: [NBINS]=max tiny nnz, [NBINS+1]=max nnz*/)
+{
+    __shared__ unsigned long long s_hist[NBINS + 2];
+    if (threadIdx.x < NBINS + 2) s_hist[threadIdx.x] = 0;
+    __syncthreads();
+    int li = blockIdx.x * blockDim.x + threadIdx.x;
+    if (li < nrows) {
+        int n = nnz_row[li], u = ub[li];
+        int bin = num_bin_of(u, n);
+        bin_out[li] = (unsigned char)bin;
+        atomicAdd(&s_hist[bin], 1ull);
+        if (bin == BIN_T) atomicMax(&s_hist[NBINS], (unsigned long long)n);
+        atomicMax(&s_hist[NBINS + 1], (unsigned long long)n);
+    }
+    __syncthreads();
+    if (threadIdx.x < NBINS && s_hist[threadIdx.x]) atomicAdd(&g_hist[threadIdx.x], s_hist[threadIdx.x]);
+    if (threadIdx.x >= NBINS && threadIdx.x < NBINS + 2) atomicMax(&g_hist[threadIdx.x], s_hist[threadIdx.x]);
+}
+
+static __global__ void k_iota(int n, int *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+
+// ---------------------------------------------------------------- tiny rows: one thread per row
+template <class AV, class BV, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_sym_tiny(const int *__restrict__ rows, int nrows, int r0, AV A, BV B,
+                                                    int *__restrict__ nnz_row)
+{
+    __shared__ int list[T_MAX * BLOCK];          // [slot][thread]: conflict free
+    int idx = blockIdx.x * BLOCK + threadIdx.x;
+    if (idx >= nrows) return;
+    int li = rows ? rows[idx] : idx;
+    int i = r0 + li;
+    int *mine = list + threadIdx.x;
+    int cnt = 0;
+    typename AV::off_t pe = A.end(i);
+    for (typename AV::off_t p = A.begin(i); p < pe; ++p) {
+        int j = __ldg(A.ci + p);
+        typename BV::off_t qe = B.end(j);
+        for (typename BV::off_t q = B.begin(j); q < qe; ++q) {
+            int k = __ldg(B.ci + q);
+            int s = 0;
+            for (; s < cnt; ++s)
+                if (mine[s * BLOCK] == k) break;
+            if (s == cnt) { mine[cnt * BLOCK] = k; ++cnt; }
+        }
+    }
+    nnz_row[li] = cnt;
+}
+
+template <class AV, class BV, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_num_tiny(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
+                                                    int *__restrict__ c_ci, double *__restrict__ c_v, int cap)
+{
+    extern __shared__ unsigned char smem_raw[];
+    double *vals = reinterpret_cast<double *>(smem_raw);      // every thread owns exactly nnz(C_i) slots
+    int *cols = reinterpret_cast<int *>(vals + (size_t)BLOCK * cap);
+    typedef cub::BlockScan<int, BLOCK> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+
+    int idx = blockIdx.x * BLOCK + threadIdx.x;
+    int li = -1, n = 0;
+    long long gstart = 0;
+    if (idx < nrows) {
+        li = rows ? rows[idx] : idx;
+        n = out.count(li);
+        gstart = out.start(li);
+    }
+    int off, total;
+    Scan(scan_tmp).ExclusiveSum(n, off, total);
+    if (n > 0) {
+        int i = r0 + li;
+        int *mc = cols + off;
+        double *mv = vals + off;
+        int cnt = 0;
+        typename AV::off_t pe = A.end(i);
+        for (typename AV::off_t p = A.begin(i); p < pe; ++p) {
+            int j = __ldg(A.ci + p);
+            double av = __ldg(A.v + p);
+            typename BV::off_t qe = B.end(j);
+            for (typename BV::off_t q = B.begin(j); q < qe; ++q) {
+                int k = __ldg(B.ci + q);
+                double x = av * __ldg(B.v + q);
+                int s = 0;
+                for (; s < cnt; ++s)
+                    if (mc[s] == k) break;
+                if (s < cnt) mv[s] += x;
+                else if (cnt < n) { mc[cnt] = k; mv[cnt] = x; ++cnt; }
+            }
+        }
+        for (int a = 1; a < cnt; ++a) {                       // insertion sort by column
+            int kk = mc[a];
+            double vv = mv[a];
+            int b = a - 1;
+            while (b >= 0 && mc[b] > kk) { mc[b + 1] = mc[b]; mv[b + 1] = mv[b]; --b; }
+            mc[b + 1] = kk; mv[b + 1] = vv;
+        }
+    }
+    __syncthreads();
+    if (rows == nullptr && out.rp != nullptr) {
+        // identity row list: the CTA's rows are consecutive, so its output is one contiguous span
+        long long base = out.start(blockIdx.x * BLOCK);
+        for (int e = threadIdx.x; e < total; e += BLOCK) { c_ci[base + e] = cols[e]; c_v[base + e] = vals[e]; }
+    } else {
+        int lane = threadIdx.x & 31;
+        for (int r = 0; r < 32; ++r) {
+            int rn = __shfl_sync(0xffffffffu, n, r);
+            int ro = __shfl_sync(0xffffffffu, off, r);
+            long long rg = __shfl_sync(0xffffffffu, gstart, r);
+            if (lane < rn) { c_ci[rg + lane] = cols[ro + lane]; c_v[rg + lane] = vals[ro + lane]; }
+        }
+    }
+}
+
+// ---------------------------------------------------------------- hash rows: warp (TPR=32) or CTA (TPR=BLOCK) per row
+template <int TPR>
+__device__ __forceinline__ void group_sync()
+{
+    if (TPR == 32) __syncwarp(); else __syncthreads();
+}
+
+template <class AV, class BV, int TPR, int BLOCK, int TSIZE>
+__global__ void __launch_bounds__(BLOCK) k_sym_hash(const int *__restrict__ rows, int nrows, int r0, AV A, BV B,
+                                                    int *__restrict__ nnz_row)
+{
+    extern __shared__ unsigned char smem_raw[];
+    constexpr int NW = TPR / 32;
+    __shared__ int s_cnt;
+    int g = threadIdx.x / TPR, t = threadIdx.x % TPR, w = t >> 5, lane = t & 31;
+    int idx = blockIdx.x * (BLOCK / TPR) + g;
+    if (idx >= nrows) return;                       // whole group leaves together
+    int *keys = reinterpret_cast<int *>(smem_raw) + (size_t)g * TSIZE;
+    for (int s = t; s < TSIZE; s += TPR) keys[s] = -1;
+    if (TPR > 32 && threadIdx.x == 0) s_cnt = 0;
+    group_sync<TPR>();
+    int li = rows ? rows[idx] : idx;
+    int i = r0 + li;
+    int cnt = 0;
+    typename AV::off_t pe = A.end(i);
+    for (typename AV::off_t p = A.begin(i) + w; p < pe; p += NW) {
+        int j = __ldg(A.ci + p);
+        typename BV::off_t qe = B.end(j);
+        for (typename BV::off_t q = B.begin(j) + lane; q < qe; q += 32) {
+            int k = __ldg(B.ci + q);
+            unsigned s = __umulhi(hash_col(k), (unsigned)TSIZE);
+            while (true) {
+                int cur = keys[s];
+                if (cur == k) break;
+                if (cur == -1) {
+                    int old = atomicCAS(&keys[s], -1, k);
+                    if (old == -1) { ++cnt; break; }
+                    if (old == k) break;
+                }
+                s = (s + 1 == TSIZE) ? 0 : s + 1;
+            }
+        }
+    }
+    cnt = warp_sum(cnt);
+    if (TPR == 32) {
+        if (lane == 0) nnz_row[li] = cnt;
+    } else {
+        if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+        __syncthreads();
+        if (threadIdx.x == 0) nnz_row[li] = s_cnt;
+    }
+}
+
+template <class AV, class BV, int TPR, int BLOCK, int TSIZE>
+__global__ void __launch_bounds__(BLOCK) k_num_hash(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
+                                                    int *__restrict__ c_ci, double *__restrict__ c_v)
+{
+    extern __shared__ unsigned char smem_raw[];
+    constexpr int NW = TPR / 32;
+    constexpr int GROUPS = BLOCK / TPR;
+    __shared__ int s_wcount[NW > 1 ? NW : 1];
+    int g = threadIdx.x / TPR, t = threadIdx.x % TPR, w = t >> 5, lane = t & 31;
+    int idx = blockIdx.x * GROUPS + g;
+    if (idx >= nrows) return;
+    double *vals = reinterpret_cast<double *>(smem_raw) + (size_t)g * TSIZE;
+    int *keys = reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + (size_t)GROUPS * TSIZE) + (size_t)g * TSIZE;
+    for (int s = t; s < TSIZE; s += TPR) { keys[s] = -1; vals[s] = 0.0; }
+    group_sync<TPR>();
+    int li = rows ? rows[idx] : idx;
+    int i = r0 + li;
+    typename AV::off_t pe = A.end(i);
+    for (typename AV::off_t p = A.begin(i) + w; p < pe; p += NW) {
+        int j = __ldg(A.ci + p);
+        double av = __ldg(A.v + p);
+        typename BV::off_t qe = B.end(j);
+        for (typename BV::off_t q = B.begin(j) + lane; q < qe; q += 32) {
+            int k = __ldg(B.ci + q);
+            double x = av * __ldg(B.v + q);
+            unsigned s = __umulhi(hash_col(k), (unsigned)TSIZE);
+            while (true) {
+                int cur = keys[s];
+                if (cur == k) break;
+                if (cur == -1) {
+                    int old = atomicCAS(&keys[s], -1, k);
+                    if (old == -1 || old == k) break;
+                }
+                s = (s + 1 == TSIZE) ? 0 : s + 1;
+            }
+            atomicAdd(&vals[s], x);
+        }
+    }
+    group_sync<TPR>();
+
+    // in-place compaction: occupied slots move to the front (write index never passes read index)
+    int n_out = 0;
+    for (int base = 0; base < TSIZE; base += TPR) {
+        int k = keys[base + t];
+        double x = vals[base + t];
+        bool valid = (k != -1);
+        unsigned m = __ballot_sync(0xffffffffu, valid);
+        int wpre = 0, chunk = __popc(m);
+        if (NW > 1) {
+            if (lane == 0) s_wcount[w] = chunk;
+            __syncthreads();
+            chunk = 0;
+            for (int u = 0; u < NW; ++u) { int c = s_wcount[u]; if (u < w) wpre += c; chunk += c; }
+        } else {
+            __syncwarp();
+        }
+        int pos = n_out + wpre + __popc(m & ((1u << lane) - 1u));
+        if (valid) { keys[pos] = k; vals[pos] = x; }
+        n_out += chunk;
+        group_sync<TPR>();
+    }
+    // bitonic sort of the first P2 >= n_out entries by column (padding keys sort last)
+    int p2 = 1;
+    while (p2 < n_out) p2 <<= 1;
+    for (int s = n_out + t; s < p2; s += TPR) keys[s] = 0x7fffffff;
+    group_sync<TPR>();
+    for (int kk = 2; kk <= p2; kk <<= 1) {
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+            for (int e = t; e < (p2 >> 1); e += TPR) {
+                int a = ((e & ~(jj - 1)) << 1) | (e & (jj - 1));
+                int b = a | jj;
+                int ka = keys[a], kb = keys[b];
+                bool up = ((a & kk) == 0);
+                if ((ka > kb) == up) {
+                    keys[a] = kb; keys[b] = ka;
+                    double va = vals[a], vb = vals[b];
+                    vals[a] = vb; vals[b] = va;
+                }
+            }
+            group_sync<TPR>();
+        }
+    }
+    long long gs = out.start(li);
+    for (int e = t; e < n_out; e += TPR) { c_ci[gs + e] = keys[e]; c_v[gs + e] = vals[e]; }
+}
+
+// ---------------------------------------------------------------- global rows: bitmap + rank in L2
+// Workspace of one slot (all 32-bit words, zero between rows except prefix/blkpref):
+//   bm[words]       column bitmap                      words   = ceil(ncols/32) rounded up to 32
+//   prefix[words]   output rank of each word's first bit
+//   summary[sumw]   one bit per block of 32 bitmap words (= 1024 columns)
+//   blkpref[blocks] output rank of each block           blocks = words/32, sumw = ceil(blocks/32)
+struct GLayout {
+    int words, blocks, sumw;
+    size_t slot_words;          // words + words + sumw + blocks
+    __host__ __device__ static GLayout make(int ncols)
+    {
+        GLayout g;
+        long long w = ((long long)ncols + 31) / 32;
+        w = (w + 31) / 32 * 32;
+        g.words = (int)w; g.blocks = g.words / 32; g.sumw = (g.blocks + 31) / 32;
+        g.slot_words = ((size_t)g.words * 2 + g.sumw + g.blocks + 31) / 32 * 32;   // keeps every slot 128-byte aligned
+        return g;
+    }
+};
+
+__device__ __forceinline__ void g_mark(unsigned *bm, unsigned *summary, int k, int &cnt)
+{
+    int w = k >> 5;
+    unsigned bit = 1u << (k & 31);
+    unsigned cur = __ldcg(bm + w);
+    if (!(cur & bit)) {
+        unsigned old = atomicOr(bm + w, bit);
+        if (!(old & bit)) {
+            ++cnt;
+            if (old == 0) atomicOr(summary + (w >> 10), 1u << ((w >> 5) & 31));
+        }
+    }
+}
+
+template <int BLOCK>
+__device__ __forceinline__ void g_clear(unsigned *bm, unsigned *summary, const GLayout &L)
+{
+    for (int sw = threadIdx.x; sw < L.sumw; sw += BLOCK) {
+        unsigned m = __ldcg(summary + sw);
+        if (!m) continue;
+        summary[sw] = 0;
+        while (m) {
+            int b = __ffs(m) - 1;
+            m &= m - 1;
+            uint4 *p = reinterpret_cast<uint4 *>(bm + ((size_t)sw * 32 + b) * 32);
+#pragma unroll
+            for (int x = 0; x < 8; ++x) p[x] = make_uint4(0, 0, 0, 0);
+        }
+    }
+}
+
+template <class AV, class BV, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_sym_global(const int *__restrict__ rows, int nrows, int r0, AV A, BV B,
+                                                      int *__restrict__ nnz_row, unsigned *__restrict__ work, GLayout L,
+                                                      int *__restrict__ cursor)
+{
+    constexpr int NW = BLOCK / 32;
+    __shared__ int s_row, s_cnt;
+    unsigned *bm = work + (size_t)blockIdx.x * L.slot_words;
+    unsigned *summary = bm + (size_t)L.words * 2;
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    while (true) {
+        if (threadIdx.x == 0) { s_row = atomicAdd(cursor, 1); s_cnt = 0; }
+        __syncthreads();
+        int idx = s_row;
+        if (idx >= nrows) break;
+        int li = rows ? rows[idx] : idx;
+        int i = r0 + li;
+        int cnt = 0;
+        typename AV::off_t pe = A.end(i);
+        for (typename AV::off_t p = A.begin(i) + w; p < pe; p += NW) {
+            int j = __ldg(A.ci + p);
+            typename BV::off_t qe = B.end(j);
+            for (typename BV::off_t q = B.begin(j) + lane; q < qe; q += 32) g_mark(bm, summary, __ldg(B.ci + q), cnt);
+        }
+        cnt = warp_sum(cnt);
+        if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+        __syncthreads();
+        if (threadIdx.x == 0) nnz_row[li] = s_cnt;
+        g_clear<BLOCK>(bm, summary, L);
+        __syncthreads();
+    }
+}
+
+template <class AV, class BV, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
+                                                      int *__restrict__ c_ci, double *__restrict__ c_v,
+                                                      unsigned *__restrict__ work, GLayout L, int *__restrict__ cursor)
+{
+    constexpr int NW = BLOCK / 32;
+    typedef cub::BlockScan<unsigned, BLOCK> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    __shared__ int s_row;
+    unsigned *bm = work + (size_t)blockIdx.x * L.slot_words;
+    unsigned *prefix = bm + L.words;
+    unsigned *summary = prefix + L.words;
+    unsigned *blkpref = summary + L.sumw;
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    while (true) {
+        if (threadIdx.x == 0) s_row = atomicAdd(cursor, 1);
+        __syncthreads();
+        int idx = s_row;
+        if (idx >= nrows) break;
+        int li = rows ? rows[idx] : idx;
+        int i = r0 + li;
+        long long gs = out.start(li);
+        typename AV::off_t pa = A.begin(i), pe = A.end(i);
+        // 1. mark the columns of the row
+        int dummy = 0;
+        for (typename AV::off_t p = pa + w; p < pe; p += NW) {
+            int j = __ldg(A.ci + p);
+            typename BV::off_t qe = B.end(j);
+            for (typename BV::off_t q = B.begin(j) + lane; q < qe; q += 32) g_mark(bm, summary, __ldg(B.ci + q), dummy);
+        }
+        __syncthreads();
+        // 2a. population of every 1024-column block, exclusive scan over blocks
+        int per = (L.blocks + BLOCK - 1) / BLOCK;
+        int b0 = threadIdx.x * per, b1 = min(b0 + per, L.blocks);
+        unsigned local = 0;
+        for (int b = b0; b < b1; ++b) {
+            unsigned c = 0;
+            if ((__ldcg(summary + (b >> 5)) >> (b & 31)) & 1u) {
+                const uint4 *p4 = reinterpret_cast<const uint4 *>(bm + (size_t)b * 32);
+#pragma unroll
+                for (int x = 0; x < 8; ++x) { uint4 u = __ldcg(p4 + x); c += __popc(u.x) + __popc(u.y) + __popc(u.z) + __popc(u.w); }
+            }
+            blkpref[b] = c;
+            local += c;
+        }
+        unsigned tbase;
+        Scan(scan_tmp).ExclusiveSum(local, tbase);
+        for (int b = b0; b < b1; ++b) { unsigned c = blkpref[b]; blkpref[b] = tbase; tbase += c; }
+        __syncthreads();
+        // 2b. per-word ranks; emit the sorted column list and zero the value slots
+        for (int b = w; b < L.blocks; b += NW) {
+            if (!((__ldcg(summary + (b >> 5)) >> (b & 31)) & 1u)) continue;
+            int wi = b * 32 + lane;
+            unsigned word = __ldcg(bm + wi);
+            unsigned c = __popc(word), incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+            unsigned rank = __ldcg(blkpref + b) + incl - c;
+            prefix[wi] = rank;
+            while (word) {
+                int bit = __ffs(word) - 1;
+                word &= word - 1;
+                c_ci[gs + rank] = wi * 32 + bit;
+                c_v[gs + rank] = 0.0;
+                ++rank;
+            }
+        }
+        __threadfence();         // the zeroed value slots must be in L2 before any RED lands on them
+        __syncthreads();
+        // 3. accumulate every product at the rank of its column
+        for (typename AV::off_t p = pa + w; p < pe; p += NW) {
+            int j = __ldg(A.ci + p);
+            double av = __ldg(A.v + p);
+            typename BV::off_t qe = B.end(j);
+            for (typename BV::off_t q = B.begin(j) + lane; q < qe; q += 32) {
+                int k = __ldg(B.ci + q);
+                double x = av * __ldg(B.v + q);
+                int wi = k >> 5;
+                unsigned below = __ldcg(bm + wi) & ((1u << (k & 31)) - 1u);
+                atomicAdd(c_v + gs + __ldcg(prefix + wi) + __popc(below), x);
+            }
+        }
+        __syncthreads();
+        // 4. leave the slot clean for the next row
+        g_clear<BLOCK>(bm, summary, L);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- consumers / small utilities
+// order-independent structure hash + checksum of a batch of C: sum over entries of mix64(row<<32 | col)
+static __global__ void __launch_bounds__(256) k_consume(int nrows, int row_base, const long long *__restrict__ rp, long long rp0,
+                                                 const int *__restrict__ ci, const double *__restrict__ v,
+                                                 unsigned long long *__restrict__ hash_out, double *__restrict__ sum_out)
+{
+    constexpr int PER = 16;
+    long long n = rp[nrows] - rp0;
+    long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PER;
+    unsigned long long h = 0;
+    double s = 0.0;
+    if (e0 < n) {
+        long long e1 = min(e0 + PER, n);
+        int lo = 0, hi = nrows;                 // last row with rp[row]-rp0 <= e0
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (rp[mid] - rp0 <= e0) lo = mid; else hi = mid; }
+        int row = lo;
+        for (long long e = e0; e < e1; ++e) {
+            while (rp[row + 1] - rp0 <= e) ++row;
+            h += mix64(((unsigned long long)(unsigned)(row_base + row) << 32) | (unsigned)ci[e]);
+            s += v[e];
+        }
+    }
+    typedef cub::BlockReduce<unsigned long long, 256> RH;
+    typedef cub::BlockReduce<double, 256> RS;
+    __shared__ typename RH::TempStorage th;
+    __shared__ typename RS::TempStorage tsm;
+    h = RH(th).Sum(h);
+    s = RS(tsm).Sum(s);
+    if (threadIdx.x == 0) { if (h) atomicAdd(hash_out, h); atomicAdd(sum_out, s); }
+}
+
+static __global__ void k_copy_counts(int n, const int *__restrict__ src, int *__restrict__ dst)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) dst[i] = src[i];
+}
+
+// greedy batch boundaries: largest row ranges whose nnz fits `cap` entries
+static __global__ void k_batch_bounds(int nrows, const long long *__restrict__ rp, long long cap, int max_batches,
+                               int *__restrict__ bounds /*max_batches+1*/, int *__restrict__ nb)
+{
+    if (threadIdx.x || blockIdx.x) return;
+    int b = 0, start = 0;
+    bounds[0] = 0;
+    while (start < nrows && b < max_batches) {
+        long long limit = rp[start] + cap;
+        int lo = start + 1, hi = nrows;          // at least one row per batch
+        while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (rp[mid] <= limit) lo = mid; else hi = mid - 1; }
+        start = lo;
+        bounds[++b] = start;
+    }
+    *nb = (start >= nrows) ? b : -1;
+}
+
+}  // namespace ias

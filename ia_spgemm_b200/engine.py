@@ -1,0 +1,442 @@
+"""Host-side mirror of the reference's operator interface, over the C ABI (include/iaspgemm.h).
+
+The reference exposes free functions on POD structs (`CSR_MUL_CSR(A, B, C)`, `CSRtoDIA`,
+`GetInfo1`, `GetFlop`, ... -- SURVEY.md section 8b); this module offers the same names on NumPy
+operands for the test-suite and bench harness.  Everything here calls libiaspgemm.so through
+ctypes: there is no CPU fallback, and import fails loudly if the library is missing.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libiaspgemm.so")
+
+_I = C.POINTER(C.c_int)
+_L = C.POINTER(C.c_longlong)
+_D = C.POINTER(C.c_double)
+
+
+class CsrMatrix(C.Structure):          # IasCsrMatrix == CsrMatrix (GPU/detail/format.h:47-57)
+    _fields_ = [("choice", C.c_bool), ("row", C.c_int), ("col", C.c_int), ("nnz", C.c_int),
+                ("row_ind", _I), ("col_ind", _I), ("values", _D)]
+
+
+class CsrMatrixDev(C.Structure):       # IasCsrMatrixDev == CsrMatrixDev (format.h:59-69)
+    _fields_ = [("choice", C.c_bool), ("row", C.c_int), ("col", C.c_int), ("nnz", C.c_int),
+                ("row_ind_dev", C.c_void_p), ("col_ind_dev", C.c_void_p), ("values_dev", C.c_void_p)]
+
+
+class Csr64Dev(C.Structure):
+    _fields_ = [("row", C.c_int), ("col", C.c_int), ("nnz", C.c_longlong),
+                ("row_ptr_dev", C.c_void_p), ("col_ind_dev", C.c_void_p), ("values_dev", C.c_void_p)]
+
+
+class CooDev(C.Structure):
+    _fields_ = [("choice", C.c_bool), ("row", C.c_int), ("col", C.c_int), ("nnz", C.c_longlong),
+                ("row_offset_dev", C.c_void_p), ("row_ind_dev", C.c_void_p), ("col_ind_dev", C.c_void_p),
+                ("values_dev", C.c_void_p)]
+
+
+class DiaDev(C.Structure):
+    _fields_ = [("choice", C.c_bool), ("row", C.c_int), ("col", C.c_int), ("num_diagonals", C.c_int),
+                ("diagonal_ind_dev", C.c_void_p), ("diagonal_offsets_dev", C.c_void_p), ("values_dev", C.c_void_p)]
+
+
+class EllDev(C.Structure):
+    _fields_ = [("choice", C.c_bool), ("row", C.c_int), ("col", C.c_int), ("nnz", C.c_longlong),
+                ("max_nnz_per_row", C.c_int),
+                ("nnz_row_dev", C.c_void_p), ("col_ind_dev", C.c_void_p), ("values_dev", C.c_void_p)]
+
+
+class SpgemmStats(C.Structure):
+    _fields_ = [("products", C.c_longlong), ("nnz", C.c_longlong), ("ms_total", C.c_double),
+                ("ms_analyze", C.c_double), ("ms_symbolic", C.c_double), ("ms_scan", C.c_double),
+                ("ms_numeric", C.c_double), ("ms_consume", C.c_double),
+                ("sym_bin_rows", C.c_longlong * 8), ("num_bin_rows", C.c_longlong * 8),
+                ("batches", C.c_int), ("kernel_launches", C.c_int), ("checksum", C.c_double),
+                ("structure_hash", C.c_ulonglong)]
+
+    def as_dict(self):
+        return {"products": self.products, "nnz": self.nnz, "ms_total": self.ms_total,
+                "ms_analyze": self.ms_analyze, "ms_symbolic": self.ms_symbolic, "ms_scan": self.ms_scan,
+                "ms_numeric": self.ms_numeric, "sym_bin_rows": list(self.sym_bin_rows)[:6],
+                "num_bin_rows": list(self.num_bin_rows)[:6], "batches": self.batches,
+                "kernel_launches": self.kernel_launches, "checksum": self.checksum,
+                "structure_hash": self.structure_hash}
+
+
+class EngineError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libiaspgemm status %d: %s" % (code, msg))
+        self.code = code
+
+
+BIN_NAMES = ["empty", "tiny", "warp", "cta_s", "cta_l", "global"]
+
+# every symbol include/iaspgemm.h declares (tests check the library exports all of them)
+ABI_SYMBOLS = [
+    "ias_init", "ias_set_stream", "ias_sync", "ias_last_error", "ias_version", "ias_device_info",
+    "ias_kernel_launches",
+    "ias_upload_csr", "ias_free_csr_dev", "ias_free_csr64_dev", "ias_download_csr64", "ias_download_csr",
+    "ias_csr_is_canonical",
+    "ias_csr_mul_csr_dev64", "ias_csr_mul_csr_dev", "ias_csr_mul_csr_rows_dev64", "ias_csr_mul_csr_stream",
+    "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_partition_rows", "ias_checksum",
+    "ias_structure_hash",
+    "ias_csr_to_dia", "ias_dia_mul_dia_dev", "ias_download_dia", "ias_free_dia_dev",
+    "ias_csr_to_ell", "ias_ell_mul_ell_dev", "ias_download_ell", "ias_free_ell_dev",
+    "ias_csr_to_coo", "ias_coo_mul_coo_dev", "ias_download_coo", "ias_free_coo_dev",
+    "ias_density_image", "ias_getinfo1", "ias_getinfo2", "ias_getinfo3", "ias_count_diagonals",
+    "ias_max_row_nnz", "ias_features26",
+    "ias_sizeof_csr", "ias_sizeof_dia", "ias_sizeof_ell", "ias_sizeof_coo",
+    "ias_mtx_load", "ias_free_host_csr",
+    "ias_gen_poisson2d", "ias_gen_uniform", "ias_gen_rmat",
+]
+
+
+def load_library():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(make -C ia_spgemm_b200/csrc).  The engine has no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    lib.ias_last_error.restype = C.c_char_p
+    lib.ias_version.restype = C.c_char_p
+    lib.ias_kernel_launches.restype = C.c_longlong
+    for n in ("ias_sizeof_csr", "ias_sizeof_dia", "ias_sizeof_ell", "ias_sizeof_coo"):
+        getattr(lib, n).restype = C.c_double
+    sigs = {
+        "ias_sizeof_csr": [C.c_int, C.c_longlong], "ias_sizeof_coo": [C.c_int, C.c_longlong],
+        "ias_sizeof_dia": [C.c_int, C.c_int, C.c_int], "ias_sizeof_ell": [C.c_int, C.c_int],
+        "ias_set_stream": [C.c_void_p], "ias_checksum": [C.c_void_p, C.c_longlong, _D],
+        "ias_csr_mul_csr_stream": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p],
+        "ias_getinfo3": [C.c_int, C.c_longlong, C.c_int, _D],
+        "ias_gen_rmat": [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p],
+        "ias_csr_to_dia": [C.c_void_p, C.c_double, C.c_void_p], "ias_csr_to_ell": [C.c_void_p, C.c_double, C.c_void_p],
+    }
+    for name, args in sigs.items():
+        if hasattr(lib, name):          # a missing export is reported by tests/test_abi.py, not here
+            getattr(lib, name).argtypes = args
+    return lib
+
+
+def _i32(a):
+    return np.ascontiguousarray(a, dtype=np.int32)
+
+
+def _f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+class DeviceCsr:
+    """A CSR operand resident on the GPU (CsrMatrixDev).  Freed on close()/GC."""
+
+    def __init__(self, eng, dev, owned=True):
+        self.eng, self.dev, self.owned = eng, dev, owned
+
+    @property
+    def shape(self):
+        return self.dev.row, self.dev.col
+
+    @property
+    def nnz(self):
+        return self.dev.nnz
+
+    def download(self):
+        d = self.dev
+        rp = np.empty(d.row + 1, np.int32)
+        ci = np.empty(d.nnz, np.int32)
+        v = np.empty(d.nnz, np.float64)
+        self.eng._ck(self.eng.lib.ias_download_csr(C.byref(d), rp.ctypes.data_as(_I), ci.ctypes.data_as(_I), v.ctypes.data_as(_D)))
+        return d.row, d.col, rp, ci, v
+
+    def close(self):
+        if self.owned and self.dev.row_ind_dev:
+            self.eng.lib.ias_free_csr_dev(C.byref(self.dev))
+        self.owned = False
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Engine:
+    def __init__(self, device=0):
+        self.lib = load_library()
+        self._ck(self.lib.ias_init(C.c_int(device)))
+
+    def _ck(self, rc):
+        if rc != 0:
+            raise EngineError(rc, (self.lib.ias_last_error() or b"").decode(errors="replace"))
+
+    # -- context -----------------------------------------------------------------------
+    def set_stream(self, cuda_stream_handle):
+        self._ck(self.lib.ias_set_stream(C.c_void_p(cuda_stream_handle or 0)))
+
+    def sync(self):
+        self._ck(self.lib.ias_sync())
+
+    def kernel_launches(self):
+        return int(self.lib.ias_kernel_launches())
+
+    def device_info(self):
+        sm, smem, fr, tot = C.c_int(), C.c_size_t(), C.c_size_t(), C.c_size_t()
+        self._ck(self.lib.ias_device_info(C.byref(sm), C.byref(smem), C.byref(fr), C.byref(tot)))
+        return {"sm_count": sm.value, "smem_optin": smem.value, "free_bytes": fr.value, "total_bytes": tot.value}
+
+    # -- transfers -----------------------------------------------------------------------
+    @staticmethod
+    def host_csr(rows, cols, rp, ci, v):
+        rp, ci, v = _i32(rp), _i32(ci), _f64(v)
+        h = CsrMatrix(True, rows, cols, int(rp[-1]), rp.ctypes.data_as(_I), ci.ctypes.data_as(_I), v.ctypes.data_as(_D))
+        h._keep = (rp, ci, v)
+        return h
+
+    def upload(self, rows, cols, rp, ci, v):
+        """UploadCsrMatrix (csr_dev:111)."""
+        h = self.host_csr(rows, cols, rp, ci, v)
+        d = CsrMatrixDev()
+        self._ck(self.lib.ias_upload_csr(C.byref(h), C.byref(d)))
+        return DeviceCsr(self, d)
+
+    def wrap_device(self, rows, cols, nnz, rp_ptr, ci_ptr, v_ptr):
+        """Operand living in caller-owned device memory (e.g. torch tensors)."""
+        return DeviceCsr(self, CsrMatrixDev(True, rows, cols, nnz, rp_ptr, ci_ptr, v_ptr), owned=False)
+
+    def is_canonical(self, A):
+        r = C.c_int()
+        self._ck(self.lib.ias_csr_is_canonical(C.byref(A.dev), C.byref(r)))
+        return bool(r.value)
+
+    def _take_csr64(self, c64, download=True):
+        out = None
+        if download:
+            rp = np.empty(c64.row + 1, np.int64)
+            ci = np.empty(c64.nnz, np.int32)
+            v = np.empty(c64.nnz, np.float64)
+            self._ck(self.lib.ias_download_csr64(C.byref(c64), rp.ctypes.data_as(_L), ci.ctypes.data_as(_I), v.ctypes.data_as(_D)))
+            out = (rp, ci, v)
+        self.lib.ias_free_csr64_dev(C.byref(c64))
+        return out
+
+    # -- Algorithm 2 ---------------------------------------------------------------------
+    def CSR_MUL_CSR_DEV(self, A, B, rows=None, download=True, keep=False):
+        """CSR_MUL_CSR_DEV (csr_dev:134): C = A*B on device operands.
+        Returns ((row_ptr int64, col_ind, values) or None, stats dict[, Csr64Dev if keep])."""
+        c64, st = Csr64Dev(), SpgemmStats()
+        if rows is None:
+            self._ck(self.lib.ias_csr_mul_csr_dev64(C.byref(A.dev), C.byref(B.dev), C.byref(c64), C.byref(st)))
+        else:
+            self._ck(self.lib.ias_csr_mul_csr_rows_dev64(C.byref(A.dev), C.byref(B.dev), C.c_int(rows[0]), C.c_int(rows[1]),
+                                                         C.byref(c64), C.byref(st)))
+        if keep:
+            return c64, st.as_dict()
+        return self._take_csr64(c64, download), st.as_dict()
+
+    def free_csr64(self, c64):
+        self.lib.ias_free_csr64_dev(C.byref(c64))
+
+    def csr_mul_csr_dev32(self, A, B):
+        """int32 reference layout (CsrMatrixDev result)."""
+        cdev, ms = CsrMatrixDev(), C.c_double()
+        self._ck(self.lib.ias_csr_mul_csr_dev(C.byref(A.dev), C.byref(B.dev), C.byref(cdev), C.byref(ms)))
+        out = DeviceCsr(self, cdev)
+        res = out.download()
+        out.close()
+        return res[2], res[3], res[4], ms.value
+
+    def CSR_MUL_CSR(self, A, B):
+        """CSR_MUL_CSR(A, B, C) on host operands (CPU/detail/csr/common_csr.h:85) -- the e2e path.
+        A, B = (rows, cols, rp, ci, v).  Returns (rp, ci, v) views of engine-owned pinned memory
+        (valid until the next host call), stats, ms_h2d, ms_d2h."""
+        hA = self.host_csr(*A)
+        hB = hA if B is A else self.host_csr(*B)
+        rp, ci, v = _L(), _I(), _D()
+        nnz, st, h2d, d2h = C.c_longlong(), SpgemmStats(), C.c_double(), C.c_double()
+        self._ck(self.lib.ias_csr_mul_csr_host(C.byref(hA), C.byref(hB), C.byref(rp), C.byref(ci), C.byref(v), C.byref(nnz),
+                                               C.byref(st), C.byref(h2d), C.byref(d2h)))
+        n = nnz.value
+        out = (np.ctypeslib.as_array(rp, shape=(A[0] + 1,)),
+               np.ctypeslib.as_array(ci, shape=(n,)) if n else np.zeros(0, np.int32),
+               np.ctypeslib.as_array(v, shape=(n,)) if n else np.zeros(0, np.float64))
+        return out, st.as_dict(), h2d.value, d2h.value
+
+    def csr_mul_csr_stream(self, A, B, rows=None, budget_bytes=0, want_row_nnz=False):
+        r0, r1 = rows if rows is not None else (0, A.dev.row)
+        st = SpgemmStats()
+        row_nnz = None
+        ptr = None
+        if want_row_nnz:
+            import torch
+            row_nnz = torch.empty(max(r1 - r0, 1), dtype=torch.int32, device="cuda")
+            ptr = row_nnz.data_ptr()
+        self._ck(self.lib.ias_csr_mul_csr_stream(C.byref(A.dev), C.byref(B.dev), r0, r1, budget_bytes, ptr, C.byref(st)))
+        d = st.as_dict()
+        if want_row_nnz:
+            d["row_nnz"] = row_nnz[: r1 - r0].cpu().numpy()
+        return d
+
+    def GetFlop(self, A, B):
+        p = C.c_longlong()
+        self._ck(self.lib.ias_getflop(C.byref(A.dev), C.byref(B.dev), C.byref(p)))
+        return p.value
+
+    def partition_rows(self, A, B, parts):
+        b = (C.c_int * (parts + 1))()
+        self._ck(self.lib.ias_partition_rows(C.byref(A.dev), C.byref(B.dev), C.c_int(parts), b))
+        return list(b)
+
+    def checksum_ptr(self, ptr, n):
+        s = C.c_double()
+        self._ck(self.lib.ias_checksum(C.c_void_p(ptr), n, C.byref(s)))
+        return s.value
+
+    def structure_hash(self, c64, row_base=0):
+        h = C.c_ulonglong()
+        self._ck(self.lib.ias_structure_hash(C.byref(c64), C.c_int(row_base), C.byref(h)))
+        return h.value
+
+    # -- DIA -----------------------------------------------------------------------------
+    def CSRtoDIA(self, A, gate=20.0):
+        d = DiaDev()
+        self._ck(self.lib.ias_csr_to_dia(C.byref(A.dev), gate, C.byref(d)))
+        return d
+
+    def download_dia(self, d):
+        di = np.zeros(max(d.row + d.col - 1, 1), np.int32)
+        off = np.zeros(max(d.num_diagonals, 1), np.int32)
+        val = np.zeros(max(d.row * d.num_diagonals, 1), np.float64)
+        self._ck(self.lib.ias_download_dia(C.byref(d), di.ctypes.data_as(_I), off.ctypes.data_as(_I), val.ctypes.data_as(_D)))
+        return {"row": d.row, "col": d.col, "num_diagonals": d.num_diagonals, "choice": bool(d.choice),
+                "diagonal_ind": di[: d.row + d.col - 1], "diagonal_offsets": off[: d.num_diagonals],
+                "values": val[: d.row * d.num_diagonals].reshape(d.row, d.num_diagonals)}
+
+    def DIA_MUL_DIA_DEV(self, A, B):
+        c, ms = DiaDev(), C.c_double()
+        self._ck(self.lib.ias_dia_mul_dia_dev(C.byref(A), C.byref(B), C.byref(c), C.byref(ms)))
+        return c, ms.value
+
+    def free_dia(self, d):
+        self.lib.ias_free_dia_dev(C.byref(d))
+
+    # -- ELL -----------------------------------------------------------------------------
+    def CSRtoELL(self, A, gate=20.0):
+        e = EllDev()
+        self._ck(self.lib.ias_csr_to_ell(C.byref(A.dev), gate, C.byref(e)))
+        return e
+
+    def download_ell(self, e):
+        w = e.max_nnz_per_row
+        nr = np.zeros(max(e.row, 1), np.int32)
+        ci = np.zeros(max(e.row * w, 1), np.int32)
+        v = np.zeros(max(e.row * w, 1), np.float64)
+        self._ck(self.lib.ias_download_ell(C.byref(e), nr.ctypes.data_as(_I), ci.ctypes.data_as(_I), v.ctypes.data_as(_D)))
+        return {"row": e.row, "col": e.col, "width": w, "nnz": e.nnz, "choice": bool(e.choice), "nnz_row": nr[: e.row],
+                "col_ind": ci[: e.row * w].reshape(e.row, w), "values": v[: e.row * w].reshape(e.row, w)}
+
+    def ELL_MUL_ELL_DEV(self, A, B):
+        c, ms = EllDev(), C.c_double()
+        self._ck(self.lib.ias_ell_mul_ell_dev(C.byref(A), C.byref(B), C.byref(c), C.byref(ms)))
+        return c, ms.value
+
+    def free_ell(self, e):
+        self.lib.ias_free_ell_dev(C.byref(e))
+
+    # -- COO -----------------------------------------------------------------------------
+    def CSRtoCOO(self, A):
+        c = CooDev()
+        self._ck(self.lib.ias_csr_to_coo(C.byref(A.dev), C.byref(c)))
+        return c
+
+    def download_coo(self, c):
+        ro = np.zeros(c.row + 1, np.int64)
+        ri = np.zeros(max(c.nnz, 1), np.int32)
+        ci = np.zeros(max(c.nnz, 1), np.int32)
+        v = np.zeros(max(c.nnz, 1), np.float64)
+        self._ck(self.lib.ias_download_coo(C.byref(c), ro.ctypes.data_as(_L), ri.ctypes.data_as(_I), ci.ctypes.data_as(_I), v.ctypes.data_as(_D)))
+        return {"row": c.row, "col": c.col, "nnz": c.nnz, "row_offset": ro, "row_ind": ri[: c.nnz], "col_ind": ci[: c.nnz],
+                "values": v[: c.nnz]}
+
+    def COO_MUL_COO_DEV(self, A, B):
+        c, ms = CooDev(), C.c_double()
+        self._ck(self.lib.ias_coo_mul_coo_dev(C.byref(A), C.byref(B), C.byref(c), C.byref(ms)))
+        return c, ms.value
+
+    def free_coo(self, c):
+        self.lib.ias_free_coo_dev(C.byref(c))
+
+    # -- features ------------------------------------------------------------------------
+    def density_image(self, A):
+        img = np.zeros(128 * 128, np.int64)
+        self._ck(self.lib.ias_density_image(C.byref(A.dev), img.ctypes.data_as(_L)))
+        return img.reshape(128, 128)
+
+    def GetInfo1(self, A):
+        f = np.zeros(9)
+        self._ck(self.lib.ias_getinfo1(C.byref(A.dev), f.ctypes.data_as(_D)))
+        return f
+
+    def GetInfo2(self, rows, cols, nd):
+        f = np.zeros(3)
+        self._ck(self.lib.ias_getinfo2(rows, cols, nd, f.ctypes.data_as(_D)))
+        return f
+
+    def GetInfo3(self, rows, nnz, width):
+        f = np.zeros(1)
+        self._ck(self.lib.ias_getinfo3(rows, nnz, width, f.ctypes.data_as(_D)))
+        return f
+
+    def count_diagonals(self, A):
+        n = C.c_int()
+        self._ck(self.lib.ias_count_diagonals(C.byref(A.dev), C.byref(n)))
+        return n.value
+
+    def max_row_nnz(self, A):
+        n = C.c_int()
+        self._ck(self.lib.ias_max_row_nnz(C.byref(A.dev), C.byref(n)))
+        return n.value
+
+    def features26(self, A, B):
+        f = np.zeros(26)
+        self._ck(self.lib.ias_features26(C.byref(A.dev), C.byref(B.dev), f.ctypes.data_as(_D)))
+        return f
+
+    # -- front end -----------------------------------------------------------------------
+    def mtx_load(self, path):
+        h = CsrMatrix()
+        rc = self.lib.ias_mtx_load(path.encode(), C.byref(h))
+        if rc != 0:
+            raise IOError("ias_mtx_load(%s) -> %d" % (path, rc))
+        rp = np.ctypeslib.as_array(h.row_ind, shape=(h.row + 1,)).copy()
+        ci = np.ctypeslib.as_array(h.col_ind, shape=(h.nnz,)).copy() if h.nnz else np.zeros(0, np.int32)
+        v = np.ctypeslib.as_array(h.values, shape=(h.nnz,)).copy() if h.nnz else np.zeros(0, np.float64)
+        self.lib.ias_free_host_csr(C.byref(h))
+        return h.row, h.col, rp, ci, v
+
+    # -- synthetic operands ----------------------------------------------------------------
+    def gen_poisson2d(self, n_grid):
+        d = CsrMatrixDev()
+        self._ck(self.lib.ias_gen_poisson2d(C.c_int(n_grid), C.byref(d)))
+        return DeviceCsr(self, d)
+
+    def gen_uniform(self, n, per_row, seed=1):
+        d = CsrMatrixDev()
+        self._ck(self.lib.ias_gen_uniform(C.c_int(n), C.c_int(per_row), C.c_int(seed), C.byref(d)))
+        return DeviceCsr(self, d)
+
+    def gen_rmat(self, scale, edge_factor=16, seed=1, a=0.57, b=0.19, c=0.19):
+        d = CsrMatrixDev()
+        self._ck(self.lib.ias_gen_rmat(scale, edge_factor, seed, a, b, c, C.byref(d)))
+        return DeviceCsr(self, d)
+
+
+_ENGINE = None
+
+
+def get_engine(device=0):
+    global _ENGINE
+    if _ENGINE is None:
+        _ENGINE = Engine(device)
+    return _ENGINE

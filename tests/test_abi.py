@@ -1,0 +1,137 @@
+"""CPU-side checks of the drop-in boundary: the shared library loads, exports every symbol that
+include/iaspgemm.h declares, has reference-compatible struct layouts, refuses to run without a GPU
+(no CPU fallback), and its host-only pieces (Matrix-Market loader, sizeof formulas) match the oracle."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from ia_spgemm_b200 import engine as E
+from util import RECT, SQUARE
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    import __graft_entry__ as g
+    if not os.path.exists(E.LIB_PATH):
+        g.build()
+    return E.load_library()
+
+
+def _declared():
+    text = open(os.path.join(ROOT, "include", "iaspgemm.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(ias_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_and_python_mirror_agree():
+    assert _declared() == sorted(E.ABI_SYMBOLS)
+
+
+def test_library_exports_every_declared_symbol(lib):
+    missing = [s for s in _declared() if not hasattr(lib, s)]
+    assert not missing, missing
+
+
+def test_every_entry_point_cites_the_reference():
+    text = open(os.path.join(ROOT, "include", "iaspgemm.h")).read()
+    for needle in ("csr_dev/common_csr_dev.h:134", "dia_dev/common_dia_dev.h:138", "ell_dev/common_ell_dev.h:310",
+                   "coo_dev/common_coo_dev.h:279", "common_csr.h:290", "common_csr.h:257", "main.cpp:516", "main.cpp:143"):
+        assert needle in text, needle
+
+
+def test_struct_layouts_match_reference_format_h():
+    # bool choice; int row, col, nnz; three pointers  ->  4 + 12 (+0 pad) + 24 on LP64
+    for S in (E.CsrMatrix, E.CsrMatrixDev):
+        assert C.sizeof(S) == 40
+        assert (S.choice.offset, S.row.offset, S.col.offset, S.nnz.offset) == (0, 4, 8, 12)
+    assert E.CsrMatrix.row_ind.offset == 16 and E.CsrMatrix.values.offset == 32
+    assert E.DiaDev.num_diagonals.offset == 12 and E.DiaDev.values_dev.offset == 32
+    assert C.sizeof(E.SpgemmStats) == 8 * 8 + 16 * 8 + 2 * 4 + 8 + 8
+
+
+def test_no_cpu_fallback(lib):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    assert lib.ias_init(0) == 1          # IAS_E_CUDA
+    assert b"no CPU fallback" in lib.ias_last_error()
+    with pytest.raises(E.EngineError):
+        E.Engine()
+
+
+def test_product_never_touches_the_oracle():
+    pkg = os.path.join(ROOT, "ia_spgemm_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath:
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "libiaoracle" not in text and "oracle." not in text.replace("the oracle.", ""), f
+                assert not re.search(r"^\s*(from|import)\s+oracle", text, flags=re.M), f
+
+
+def test_sizeof_formulas(lib, oracle):
+    for rows, nnz, cols, nd, w in ((4, 9, 4, 3, 3), (16777216, 218021892, 16777216, 13, 13), (8000000, 2048000000, 8000000, 5, 256)):
+        assert lib.ias_sizeof_csr(rows, nnz) == oracle.sizeof_csr(rows, nnz)
+        assert lib.ias_sizeof_coo(rows, nnz) == oracle.sizeof_coo(rows, nnz)
+        assert lib.ias_sizeof_dia(rows, cols, nd) == oracle.sizeof_dia(rows, cols, nd)
+        assert lib.ias_sizeof_ell(rows, w) == oracle.sizeof_ell(rows, w)
+    assert lib.ias_sizeof_csr(4, 9) == 140.0 and lib.ias_sizeof_csr(4, 10) == 152.0      # screenshot values
+
+
+def _mtx_load(lib, path):
+    h = E.CsrMatrix()
+    rc = lib.ias_mtx_load(path.encode(), C.byref(h))
+    if rc != 0:
+        return rc
+    out = (h.row, h.col, np.ctypeslib.as_array(h.row_ind, shape=(h.row + 1,)).copy(),
+           np.ctypeslib.as_array(h.col_ind, shape=(max(h.nnz, 1),))[: h.nnz].copy(),
+           np.ctypeslib.as_array(h.values, shape=(max(h.nnz, 1),))[: h.nnz].copy())
+    lib.ias_free_host_csr(C.byref(h))
+    return out
+
+
+@pytest.mark.parametrize("name", SQUARE + RECT)
+def test_loader_matches_reference_dump(lib, golden, mtx_dir, name):
+    g = golden["inputs"][name]
+    rows, cols, rp, ci, v = _mtx_load(lib, os.path.join(mtx_dir, name + ".mtx"))
+    assert (rows, cols) == (g["rows"], g["cols"])
+    assert rp.tolist() == g["loader_row_ptr"]
+    assert ci.tolist() == g["loader_col_ind"]
+    assert v.tolist() == g["loader_values"]
+
+
+def test_loader_error_codes(lib, tmp_path):
+    assert _mtx_load(lib, str(tmp_path / "missing.mtx")) == -1
+    p = tmp_path / "nobanner.mtx"; p.write_text("hello world\n")
+    assert _mtx_load(lib, str(p)) == -2
+    p = tmp_path / "cplx.mtx"; p.write_text("%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 1.0 0.0\n")
+    assert _mtx_load(lib, str(p)) == -3
+    p = tmp_path / "nosize.mtx"; p.write_text("%%MatrixMarket matrix coordinate real general\n% only comments\n")
+    assert _mtx_load(lib, str(p)) == -4
+    p = tmp_path / "skew.mtx"; p.write_text("%%MatrixMarket matrix coordinate real skew-symmetric\n3 3 2\n2 1 5.0\n3 2 -1.5\n")
+    rows, cols, rp, ci, v = _mtx_load(lib, str(p))
+    assert rp.tolist() == [0, 0, 1, 2] and ci.tolist() == [0, 1] and v.tolist() == [5.0, -1.5]     # not mirrored
+
+
+def test_loader_agrees_with_oracle_on_random_files(lib, oracle, tmp_path):
+    rng = np.random.default_rng(0)
+    for t, (field, symm) in enumerate([("real", "general"), ("integer", "symmetric"), ("pattern", "hermitian"), ("real", "symmetric")]):
+        n = 17
+        ent = {(int(i), int(j)) for i, j in rng.integers(1, n + 1, size=(60, 2)) if symm == "general" or i >= j}
+        lines = ["%%MatrixMarket matrix coordinate " + field + " " + symm, "% c", "%d %d %d" % (n, n, len(ent))]
+        for i, j in ent:
+            val = "" if field == "pattern" else (" %d" % rng.integers(-9, 9) if field == "integer" else " %.17g" % rng.normal())
+            lines.append("%d %d%s" % (i, j, val))
+        p = tmp_path / ("m%d.mtx" % t)
+        p.write_text("\n".join(lines) + "\n")
+        got, want = _mtx_load(lib, str(p)), oracle.mtx_load(str(p))
+        assert got[:2] == want[:2]
+        for a, b in zip(got[2:], want[2:]):
+            assert np.array_equal(a, b)

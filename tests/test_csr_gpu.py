@@ -1,0 +1,221 @@
+"""Parity of the CUDA CSR hot path (through the C ABI) with the CPU oracle.
+
+Bar (BASELINE.json north_star): row_ptr and column indices bit-exact after sorting, values within
+1e-12 relative per entry.  Oracle rows come out unsorted (reverse first-touch), the engine's are
+column sorted, so the oracle side is sorted before comparison (tests/util.py).
+"""
+import os
+
+import numpy as np
+import pytest
+
+from ia_spgemm_b200 import workloads as W
+from util import RTOL, SQUARE, abs_product, assert_csr_parity, sort_rows
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from ia_spgemm_b200.engine import get_engine
+    return get_engine()
+
+
+def _mul(eng, A, B=None):
+    dA = eng.upload(*A)
+    dB = dA if B is None else eng.upload(*B)
+    got, st = eng.CSR_MUL_CSR_DEV(dA, dB)
+    dA.close()
+    if B is not None:
+        dB.close()
+    return got, st
+
+
+def _oracle(oracle, A, B=None):
+    B = A if B is None else B
+    return oracle.csr_mul_csr(A[0], B[1], A[2], A[3], A[4], B[2], B[3], B[4])
+
+
+def _check(eng, oracle, A, B=None, mag=True):
+    got, st = _mul(eng, A, B)
+    want = _oracle(oracle, A, B)
+    m = abs_product(oracle, A, A if B is None else B) if mag else None
+    assert_csr_parity(got, want, mag=m)
+    assert st["nnz"] == int(want[0][-1])
+    assert st["products"] == oracle.getflop(A[2], A[3], (A if B is None else B)[2])
+    return got, st
+
+
+@pytest.mark.parametrize("name", SQUARE)
+def test_bundled_square_inputs(eng, oracle, golden, mtx_dir, name):
+    """A^2 of the reference's own Inputs/*.mtx, against the oracle and the committed reference output."""
+    A = oracle.mtx_load(os.path.join(mtx_dir, name + ".mtx"))
+    got, st = _check(eng, oracle, A)
+    g = golden["inputs"][name]
+    if "csr_row_ptr" not in g:
+        return
+    assert st["nnz"] == g["csr_row_ptr"][-1]
+    assert st["products"] == g["flop"]
+    ref = sort_rows(np.array(g["csr_row_ptr"]), np.array(g["csr_col_ind"]), np.array(g["csr_values"], dtype=np.float64))
+    assert np.array_equal(got[0], ref[0]) and np.array_equal(got[1], ref[1])
+    scale = np.maximum(np.abs(ref[2]), abs_product(oracle, A, A))
+    assert np.all(np.abs(got[2] - ref[2]) <= RTOL * scale)
+    assert eng.lib.ias_sizeof_csr(A[0], st["nnz"]) == g["sizeof_csr_c"]
+
+
+def test_dia_mtx_known_answer(eng, oracle, mtx_dir):
+    """dia.mtx A^2 = rows {0:1,1:2,2:1} {1:1,2:2,3:1} {2:1,3:2} {3:1}."""
+    A = oracle.mtx_load(os.path.join(mtx_dir, "dia.mtx"))
+    (rp, ci, v), st = _mul(eng, A)
+    assert rp.tolist() == [0, 3, 6, 8, 9]
+    assert ci.tolist() == [0, 1, 2, 1, 2, 3, 2, 3, 3]
+    assert v.tolist() == [1, 2, 1, 1, 2, 1, 1, 2, 1]
+    assert st["products"] == 12
+
+
+def test_keeps_numerical_zeros(eng, oracle, mtx_dir):
+    """b1_ss has three entries that cancel to exactly 0.0; the structure must keep them."""
+    A = oracle.mtx_load(os.path.join(mtx_dir, "b1_ss.mtx"))
+    (rp, ci, v), _ = _mul(eng, A)
+    assert int(rp[-1]) == 30
+    assert np.count_nonzero(np.abs(v) < 1e-15) == 3
+
+
+@pytest.mark.parametrize("rows,inner,cols,density,seed", [
+    (1, 1, 1, 1.0, 1), (7, 5, 9, 0.5, 2), (64, 64, 64, 0.1, 3), (300, 200, 500, 0.05, 4),
+    (1000, 1000, 1000, 0.02, 5), (513, 2000, 3000, 0.3, 6), (50, 4000, 20000, 0.6, 7),
+])
+def test_random_rectangular_unsorted(eng, oracle, rows, inner, cols, density, seed):
+    """A*B with empty rows, unsorted column order inside rows, every smem bin."""
+    A = W.random_sparse(rows, inner, density, seed=seed, sort_columns=False)
+    B = W.random_sparse(inner, cols, density, seed=seed + 100, sort_columns=False)
+    _check(eng, oracle, A, B)
+
+
+def test_empty_operands(eng, oracle):
+    z = (5, 5, np.zeros(6, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    (rp, ci, v), st = _mul(eng, z)
+    assert rp.tolist() == [0] * 6 and len(ci) == 0 and st["products"] == 0
+    A = W.random_sparse(5, 5, 0.5, seed=1)
+    (rp, ci, v), st = _mul(eng, A, z)
+    assert int(rp[-1]) == 0
+    z0 = (0, 4, np.zeros(1, np.int32), np.zeros(0, np.int32), np.zeros(0))
+    B = W.random_sparse(4, 4, 0.5, seed=1)
+    (rp, ci, v), st = _mul(eng, z0, B)
+    assert rp.tolist() == [0]
+
+
+def test_duplicate_entries_are_merged_like_csr_mul_csr(eng, oracle):
+    """The reference loader does not merge duplicate (i,j); CSR_MUL_CSR accumulates them."""
+    rp = np.array([0, 3, 5], np.int32)
+    ci = np.array([1, 1, 0, 0, 0], np.int32)
+    v = np.array([1.0, 2.0, 3.0, 4.0, 5.0])
+    _check(eng, oracle, (2, 2, rp, ci, v))
+
+
+def test_shape_mismatch_is_an_error(eng):
+    from ia_spgemm_b200.engine import EngineError
+    A = W.random_sparse(4, 6, 0.5, seed=1)
+    B = W.random_sparse(5, 4, 0.5, seed=2)
+    dA, dB = eng.upload(*A), eng.upload(*B)
+    with pytest.raises(EngineError) as e:
+        eng.CSR_MUL_CSR_DEV(dA, dB)
+    assert e.value.code == 2
+
+
+def test_poisson_tiny_bin(eng, oracle):
+    A = W.poisson2d(192)
+    got, st = _check(eng, oracle, A, mag=True)
+    nnz_a, prod, nnz_c = W.poisson_counts(192)
+    assert (st["products"], st["nnz"]) == (prod, nnz_c)
+    assert st["sym_bin_rows"][1] == 192 * 192           # every row in the tiny bin
+
+
+def test_uniform_warp_bin(eng, oracle):
+    A = W.uniform_rows(30000, 16, seed=1)
+    got, st = _check(eng, oracle, A, mag=False)
+    assert st["products"] == 30000 * 256
+    assert st["sym_bin_rows"][2] == 30000
+
+
+@pytest.mark.parametrize("scale", [10, 13])
+def test_rmat_all_bins(eng, oracle, scale):
+    A = W.rmat(scale, 16, seed=1)
+    got, st = _check(eng, oracle, A, mag=False)
+    if scale == 13:
+        assert st["sym_bin_rows"][5] > 0 and st["num_bin_rows"][4] > 0      # global + large CTA bins exercised
+
+
+def test_rmat_forced_global_bin(eng, oracle):
+    """A dense-ish operand whose rows exceed the shared-memory hash: bitmap + rank path."""
+    A = W.random_sparse(40, 300, 0.9, seed=3)
+    B = W.random_sparse(300, 40000, 0.4, seed=4, sort_columns=False)
+    got, st = _check(eng, oracle, A, B, mag=False)
+    assert st["num_bin_rows"][5] > 0
+
+
+def test_row_blocks_concatenate_to_full_result(eng, oracle):
+    """Multi-GPU row blocks: C[r0:r1,:] computed independently equals the slice of the full product."""
+    A = W.rmat(11, 16, seed=2)
+    dA = eng.upload(*A)
+    (rp, ci, v), st = eng.CSR_MUL_CSR_DEV(dA, dA)
+    bounds = eng.partition_rows(dA, dA, 4)
+    assert bounds[0] == 0 and bounds[-1] == A[0] and all(b0 <= b1 for b0, b1 in zip(bounds, bounds[1:]))
+    tot = 0
+    for b0, b1 in zip(bounds, bounds[1:]):
+        (rpb, cib, vb), sb = eng.CSR_MUL_CSR_DEV(dA, dA, rows=(b0, b1))
+        assert np.array_equal(rpb, rp[b0:b1 + 1] - rp[b0])
+        assert np.array_equal(cib, ci[rp[b0]:rp[b1]])
+        assert np.allclose(vb, v[rp[b0]:rp[b1]], rtol=1e-13, atol=0)
+        tot += sb["products"]
+    assert tot == st["products"] == eng.GetFlop(dA, dA)
+    # balance: no block above 2x the mean share (contiguous split of a skewed matrix)
+    shares = [eng.CSR_MUL_CSR_DEV(dA, dA, rows=(b0, b1), download=False)[1]["products"] for b0, b1 in zip(bounds, bounds[1:])]
+    assert max(shares) <= 2.0 * st["products"] / 4 + max(A[2][1:] - A[2][:-1]) * 2000
+    dA.close()
+
+
+def test_streaming_matches_materialised(eng, oracle):
+    """Streaming mode (row batches under a byte budget) reproduces nnz, checksum, structure hash, row nnz."""
+    A = W.rmat(12, 16, seed=3)
+    dA = eng.upload(*A)
+    c64, st = eng.CSR_MUL_CSR_DEV(dA, dA, keep=True)
+    h = eng.structure_hash(c64)
+    s = eng.checksum_ptr(c64.values_dev, c64.nnz)
+    (rp, ci, v) = eng._take_csr64(c64)
+    for budget in (0, 12 * 40000, 12 * 5000):
+        d = eng.csr_mul_csr_stream(dA, dA, budget_bytes=budget, want_row_nnz=True)
+        assert d["nnz"] == st["nnz"] and d["products"] == st["products"]
+        assert d["structure_hash"] == h
+        assert np.isclose(d["checksum"], s, rtol=1e-11)
+        assert np.array_equal(d["row_nnz"], np.diff(rp))
+        if budget:
+            assert d["batches"] > 1
+    # host restatement of the hash: sum of mix64(row<<32|col)
+    rows = np.repeat(np.arange(A[0], dtype=np.uint64), np.diff(rp))
+    with np.errstate(over="ignore"):
+        want = int(W.mix64((rows << np.uint64(32)) | ci.astype(np.uint64)).sum(dtype=np.uint64))
+    assert h == want
+    dA.close()
+
+
+def test_int32_layout_and_host_path(eng, oracle):
+    A = W.random_sparse(200, 200, 0.05, seed=9)
+    dA = eng.upload(*A)
+    rp32, ci32, v32, ms = eng.csr_mul_csr_dev32(dA, dA)
+    want = _oracle(oracle, A)
+    assert_csr_parity((rp32, ci32, v32), want, mag=abs_product(oracle, A, A))
+    assert rp32.dtype == np.int32 and ms > 0
+    (rp, ci, v), st, h2d, d2h = eng.CSR_MUL_CSR(A, A)
+    assert_csr_parity((rp.copy(), ci.copy(), v.copy()), want, mag=abs_product(oracle, A, A))
+    assert eng.is_canonical(dA)
+    dA.close()
+
+
+def test_launch_counter_moves(eng):
+    A = W.poisson2d(32)
+    dA = eng.upload(*A)
+    before = eng.kernel_launches()
+    _, st = eng.CSR_MUL_CSR_DEV(dA, dA, download=False)
+    assert eng.kernel_launches() - before == st["kernel_launches"] > 0
+    dA.close()

@@ -1,0 +1,273 @@
+"""Parity of the DIA / ELL / COO kernels, the converters, the density image, the features and the
+device generators with the CPU oracle and the committed reference fixtures (through the C ABI)."""
+import os
+
+import numpy as np
+import pytest
+
+from ia_spgemm_b200 import workloads as W
+from util import RECT, RTOL, SQUARE, abs_product, decode_img, sort_rows
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from ia_spgemm_b200.engine import get_engine
+    return get_engine()
+
+
+def _load(oracle, mtx_dir, name):
+    return oracle.mtx_load(os.path.join(mtx_dir, name + ".mtx"))
+
+
+CASES = [
+    ("poisson40", lambda: W.poisson2d(40)),
+    ("banded", lambda: W.banded(700, [-9, -1, 0, 2, 17], seed=4)),
+    ("uniform", lambda: W.uniform_rows(3000, 8, seed=3)),
+    ("irregular", lambda: W.random_sparse(257, 300, 0.03, seed=5)),
+    ("unsorted", lambda: W.random_sparse(120, 120, 0.08, seed=6, sort_columns=False)),
+    ("rmat9", lambda: W.rmat(9, 8, seed=2)),
+]
+
+
+def _close(got, want, scale=None, rtol=RTOL):
+    got, want = np.asarray(got, dtype=np.float64), np.asarray(want, dtype=np.float64)
+    s = np.abs(want) if scale is None else np.maximum(np.abs(scale), np.abs(want))
+    return bool(np.all(np.abs(got - want) <= rtol * s))
+
+
+# ---------------------------------------------------------------- DIA
+@pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
+def test_csr_to_dia_matches_oracle(eng, oracle, name, make):
+    A = make()
+    dA = eng.upload(*A)
+    for gate in (20.0, 50.0):
+        want = oracle.csr_to_dia(*A, gate=gate)
+        d = eng.CSRtoDIA(dA, gate=gate)
+        assert bool(d.choice) == want["choice"] and d.num_diagonals == want["num_diagonals"]
+        if want["choice"]:
+            got = eng.download_dia(d)
+            assert np.array_equal(got["diagonal_offsets"], want["diagonal_offsets"])
+            assert np.array_equal(got["diagonal_ind"], want["diagonal_ind"])
+            assert np.array_equal(got["values"], want["values"])
+        eng.free_dia(d)
+    dA.close()
+
+
+@pytest.mark.parametrize("name,make", CASES[:3] + CASES[4:5], ids=[c[0] for c in CASES[:3] + CASES[4:5]])
+def test_dia_mul_dia_matches_oracle(eng, oracle, name, make):
+    A = make()
+    want_a = oracle.csr_to_dia(*A, gate=1e9)
+    want = oracle.dia_mul_dia(want_a, want_a)
+    dA = eng.upload(*A)
+    d = eng.CSRtoDIA(dA, gate=1e9)
+    c, ms = eng.DIA_MUL_DIA_DEV(d, d)
+    got = eng.download_dia(c)
+    assert np.array_equal(got["diagonal_offsets"], want["diagonal_offsets"])     # offsets exact
+    assert np.array_equal(got["diagonal_ind"], want["diagonal_ind"])
+    absa = dict(want_a, values=np.abs(want_a["values"]))
+    mag = oracle.dia_mul_dia(absa, absa)["values"]
+    assert _close(got["values"], want["values"], scale=mag)                      # full padded array, 1e-12
+    # (ii) SURVEY appendix A: the CSR result sits inside the DIA result, every other position is 0
+    rp, ci, v = sort_rows(*oracle.csr_mul_csr(A[0], A[1], A[2], A[3], A[4], A[2], A[3], A[4]))
+    rows = np.repeat(np.arange(A[0]), np.diff(rp))
+    slot = np.searchsorted(got["diagonal_offsets"], ci.astype(np.int64) - rows)
+    dense = got["values"].copy()
+    magc = abs_product(oracle, A, A)
+    assert _close(dense[rows, slot], v, scale=magc)
+    dense[rows, slot] = 0.0
+    assert np.all(np.abs(dense) <= RTOL * mag)
+    assert ms > 0
+    eng.free_dia(c); eng.free_dia(d); dA.close()
+
+
+@pytest.mark.parametrize("name", SQUARE)
+def test_dia_golden(eng, oracle, golden, mtx_dir, name):
+    g = golden["inputs"][name]
+    if "dia_offsets_c" not in g:
+        pytest.skip("reference refused DIA for this input")
+    A = _load(oracle, mtx_dir, name)
+    dA = eng.upload(*A)
+    d = eng.CSRtoDIA(dA, gate=50.0)
+    assert eng.download_dia(d)["diagonal_offsets"].tolist() == g["dia_offsets_a"]
+    c, _ = eng.DIA_MUL_DIA_DEV(d, d)
+    got = eng.download_dia(c)
+    assert got["diagonal_offsets"].tolist() == g["dia_offsets_c"]
+    assert got["diagonal_ind"].tolist() == g["dia_diag_ind_c"]
+    want = np.array(g["dia_values_c"], dtype=np.float64)
+    absd = oracle.csr_to_dia(A[0], A[1], A[2], A[3], np.abs(A[4]), gate=50.0)
+    mag = oracle.dia_mul_dia(absd, absd)["values"].ravel()
+    assert _close(got["values"].ravel(), want, scale=mag)
+    assert eng.lib.ias_sizeof_dia(c.row, c.col, c.num_diagonals) == oracle.sizeof_dia(c.row, c.col, c.num_diagonals)
+    eng.free_dia(c); eng.free_dia(d); dA.close()
+
+
+def test_dia_gate_refuses_scattered(eng, oracle):
+    from ia_spgemm_b200.engine import EngineError
+    S = W.uniform_rows(4000, 2, seed=1)
+    dS = eng.upload(*S)
+    d = eng.CSRtoDIA(dS, gate=20.0)
+    assert not d.choice and d.num_diagonals == oracle.csr_to_dia(*S, gate=20.0)["num_diagonals"]
+    with pytest.raises(EngineError) as e:
+        eng.DIA_MUL_DIA_DEV(d, d)
+    assert e.value.code == 5
+    dS.close()
+
+
+def test_dia_rectangular(eng, oracle):
+    A = W.random_sparse(30, 45, 0.2, seed=1)
+    B = W.random_sparse(45, 25, 0.2, seed=2)
+    oa, ob = oracle.csr_to_dia(*A, gate=1e9), oracle.csr_to_dia(*B, gate=1e9)
+    want = oracle.dia_mul_dia(oa, ob)
+    dA, dB = eng.upload(*A), eng.upload(*B)
+    da, db = eng.CSRtoDIA(dA, gate=1e9), eng.CSRtoDIA(dB, gate=1e9)
+    c, _ = eng.DIA_MUL_DIA_DEV(da, db)
+    got = eng.download_dia(c)
+    assert np.array_equal(got["diagonal_offsets"], want["diagonal_offsets"])
+    assert np.array_equal(got["diagonal_ind"], want["diagonal_ind"])
+    assert np.allclose(got["values"], want["values"], rtol=1e-12, atol=1e-14)
+    for x in (c, da, db):
+        eng.free_dia(x)
+    dA.close(); dB.close()
+
+
+# ---------------------------------------------------------------- ELL
+@pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
+def test_ell_matches_oracle(eng, oracle, name, make):
+    A = make()
+    dA = eng.upload(*A)
+    want_a = oracle.csr_to_ell(*A, gate=20.0)
+    e = eng.CSRtoELL(dA, gate=20.0)
+    assert bool(e.choice) == want_a["choice"] and e.max_nnz_per_row == want_a["width"]
+    if want_a["choice"]:
+        got_a = eng.download_ell(e)
+        for key in ("nnz_row", "col_ind", "values"):
+            assert np.array_equal(got_a[key], want_a[key]), key
+        want = oracle.ell_mul_ell(want_a, want_a)
+        c, ms = eng.ELL_MUL_ELL_DEV(e, e)
+        got = eng.download_ell(c)
+        assert got["width"] == want["width"] and got["nnz"] == want["nnz"]
+        assert np.array_equal(got["nnz_row"], want["nnz_row"])
+        mag = abs_product(oracle, A, A)
+        p = 0
+        for i in range(A[0]):                     # engine rows are sorted, the reference's are reverse first-touch
+            n = int(want["nnz_row"][i])
+            o = np.argsort(want["col_ind"][i, :n], kind="stable")
+            assert np.array_equal(got["col_ind"][i, :n], want["col_ind"][i, :n][o])
+            assert _close(got["values"][i, :n], want["values"][i, :n][o], scale=mag[p:p + n])
+            assert not got["col_ind"][i, n:].any() and not got["values"][i, n:].any()      # 0 / 0.0 padding
+            p += n
+        eng.free_ell(c)
+    eng.free_ell(e); dA.close()
+
+
+@pytest.mark.parametrize("name", SQUARE)
+def test_ell_golden(eng, oracle, golden, mtx_dir, name):
+    g = golden["inputs"][name]
+    if "ell_width_c" not in g:
+        pytest.skip("reference refused ELL for this input")
+    A = _load(oracle, mtx_dir, name)
+    dA = eng.upload(*A)
+    e = eng.CSRtoELL(dA, gate=50.0)
+    c, _ = eng.ELL_MUL_ELL_DEV(e, e)
+    got = eng.download_ell(c)
+    assert got["width"] == g["ell_width_c"] and got["nnz_row"].tolist() == g["ell_nnz_row_c"]
+    w = got["width"]
+    wc = np.array(g["ell_col_ind_c"]).reshape(A[0], w)
+    wv = np.array(g["ell_values_c"], dtype=np.float64).reshape(A[0], w)
+    for i in range(A[0]):
+        n = got["nnz_row"][i]
+        o = np.argsort(wc[i, :n], kind="stable")
+        assert np.array_equal(got["col_ind"][i, :n], wc[i, :n][o])
+        assert np.allclose(got["values"][i, :n], wv[i, :n][o], rtol=1e-12, atol=1e-9 if name in ("LFAT5", "b1_ss") else 0)
+    eng.free_ell(c); eng.free_ell(e); dA.close()
+
+
+# ---------------------------------------------------------------- COO
+@pytest.mark.parametrize("name,make", CASES, ids=[c[0] for c in CASES])
+def test_coo_matches_oracle(eng, oracle, name, make):
+    A = make()
+    dA = eng.upload(*A)
+    k = eng.CSRtoCOO(dA)
+    got_a = eng.download_coo(k)
+    want_a = oracle.csr_to_coo(A[0], A[2], A[3], A[4])
+    for key in ("row_offset", "row_ind", "col_ind", "values"):
+        assert np.array_equal(got_a[key], want_a[key]), key
+    c, ms = eng.COO_MUL_COO_DEV(k, k)
+    got = eng.download_coo(c)
+    want = oracle.csr_mul_csr(A[0], A[1], A[2], A[3], A[4], A[2], A[3], A[4])     # same symbolic pass as COO_MUL_COO
+    rp, ci, v = sort_rows(*want)
+    assert np.array_equal(got["row_offset"], rp) and np.array_equal(got["col_ind"], ci)
+    assert np.array_equal(got["row_ind"], np.repeat(np.arange(A[0]), np.diff(rp)))
+    assert _close(got["values"], v, scale=abs_product(oracle, A, A))
+    if A[0] <= 600:                               # the reference's own COO kernel (first-touch order), small cases only
+        wc = oracle.coo_mul_coo(A[0], A[1], want_a, want_a)
+        o = np.lexsort((wc["col_ind"], wc["row_ind"]))
+        assert np.array_equal(got["col_ind"], wc["col_ind"][o]) and np.array_equal(got["row_offset"], wc["row_offset"])
+        assert _close(got["values"], wc["values"][o], scale=abs_product(oracle, A, A))
+    assert eng.lib.ias_sizeof_coo(A[0], c.nnz) == oracle.sizeof_coo(A[0], c.nnz)
+    eng.free_coo(c); eng.free_coo(k); dA.close()
+
+
+# ---------------------------------------------------------------- density + features
+@pytest.mark.parametrize("name", SQUARE + RECT)
+def test_density_golden(eng, oracle, golden, mtx_dir, name):
+    A = _load(oracle, mtx_dir, name)
+    dA = eng.upload(*A)
+    assert np.array_equal(eng.density_image(dA), decode_img(golden["inputs"][name]["density"]))
+    dA.close()
+
+
+def test_density_shipped_images(eng, oracle, golden, mtx_dir):
+    ship = golden["shipped_imgs"]
+    for name, key in (("dia", "gpu_img1_dia"), ("small", "cpu_img1_small")):
+        A = _load(oracle, mtx_dir, name)
+        dA = eng.upload(*A)
+        assert np.array_equal(eng.density_image(dA), decode_img(ship[key]))
+        dA.close()
+
+
+@pytest.mark.parametrize("name,make", CASES + [("exact128", lambda: W.random_sparse(128, 128, 0.1, seed=8)),
+                                                ("wide", lambda: W.random_sparse(50, 5000, 0.01, seed=9))],
+                         ids=[c[0] for c in CASES] + ["exact128", "wide"])
+def test_density_and_features_match_oracle(eng, oracle, name, make):
+    A = make()
+    dA = eng.upload(*A)
+    assert np.array_equal(eng.density_image(dA), oracle.density(A[0], A[1], A[2], A[3]))
+    want = oracle.features26(A, A, gate=20.0)
+    got = eng.features26(dA, dA)
+    assert np.allclose(got, want, rtol=1e-12, atol=0), (got, want)
+    assert eng.count_diagonals(dA) == oracle.csr_to_dia(*A, gate=1e9)["num_diagonals"]
+    assert eng.max_row_nnz(dA) == int(np.diff(A[2]).max())
+    assert eng.GetFlop(dA, dA) == oracle.getflop(A[2], A[3], A[2]) if A[0] == A[1] else True
+    dA.close()
+
+
+def test_features_screenshot(eng, oracle, golden, mtx_dir):
+    A = _load(oracle, mtx_dir, "dia")
+    dA = eng.upload(*A)
+    assert eng.features26(dA, dA).tolist() == golden["screenshot_features_dia"]
+    dA.close()
+
+
+# ---------------------------------------------------------------- loader + generators
+@pytest.mark.parametrize("name", SQUARE + RECT)
+def test_engine_loader_golden(eng, golden, mtx_dir, name):
+    g = golden["inputs"][name]
+    rows, cols, rp, ci, v = eng.mtx_load(os.path.join(mtx_dir, name + ".mtx"))
+    assert (rows, cols) == (g["rows"], g["cols"])
+    assert rp.tolist() == g["loader_row_ptr"] and ci.tolist() == g["loader_col_ind"] and v.tolist() == g["loader_values"]
+
+
+def test_device_generators_are_bit_identical_to_numpy(eng):
+    for dev, host in ((eng.gen_poisson2d(37), W.poisson2d(37)),
+                      (eng.gen_uniform(5000, 16, seed=1), W.uniform_rows(5000, 16, seed=1)),
+                      (eng.gen_uniform(40, 16, seed=3), W.uniform_rows(40, 16, seed=3)),     # collisions -> redraws
+                      (eng.gen_rmat(12, 16, seed=1), W.rmat(12, 16, seed=1)),
+                      (eng.gen_rmat(9, 4, seed=5), W.rmat(9, 4, seed=5))):
+        rows, cols, rp, ci, v = dev.download()
+        assert (rows, cols) == (host[0], host[1])
+        assert np.array_equal(rp, host[2]) and np.array_equal(ci, host[3]) and np.array_equal(v, host[4])
+        assert eng.is_canonical(dev)
+        dev.close()
