@@ -18,6 +18,7 @@ struct Ctx {
     cudaStream_t stream = nullptr;      // stream every engine kernel is launched on
     cudaMemPool_t pool = nullptr;
     cudaEvent_t ev[8] = {};
+    cudaEvent_t ev_bin[32] = {};        // [2*bin], [2*bin+1]: symbolic bins 0..7, numeric bins 8..15
     long long launches = 0;             // engine kernels launched since ias_init
     char err[512] = {0};
     // pinned host arena for ias_csr_mul_csr_host results (grow only)

@@ -67,6 +67,8 @@ int ias_init(int device)
     IAS_CUDA(cudaMemPoolSetAttribute(c.pool, cudaMemPoolAttrReleaseThreshold, &keep));
     for (int i = 0; i < 8; ++i)
         if (!c.ev[i]) IAS_CUDA(cudaEventCreate(&c.ev[i]));
+    for (int i = 0; i < 32; ++i)
+        if (!c.ev_bin[i]) IAS_CUDA(cudaEventCreate(&c.ev_bin[i]));
     if (!c.h_scalars) IAS_CUDA(cudaMallocHost((void **)&c.h_scalars, 64 * sizeof(long long)));
     c.ready = true;
     return IAS_OK;

@@ -134,6 +134,7 @@ int ias_csr_mul_csr_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, i
         IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 40, rp.p + b0, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
         IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 41, rp.p + b1, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
         IAS_CUDA(cudaStreamSynchronize(c.stream));
+        collect_bin_times(rw);                   // previous batch (and the symbolic bins) are complete here
         long long e0 = c.h_scalars[40], e1 = c.h_scalars[41];
         if (e1 == e0) continue;
         OutMap out{rp.p, e0, nullptr, 0};
@@ -146,6 +147,8 @@ int ias_csr_mul_csr_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, i
     IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 43, d_sum.p, sizeof(double), cudaMemcpyDeviceToHost, c.stream));
     IAS_CUDA(cudaStreamSynchronize(c.stream));
 
+    collect_bin_times(rw);
+    for (int b = 0; b < 8; ++b) { local.ms_bin_sym[b] = rw.ms_bin_sym[b]; local.ms_bin_num[b] = rw.ms_bin_num[b]; }
     local.nnz = nnz;
     local.batches = h_nb;
     local.structure_hash = (unsigned long long)c.h_scalars[42];

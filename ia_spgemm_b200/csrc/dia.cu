@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(256) k_fill_dia(int rows, const int *__restric
 
 // C[d][i] = sum over pairs (a,b) of diagonal d:  A[a][i] * B[b][i + offA[a]]   (dia:162-193)
 // pair tables live in shared memory; one thread per row, all diagonals of the row in one pass.
-template <int BLOCK>
+template <int BLOCK, bool TABLES_IN_SMEM>
 __global__ void __launch_bounds__(BLOCK) k_dia_mul_dia(int rows, int a_cols, int b_cols, int a_nd, int b_nd, int c_nd,
                                                        const int *__restrict__ a_off, const int *__restrict__ b_off,
                                                        const double *__restrict__ a_val, const double *__restrict__ b_val,
@@ -69,15 +69,20 @@ __global__ void __launch_bounds__(BLOCK) k_dia_mul_dia(int rows, int a_cols, int
                                                        double *__restrict__ c_val)
 {
     extern __shared__ int sm[];
-    int *s_start = sm;                         // c_nd + 1
-    int *s_aoff = s_start + c_nd + 1;          // a_nd
-    int *s_boff = s_aoff + a_nd;               // b_nd
-    unsigned *s_pairs = reinterpret_cast<unsigned *>(s_boff + b_nd);   // npairs
-    for (int t = threadIdx.x; t <= c_nd; t += BLOCK) s_start[t] = pair_start[t];
-    for (int t = threadIdx.x; t < a_nd; t += BLOCK) s_aoff[t] = a_off[t];
-    for (int t = threadIdx.x; t < b_nd; t += BLOCK) s_boff[t] = b_off[t];
-    for (int t = threadIdx.x; t < npairs; t += BLOCK) s_pairs[t] = pairs[t];
-    __syncthreads();
+    const int *s_start = pair_start, *s_aoff = a_off, *s_boff = b_off;
+    const unsigned *s_pairs = pairs;
+    if (TABLES_IN_SMEM) {                      // the usual case: a few diagonals, tables of a few hundred bytes
+        int *w_start = sm;                         // c_nd + 1
+        int *w_aoff = w_start + c_nd + 1;          // a_nd
+        int *w_boff = w_aoff + a_nd;               // b_nd
+        unsigned *w_pairs = reinterpret_cast<unsigned *>(w_boff + b_nd);   // npairs
+        for (int t = threadIdx.x; t <= c_nd; t += BLOCK) w_start[t] = pair_start[t];
+        for (int t = threadIdx.x; t < a_nd; t += BLOCK) w_aoff[t] = a_off[t];
+        for (int t = threadIdx.x; t < b_nd; t += BLOCK) w_boff[t] = b_off[t];
+        for (int t = threadIdx.x; t < npairs; t += BLOCK) w_pairs[t] = pairs[t];
+        __syncthreads();
+        s_start = w_start; s_aoff = w_aoff; s_boff = w_boff; s_pairs = w_pairs;
+    }
     const int b_rows = a_cols;
     for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < rows; i += (long long)gridDim.x * BLOCK) {
         for (int d = 0; d < c_nd; ++d) {
@@ -233,14 +238,18 @@ int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, do
     if (!pab.empty()) IAS_CUDA(cudaMemcpyAsync(d_pairs.p, pab.data(), sizeof(unsigned) * pab.size(), cudaMemcpyHostToDevice, s));
 
     size_t sm = sizeof(int) * ((size_t)c_nd + 1 + ao.size() + bo.size() + pab.size());
-    if (sm > c.smem_optin) return fail(IAS_E_NOMEM, "DIA pair table (%zu bytes) exceeds shared memory", sm);
     if (A->row && c_nd) {
         constexpr int BLOCK = 256;
-        auto k = k_dia_mul_dia<BLOCK>;
-        if (sm > 48 * 1024) IAS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
         unsigned grid = (unsigned)std::min<long long>(grid_for(A->row, BLOCK), (long long)c.sm_count * 8 * 64);
-        IAS_LAUNCH(k, grid, BLOCK, sm, A->row, A->col, B->col, (int)ao.size(), (int)bo.size(), c_nd, A->diagonal_offsets_dev,
-                   B->diagonal_offsets_dev, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p, (int)pab.size(), val.p);
+        if (sm <= 32 * 1024) {
+            IAS_LAUNCH((k_dia_mul_dia<BLOCK, true>), grid, BLOCK, sm, A->row, A->col, B->col, (int)ao.size(), (int)bo.size(), c_nd,
+                       A->diagonal_offsets_dev, B->diagonal_offsets_dev, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p,
+                       (int)pab.size(), val.p);
+        } else {                               // many diagonals: the tables stay in global memory (L1/L2 resident)
+            IAS_LAUNCH((k_dia_mul_dia<BLOCK, false>), grid, BLOCK, 0, A->row, A->col, B->col, (int)ao.size(), (int)bo.size(), c_nd,
+                       A->diagonal_offsets_dev, B->diagonal_offsets_dev, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p,
+                       (int)pab.size(), val.p);
+        }
     }
     IAS_CUDA(cudaEventRecord(c.ev[1], s));
     IAS_CUDA(cudaStreamSynchronize(s));

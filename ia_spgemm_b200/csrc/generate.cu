@@ -23,30 +23,30 @@ inline uint64_t seed_salt(long long seed) { return mix64_hd((uint64_t)seed * 0x9
 __device__ __forceinline__ uint64_t key2(uint64_t salt, uint64_t i, uint64_t j) { return ((i << 32) | j) ^ salt; }
 __device__ __forceinline__ double unit53(uint64_t h) { return (double)(h >> 11) * (1.0 / 9007199254740992.0); }
 
-// ---- Poisson 2-D 5-point: closed-form row pointers
-__device__ __forceinline__ long long poisson_rp(long long r, long long N)
+// ---- Poisson 2-D 5-point on an nx x ny grid (row-major node order r = y*nx + x): closed-form row pointers
+__device__ __forceinline__ long long poisson_rp(long long r, long long nx, long long ny)
 {
-    long long top = r < N ? r : N;                                  // rows before r on the first grid line
-    long long bottom = r > N * (N - 1) ? r - N * (N - 1) : 0;       // ... on the last grid line
-    long long left = (r + N - 1) / N;                               // ... with x == 0
-    long long right = r / N;                                        // ... with x == N-1
+    long long top = r < nx ? r : nx;                                  // rows before r on the first grid line
+    long long bottom = r > nx * (ny - 1) ? r - nx * (ny - 1) : 0;     // ... on the last grid line
+    long long left = (r + nx - 1) / nx;                               // ... with x == 0
+    long long right = r / nx;                                         // ... with x == nx-1
     return 5 * r - top - bottom - left - right;
 }
 
-__global__ void __launch_bounds__(256) k_poisson(int N, int *__restrict__ rp, int *__restrict__ ci, double *__restrict__ v)
+__global__ void __launch_bounds__(256) k_poisson(int nx, int ny, int *__restrict__ rp, int *__restrict__ ci, double *__restrict__ v)
 {
-    long long n = (long long)N * N;
+    long long n = (long long)nx * ny;
     long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (r > n) return;
-    long long p = poisson_rp(r, N);
+    long long p = poisson_rp(r, nx, ny);
     rp[r] = (int)p;
     if (r == n) return;
-    long long x = r % N, y = r / N;
-    if (y > 0)     { ci[p] = (int)(r - N); v[p] = -1.0; ++p; }
-    if (x > 0)     { ci[p] = (int)(r - 1); v[p] = -1.0; ++p; }
+    long long x = r % nx, y = r / nx;
+    if (y > 0)      { ci[p] = (int)(r - nx); v[p] = -1.0; ++p; }
+    if (x > 0)      { ci[p] = (int)(r - 1); v[p] = -1.0; ++p; }
     ci[p] = (int)r; v[p] = 4.0; ++p;
-    if (x < N - 1) { ci[p] = (int)(r + 1); v[p] = -1.0; ++p; }
-    if (y < N - 1) { ci[p] = (int)(r + N); v[p] = -1.0; ++p; }
+    if (x < nx - 1) { ci[p] = (int)(r + 1); v[p] = -1.0; ++p; }
+    if (y < ny - 1) { ci[p] = (int)(r + nx); v[p] = -1.0; ++p; }
 }
 
 // ---- uniform: per_row distinct sorted columns per row; a row with a collision is re-drawn whole
@@ -119,18 +119,18 @@ __global__ void __launch_bounds__(256) k_rmat_fill(long long nnz, const uint64_t
 
 extern "C" {
 
-int ias_gen_poisson2d(int N, IasCsrMatrixDev *out)
+int ias_gen_poisson2d(int nx, int ny, IasCsrMatrixDev *out)
 {
     IAS_TRY(ensure_init());
-    if (!out || N < 1) return fail(IAS_E_ARG, "bad argument");
-    long long n = (long long)N * N, nnz = 5 * n - 4LL * N;
-    if (nnz >= 0x7fffffffLL) return fail(IAS_E_OVERFLOW, "Poisson grid %d overflows int32 indices", N);
+    if (!out || nx < 1 || ny < 1) return fail(IAS_E_ARG, "bad argument");
+    long long n = (long long)nx * ny, nnz = 5 * n - 2LL * nx - 2LL * ny;
+    if (nnz >= 0x7fffffffLL || n >= 0x7fffffffLL) return fail(IAS_E_OVERFLOW, "Poisson grid %dx%d overflows int32 indices", nx, ny);
     memset(out, 0, sizeof *out);
     out->choice = true; out->row = (int)n; out->col = (int)n; out->nnz = (int)nnz;
     IAS_TRY(dalloc(&out->row_ind_dev, (size_t)n + 1));
     IAS_TRY(dalloc(&out->col_ind_dev, (size_t)nnz));
     IAS_TRY(dalloc(&out->values_dev, (size_t)nnz));
-    IAS_LAUNCH(k_poisson, grid_for(n + 1, 256), 256, 0, N, out->row_ind_dev, out->col_ind_dev, out->values_dev);
+    IAS_LAUNCH(k_poisson, grid_for(n + 1, 256), 256, 0, nx, ny, out->row_ind_dev, out->col_ind_dev, out->values_dev);
     IAS_CUDA(cudaStreamSynchronize(ctx().stream));
     return IAS_OK;
 }

@@ -68,7 +68,27 @@ struct RangeWork {
     long long sym_hist[8] = {0};
     long long num_hist[8] = {0};
     int max_tiny_nnz = 0, max_nnz = 0;
+    bool sym_timed[8] = {false};   // which bin kernels were launched (their ev_bin pairs are pending)
+    bool num_timed[8] = {false};
+    double ms_bin_sym[8] = {0};
+    double ms_bin_num[8] = {0};
 };
+
+// events around one bin kernel: slot = bin (symbolic) or 8 + bin (numeric)
+#define IAS_BIN_BEGIN(slot) IAS_CUDA(cudaEventRecord(ctx().ev_bin[2 * (slot)], ctx().stream))
+#define IAS_BIN_END(slot) IAS_CUDA(cudaEventRecord(ctx().ev_bin[2 * (slot) + 1], ctx().stream))
+
+// after a stream synchronize: fold the pending per-bin event pairs into rw.ms_bin_*
+inline void collect_bin_times(RangeWork &rw)
+{
+    for (int b = 0; b < 8; ++b) {
+        float ms = 0.f;
+        if (rw.sym_timed[b] && cudaEventElapsedTime(&ms, ctx().ev_bin[2 * b], ctx().ev_bin[2 * b + 1]) == cudaSuccess) rw.ms_bin_sym[b] += ms;
+        if (rw.num_timed[b] && cudaEventElapsedTime(&ms, ctx().ev_bin[2 * (8 + b)], ctx().ev_bin[2 * (8 + b) + 1]) == cudaSuccess) rw.ms_bin_num[b] += ms;
+        rw.sym_timed[b] = rw.num_timed[b] = false;
+    }
+    cudaGetLastError();
+}
 
 inline int read_hist(RangeWork &rw, int n, long long *out)
 {
@@ -119,36 +139,51 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
     BinLists bl;
     IAS_TRY(build_bin_lists(nrows, rw.bin.p, h, bl));
     if (bl.count[BIN_T]) {
+        IAS_BIN_BEGIN(BIN_T);
         int n = (int)bl.count[BIN_T];
         IAS_LAUNCH((k_sym_tiny<AV, BV, TINY_BLOCK>), grid_for(n, TINY_BLOCK), TINY_BLOCK, 0, bl.rows_of(BIN_T), n, r0, A, B, rw.nnz_row.p);
+        IAS_BIN_END(BIN_T);
+        rw.sym_timed[BIN_T] = true;
     }
     if (bl.count[BIN_W]) {
+        IAS_BIN_BEGIN(BIN_W);
         int n = (int)bl.count[BIN_W];
         auto k = k_sym_hash<AV, BV, 32, 256, SYM_W_TSIZE>;
         size_t sm = (size_t)8 * SYM_W_TSIZE * sizeof(int);
         IAS_TRY(opt_in_smem(k, sm));
         IAS_LAUNCH(k, grid_for(n, 8), 256, sm, bl.rows_of(BIN_W), n, r0, A, B, rw.nnz_row.p);
+        IAS_BIN_END(BIN_W);
+        rw.sym_timed[BIN_W] = true;
     }
     if (bl.count[BIN_B1]) {
+        IAS_BIN_BEGIN(BIN_B1);
         int n = (int)bl.count[BIN_B1];
         auto k = k_sym_hash<AV, BV, 256, 256, SYM_B1_TSIZE>;
         size_t sm = (size_t)SYM_B1_TSIZE * sizeof(int);
         IAS_TRY(opt_in_smem(k, sm));
         IAS_LAUNCH(k, n, 256, sm, bl.rows_of(BIN_B1), n, r0, A, B, rw.nnz_row.p);
+        IAS_BIN_END(BIN_B1);
+        rw.sym_timed[BIN_B1] = true;
     }
     if (bl.count[BIN_B2]) {
+        IAS_BIN_BEGIN(BIN_B2);
         int n = (int)bl.count[BIN_B2];
         auto k = k_sym_hash<AV, BV, 1024, 1024, SYM_B2_TSIZE>;
         size_t sm = (size_t)SYM_B2_TSIZE * sizeof(int);
         IAS_TRY(opt_in_smem(k, sm));
         IAS_LAUNCH(k, n, 1024, sm, bl.rows_of(BIN_B2), n, r0, A, B, rw.nnz_row.p);
+        IAS_BIN_END(BIN_B2);
+        rw.sym_timed[BIN_B2] = true;
     }
     if (bl.count[BIN_G]) {
+        IAS_BIN_BEGIN(BIN_G);
         int n = (int)bl.count[BIN_G];
         IAS_TRY(ensure_gwork(rw, ncols_b, n));
         IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
         IAS_LAUNCH((k_sym_global<AV, BV, G_BLOCK>), rw.gslots, G_BLOCK, 0, bl.rows_of(BIN_G), n, r0, A, B, rw.nnz_row.p, rw.gwork.p,
                    GLayout::make(ncols_b), rw.cursor.p);
+        IAS_BIN_END(BIN_G);
+        rw.sym_timed[BIN_G] = true;
     }
     if (st) {
         st->products = rw.products;
@@ -177,40 +212,55 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
     if (out.rp) out.rp += b0;
     if (out.nnz_row) out.nnz_row += b0;
     if (bl.count[BIN_T]) {
+        IAS_BIN_BEGIN(8 + BIN_T);
         int m = (int)bl.count[BIN_T];
         int cap = std::max(1, (int)h[NBINS]);
         auto k = k_num_tiny<AV, BV, TINY_BLOCK>;
         size_t sm = (size_t)TINY_BLOCK * cap * (sizeof(double) + sizeof(int));
         IAS_TRY(opt_in_smem(k, sm));
         IAS_LAUNCH(k, grid_for(m, TINY_BLOCK), TINY_BLOCK, sm, bl.rows_of(BIN_T), m, r0, A, B, out, c_ci, c_v, cap);
+        IAS_BIN_END(8 + BIN_T);
+        rw.num_timed[BIN_T] = true;
     }
     if (bl.count[BIN_W]) {
+        IAS_BIN_BEGIN(8 + BIN_W);
         int m = (int)bl.count[BIN_W];
         auto k = k_num_hash<AV, BV, 32, 256, NUM_W_TSIZE>;
         size_t sm = (size_t)8 * NUM_W_TSIZE * 12;
         IAS_TRY(opt_in_smem(k, sm));
         IAS_LAUNCH(k, grid_for(m, 8), 256, sm, bl.rows_of(BIN_W), m, r0, A, B, out, c_ci, c_v);
+        IAS_BIN_END(8 + BIN_W);
+        rw.num_timed[BIN_W] = true;
     }
     if (bl.count[BIN_B1]) {
+        IAS_BIN_BEGIN(8 + BIN_B1);
         int m = (int)bl.count[BIN_B1];
         auto k = k_num_hash<AV, BV, 256, 256, NUM_B1_TSIZE>;
         size_t sm = (size_t)NUM_B1_TSIZE * 12;
         IAS_TRY(opt_in_smem(k, sm));
         IAS_LAUNCH(k, m, 256, sm, bl.rows_of(BIN_B1), m, r0, A, B, out, c_ci, c_v);
+        IAS_BIN_END(8 + BIN_B1);
+        rw.num_timed[BIN_B1] = true;
     }
     if (bl.count[BIN_B2]) {
+        IAS_BIN_BEGIN(8 + BIN_B2);
         int m = (int)bl.count[BIN_B2];
         auto k = k_num_hash<AV, BV, 1024, 1024, NUM_B2_TSIZE>;
         size_t sm = (size_t)NUM_B2_TSIZE * 12;
         IAS_TRY(opt_in_smem(k, sm));
         IAS_LAUNCH(k, m, 1024, sm, bl.rows_of(BIN_B2), m, r0, A, B, out, c_ci, c_v);
+        IAS_BIN_END(8 + BIN_B2);
+        rw.num_timed[BIN_B2] = true;
     }
     if (bl.count[BIN_G]) {
+        IAS_BIN_BEGIN(8 + BIN_G);
         int m = (int)bl.count[BIN_G];
         IAS_TRY(ensure_gwork(rw, ncols_b, m));
         IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
         IAS_LAUNCH((k_num_global<AV, BV, G_BLOCK>), rw.gslots, G_BLOCK, 0, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
                    GLayout::make(ncols_b), rw.cursor.p);
+        IAS_BIN_END(8 + BIN_G);
+        rw.num_timed[BIN_G] = true;
     }
     (void)st;
     return IAS_OK;
@@ -276,6 +326,8 @@ int spgemm_materialise(const AV &av, const BV &bv, double avg_a_row, int ncols_b
     IAS_TRY(numeric_rows(av, bv, rw, 0, nrows, ncols_b, out, ci.p, cv.p, &local));
     IAS_CUDA(cudaEventRecord(c.ev[4], c.stream));
     IAS_CUDA(cudaStreamSynchronize(c.stream));
+    collect_bin_times(rw);
+    for (int b = 0; b < 8; ++b) { local.ms_bin_sym[b] = rw.ms_bin_sym[b]; local.ms_bin_num[b] = rw.ms_bin_num[b]; }
 
     C->nnz = nnz;
     C->row_ptr_dev = rp.release(); C->col_ind_dev = ci.release(); C->values_dev = cv.release();

@@ -54,6 +54,7 @@ class SpgemmStats(C.Structure):
     _fields_ = [("products", C.c_longlong), ("nnz", C.c_longlong), ("ms_total", C.c_double),
                 ("ms_analyze", C.c_double), ("ms_symbolic", C.c_double), ("ms_scan", C.c_double),
                 ("ms_numeric", C.c_double), ("ms_consume", C.c_double),
+                ("ms_bin_sym", C.c_double * 8), ("ms_bin_num", C.c_double * 8),
                 ("sym_bin_rows", C.c_longlong * 8), ("num_bin_rows", C.c_longlong * 8),
                 ("batches", C.c_int), ("kernel_launches", C.c_int), ("checksum", C.c_double),
                 ("structure_hash", C.c_ulonglong)]
@@ -61,7 +62,8 @@ class SpgemmStats(C.Structure):
     def as_dict(self):
         return {"products": self.products, "nnz": self.nnz, "ms_total": self.ms_total,
                 "ms_analyze": self.ms_analyze, "ms_symbolic": self.ms_symbolic, "ms_scan": self.ms_scan,
-                "ms_numeric": self.ms_numeric, "sym_bin_rows": list(self.sym_bin_rows)[:6],
+                "ms_numeric": self.ms_numeric, "ms_bin_sym": list(self.ms_bin_sym)[:6],
+                "ms_bin_num": list(self.ms_bin_num)[:6], "sym_bin_rows": list(self.sym_bin_rows)[:6],
                 "num_bin_rows": list(self.num_bin_rows)[:6], "batches": self.batches,
                 "kernel_launches": self.kernel_launches, "checksum": self.checksum,
                 "structure_hash": self.structure_hash}
@@ -416,9 +418,9 @@ class Engine:
         return h.row, h.col, rp, ci, v
 
     # -- synthetic operands ----------------------------------------------------------------
-    def gen_poisson2d(self, n_grid):
+    def gen_poisson2d(self, nx, ny=None):
         d = CsrMatrixDev()
-        self._ck(self.lib.ias_gen_poisson2d(C.c_int(n_grid), C.byref(d)))
+        self._ck(self.lib.ias_gen_poisson2d(C.c_int(nx), C.c_int(nx if ny is None else ny), C.byref(d)))
         return DeviceCsr(self, d)
 
     def gen_uniform(self, n, per_row, seed=1):

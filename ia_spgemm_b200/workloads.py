@@ -41,14 +41,15 @@ def row_index(row_ptr):
     return np.repeat(np.arange(n, dtype=np.int64), np.diff(row_ptr).astype(np.int64))
 
 
-def poisson2d(n_grid):
-    """2-D 5-point Poisson operator on an n_grid x n_grid grid, row-major node order."""
-    n = n_grid * n_grid
+def poisson2d(nx, ny=None):
+    """2-D 5-point Poisson operator on an nx x ny grid (ny defaults to nx), row-major node order."""
+    ny = nx if ny is None else ny
+    n = nx * ny
     r = np.arange(n, dtype=np.int64)
-    x = r % n_grid
-    y = r // n_grid
-    cand = np.stack([r - n_grid, r - 1, r, r + 1, r + n_grid], axis=1)
-    mask = np.stack([y > 0, x > 0, np.ones(n, bool), x < n_grid - 1, y < n_grid - 1], axis=1)
+    x = r % nx
+    y = r // nx
+    cand = np.stack([r - nx, r - 1, r, r + 1, r + nx], axis=1)
+    mask = np.stack([y > 0, x > 0, np.ones(n, bool), x < nx - 1, y < ny - 1], axis=1)
     vals = np.broadcast_to(np.array([-1.0, -1.0, 4.0, -1.0, -1.0]), (n, 5))
     row_ptr = np.zeros(n + 1, dtype=np.int64)
     np.cumsum(mask.sum(axis=1), out=row_ptr[1:])

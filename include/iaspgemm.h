@@ -101,6 +101,8 @@ typedef struct {
     long long nnz;              /* nnz(C) of the processed rows */
     double ms_total;            /* symbolic + allocation + numeric (+ consumer in streaming mode) */
     double ms_analyze, ms_symbolic, ms_scan, ms_numeric, ms_consume;
+    double ms_bin_sym[8];       /* device time of each symbolic bin kernel (same bin order as below) */
+    double ms_bin_num[8];       /* device time of each numeric bin kernel, summed over batches */
     long long sym_bin_rows[8];  /* rows per symbolic bin: empty, tiny, warp, cta-s, cta-l, global, -, - */
     long long num_bin_rows[8];  /* rows per numeric bin */
     int batches;                /* row batches used (1 unless streaming) */
@@ -218,7 +220,7 @@ void ias_free_host_csr(IasCsrMatrix *m);
 
 /* ---------------------------------------------------------------- synthetic operands (device) */
 /* BASELINE.json configs, bit-identical to ia_spgemm_b200/workloads.py */
-int ias_gen_poisson2d(int n_grid, IasCsrMatrixDev *out);
+int ias_gen_poisson2d(int nx, int ny, IasCsrMatrixDev *out);   /* nx*ny nodes, row-major node order */
 int ias_gen_uniform(int n, int per_row, int seed, IasCsrMatrixDev *out);
 int ias_gen_rmat(int scale, int edge_factor, int seed, double a, double b, double c,
                  IasCsrMatrixDev *out);

@@ -51,7 +51,7 @@ def test_struct_layouts_match_reference_format_h():
         assert (S.choice.offset, S.row.offset, S.col.offset, S.nnz.offset) == (0, 4, 8, 12)
     assert E.CsrMatrix.row_ind.offset == 16 and E.CsrMatrix.values.offset == 32
     assert E.DiaDev.num_diagonals.offset == 12 and E.DiaDev.values_dev.offset == 32
-    assert C.sizeof(E.SpgemmStats) == 8 * 8 + 16 * 8 + 2 * 4 + 8 + 8
+    assert C.sizeof(E.SpgemmStats) == 8 * 8 + 16 * 8 + 16 * 8 + 2 * 4 + 8 + 8
 
 
 def test_no_cpu_fallback(lib):

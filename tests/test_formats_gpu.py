@@ -25,7 +25,7 @@ CASES = [
     ("poisson40", lambda: W.poisson2d(40)),
     ("banded", lambda: W.banded(700, [-9, -1, 0, 2, 17], seed=4)),
     ("uniform", lambda: W.uniform_rows(3000, 8, seed=3)),
-    ("irregular", lambda: W.random_sparse(257, 300, 0.03, seed=5)),
+    ("irregular", lambda: W.random_sparse(257, 257, 0.03, seed=5)),
     ("unsorted", lambda: W.random_sparse(120, 120, 0.08, seed=6, sort_columns=False)),
     ("rmat9", lambda: W.rmat(9, 8, seed=2)),
 ]
@@ -55,7 +55,7 @@ def test_csr_to_dia_matches_oracle(eng, oracle, name, make):
     dA.close()
 
 
-@pytest.mark.parametrize("name,make", CASES[:3] + CASES[4:5], ids=[c[0] for c in CASES[:3] + CASES[4:5]])
+@pytest.mark.parametrize("name,make", CASES[:2] + CASES[4:5], ids=[c[0] for c in CASES[:2] + CASES[4:5]])
 def test_dia_mul_dia_matches_oracle(eng, oracle, name, make):
     A = make()
     want_a = oracle.csr_to_dia(*A, gate=1e9)
@@ -261,7 +261,7 @@ def test_engine_loader_golden(eng, golden, mtx_dir, name):
 
 
 def test_device_generators_are_bit_identical_to_numpy(eng):
-    for dev, host in ((eng.gen_poisson2d(37), W.poisson2d(37)),
+    for dev, host in ((eng.gen_poisson2d(37), W.poisson2d(37)), (eng.gen_poisson2d(16, 48), W.poisson2d(16, 48)),
                       (eng.gen_uniform(5000, 16, seed=1), W.uniform_rows(5000, 16, seed=1)),
                       (eng.gen_uniform(40, 16, seed=3), W.uniform_rows(40, 16, seed=3)),     # collisions -> redraws
                       (eng.gen_rmat(12, 16, seed=1), W.rmat(12, 16, seed=1)),
