@@ -101,6 +101,13 @@ __global__ void __launch_bounds__(BLOCK) k_dia_mul_dia(int rows, int a_cols, int
     }
 }
 
+// diagonal_ind[offset + rows - 1] = slot for the c_nd present diagonals (the rest stays 0)
+__global__ void k_scatter_diag_ind(int c_nd, int rows, const int *__restrict__ offsets, int *__restrict__ diag_ind)
+{
+    int d = blockIdx.x * blockDim.x + threadIdx.x;
+    if (d < c_nd) diag_ind[(long long)offsets[d] + rows - 1] = d;
+}
+
 // diagonal-major -> the reference's row-major [i*nd + slot] (for downloads / parity checks)
 __global__ void __launch_bounds__(256) k_dia_to_row_major(int rows, int nd, const double *__restrict__ in, double *__restrict__ out)
 {
@@ -222,18 +229,19 @@ int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, do
     C->num_diagonals = c_nd;
 
     int span = A->row + B->col - 1;
-    std::vector<int> h_di((size_t)std::max(span, 1), 0);
-    for (int d = 0; d < c_nd; ++d) h_di[(size_t)c_off[d] + A->row - 1] = d;     // dia:150-158
     DBuf<int> di, off, d_pstart;
     DBuf<unsigned> d_pairs;
     DBuf<double> val;
-    IAS_TRY(di.alloc(h_di.size()));
+    IAS_TRY(di.alloc((size_t)std::max(span, 1)));
     IAS_TRY(off.alloc((size_t)std::max(c_nd, 1)));
     IAS_TRY(d_pstart.alloc(pstart.size()));
     IAS_TRY(d_pairs.alloc(std::max<size_t>(pab.size(), 1)));
     IAS_TRY(val.alloc((size_t)A->row * c_nd));
-    IAS_CUDA(cudaMemcpyAsync(di.p, h_di.data(), sizeof(int) * h_di.size(), cudaMemcpyHostToDevice, s));
-    if (c_nd) IAS_CUDA(cudaMemcpyAsync(off.p, c_off.data(), sizeof(int) * c_nd, cudaMemcpyHostToDevice, s));
+    IAS_CUDA(cudaMemsetAsync(di.p, 0, sizeof(int) * (size_t)std::max(span, 1), s));
+    if (c_nd) {
+        IAS_CUDA(cudaMemcpyAsync(off.p, c_off.data(), sizeof(int) * c_nd, cudaMemcpyHostToDevice, s));
+        IAS_LAUNCH(k_scatter_diag_ind, grid_for(c_nd, 256), 256, 0, c_nd, A->row, off.p, di.p);     // dia:150-158
+    }
     IAS_CUDA(cudaMemcpyAsync(d_pstart.p, pstart.data(), sizeof(int) * pstart.size(), cudaMemcpyHostToDevice, s));
     if (!pab.empty()) IAS_CUDA(cudaMemcpyAsync(d_pairs.p, pab.data(), sizeof(unsigned) * pab.size(), cudaMemcpyHostToDevice, s));
 

@@ -146,7 +146,8 @@ int ias_ell_mul_ell_dev(const IasEllDev *A, const IasEllDev *B, IasEllDev *C, do
     IAS_CUDA(cudaEventRecord(c.ev[1], c.stream));
     RangeWork rw;
     double avg = A->row ? (double)A->nnz / A->row : 0.0;
-    IAS_TRY(symbolic_range(av, bv, 0, nrows, B->col, avg, rw, nullptr));
+    bool same = A->col_ind_dev == B->col_ind_dev && A->nnz_row_dev == B->nnz_row_dev;
+    IAS_TRY(symbolic_range(av, bv, 0, nrows, B->col, avg, rw, nullptr, same, B->row));
     int w = 0;
     IAS_TRY(max_of_counts(rw.nnz_row.p, nrows, &w));          // C width = max nnz(C_i), ell:117-128
     // total nnz
@@ -235,7 +236,8 @@ int ias_coo_mul_coo_dev(const IasCooDev *A, const IasCooDev *B, IasCooDev *C, do
     IasCsr64Dev c64;
     IasSpgemmStats st;
     double avg = A->row ? (double)A->nnz / A->row : 0.0;
-    IAS_TRY(spgemm_materialise(av, bv, avg, B->col, 0, A->row, &c64, &st));
+    bool same = A->col_ind_dev == B->col_ind_dev && A->row_offset_dev == B->row_offset_dev;
+    IAS_TRY(spgemm_materialise(av, bv, avg, B->col, 0, A->row, &c64, &st, same, B->row));
     DBuf<int> ri;
     IAS_TRY(ri.alloc((size_t)c64.nnz));
     IAS_CUDA(cudaEventRecord(c.ev[5], c.stream));

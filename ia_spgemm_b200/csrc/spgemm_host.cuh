@@ -68,6 +68,7 @@ struct RangeWork {
     long long sym_hist[8] = {0};
     long long num_hist[8] = {0};
     int max_tiny_nnz = 0, max_nnz = 0;
+    int b_canonical = 0;           // every B row strictly increasing in column (enables the merge kernels)
     bool sym_timed[8] = {false};   // which bin kernels were launched (their ev_bin pairs are pending)
     bool num_timed[8] = {false};
     double ms_bin_sym[8] = {0};
@@ -114,7 +115,8 @@ inline int ensure_gwork(RangeWork &rw, int ncols, long long nrows_g)
 
 // analysis + symbolic over [r0, r1): fills rw.ub, rw.nnz_row (exact nnz(C_i)), products
 template <class AV, class BV>
-int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double avg_a_row, RangeWork &rw, IasSpgemmStats *st)
+int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double avg_a_row, RangeWork &rw, IasSpgemmStats *st,
+                   bool b_is_a = false, int b_rows = 0)
 {
     Ctx &c = ctx();
     int nrows = r1 - r0;
@@ -130,9 +132,17 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
         IAS_LAUNCH((k_row_ub_warp<AV, BV>), grid_for((long long)nrows * 32, 256), 256, 0, nrows, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p);
     else
         IAS_LAUNCH((k_row_ub_thread<AV, BV>), grid_for(nrows, 256), 256, 0, nrows, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p);
-    long long h[NBINS + 1];
-    IAS_TRY(read_hist(rw, NBINS + 1, h));
+    // canonical B: the analyze kernel has just checked the rows of A it walked; that covers B only when B is A
+    // and the range is the whole matrix, otherwise B gets its own pass (4 B per entry of B)
+    bool covered = b_is_a && r0 == 0 && r1 == b_rows;
+    if (!covered && b_rows > 0) {
+        IAS_CUDA(cudaMemsetAsync(rw.hist.p + NBINS + 1, 0, sizeof(unsigned long long), c.stream));
+        IAS_LAUNCH((k_rows_canonical<BV>), grid_for(b_rows, 256), 256, 0, b_rows, B, rw.hist.p + NBINS + 1);
+    }
+    long long h[NBINS + 2];
+    IAS_TRY(read_hist(rw, NBINS + 2, h));
     rw.products = h[NBINS];
+    rw.b_canonical = (b_rows > 0 && h[NBINS + 1] == 0) ? 1 : 0;
     for (int b = 0; b < NBINS; ++b) rw.sym_hist[b] = h[b];
     IAS_CUDA(cudaEventRecord(c.ev[1], c.stream));
 
@@ -141,7 +151,7 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
     if (bl.count[BIN_T]) {
         IAS_BIN_BEGIN(BIN_T);
         int n = (int)bl.count[BIN_T];
-        IAS_LAUNCH((k_sym_tiny<AV, BV, TINY_BLOCK>), grid_for(n, TINY_BLOCK), TINY_BLOCK, 0, bl.rows_of(BIN_T), n, r0, A, B, rw.nnz_row.p);
+        IAS_LAUNCH((k_sym_tiny<AV, BV, TINY_BLOCK>), grid_for(n, TINY_BLOCK), TINY_BLOCK, 0, bl.rows_of(BIN_T), n, r0, A, B, rw.nnz_row.p, rw.b_canonical);
         IAS_BIN_END(BIN_T);
         rw.sym_timed[BIN_T] = true;
     }
@@ -218,7 +228,7 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         auto k = k_num_tiny<AV, BV, TINY_BLOCK>;
         size_t sm = (size_t)TINY_BLOCK * cap * (sizeof(double) + sizeof(int));
         IAS_TRY(opt_in_smem(k, sm));
-        IAS_LAUNCH(k, grid_for(m, TINY_BLOCK), TINY_BLOCK, sm, bl.rows_of(BIN_T), m, r0, A, B, out, c_ci, c_v, cap);
+        IAS_LAUNCH(k, grid_for(m, TINY_BLOCK), TINY_BLOCK, sm, bl.rows_of(BIN_T), m, r0, A, B, out, c_ci, c_v, cap, rw.b_canonical);
         IAS_BIN_END(8 + BIN_T);
         rw.num_timed[BIN_T] = true;
     }
@@ -294,7 +304,7 @@ inline double ev_ms(int a, int b)
 // of C, numeric pass, sort; operands already resident.
 template <class AV, class BV>
 int spgemm_materialise(const AV &av, const BV &bv, double avg_a_row, int ncols_b, int r0, int r1, IasCsr64Dev *C,
-                       IasSpgemmStats *st)
+                       IasSpgemmStats *st, bool b_is_a = false, int b_rows = 0)
 {
     Ctx &c = ctx();
     long long l0 = c.launches;
@@ -307,7 +317,7 @@ int spgemm_materialise(const AV &av, const BV &bv, double avg_a_row, int ncols_b
     IAS_CUDA(cudaEventRecord(c.ev[0], c.stream));
     IAS_CUDA(cudaEventRecord(c.ev[1], c.stream));
     RangeWork rw;
-    IAS_TRY(symbolic_range(av, bv, r0, r1, ncols_b, avg_a_row, rw, &local));
+    IAS_TRY(symbolic_range(av, bv, r0, r1, ncols_b, avg_a_row, rw, &local, b_is_a, b_rows));
     IAS_CUDA(cudaEventRecord(c.ev[2], c.stream));
 
     DBuf<long long> rp;
