@@ -1,6 +1,8 @@
 // spgemm_host.cuh -- host orchestration of the Gustavson pipeline for one row range of C.
 // Templated on the operand views so that the CSR, ELL and COO entry points share it.
 #pragma once
+#include <stdlib.h>
+
 #include <algorithm>
 
 #include <thrust/iterator/transform_iterator.h>
@@ -69,6 +71,11 @@ struct RangeWork {
     long long num_hist[8] = {0};
     int max_tiny_nnz = 0, max_nnz = 0;
     int b_canonical = 0;           // every B row strictly increasing in column (enables the merge kernels)
+    int max_tiny_na = 0;           // longest A row / largest upper bound among tiny rows
+    int max_tiny_ub = 0;
+    bool tiny_only = false;        // every non-empty row is tiny: numeric bins == symbolic bins
+    DBuf<int> tiny_list;           // kept row list of the tiny bin (tiny_only with empty rows)
+    bool tiny_identity = false;
     bool sym_timed[8] = {false};   // which bin kernels were launched (their ev_bin pairs are pending)
     bool num_timed[8] = {false};
     double ms_bin_sym[8] = {0};
@@ -139,19 +146,38 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
         IAS_CUDA(cudaMemsetAsync(rw.hist.p + NBINS + 1, 0, sizeof(unsigned long long), c.stream));
         IAS_LAUNCH((k_rows_canonical<BV>), grid_for(b_rows, 256), 256, 0, b_rows, B, rw.hist.p + NBINS + 1);
     }
-    long long h[NBINS + 2];
-    IAS_TRY(read_hist(rw, NBINS + 2, h));
+    long long h[NBINS + 4];
+    IAS_TRY(read_hist(rw, NBINS + 4, h));
     rw.products = h[NBINS];
     rw.b_canonical = (b_rows > 0 && h[NBINS + 1] == 0) ? 1 : 0;
+    rw.max_tiny_na = (int)h[NBINS + 2];
+    rw.max_tiny_ub = (int)h[NBINS + 3];
+    // every non-empty row is tiny: the numeric bins equal the symbolic ones (ub <= 32 decides), no re-classification
+    rw.tiny_only = h[BIN_T] > 0 && h[BIN_T] + h[BIN_EMPTY] == nrows;
     for (int b = 0; b < NBINS; ++b) rw.sym_hist[b] = h[b];
     IAS_CUDA(cudaEventRecord(c.ev[1], c.stream));
-
+    if (st) {
+        st->products = rw.products;
+        for (int b = 0; b < 8; ++b) st->sym_bin_rows[b] = b < NBINS ? rw.sym_hist[b] : 0;
+    }
+    IAS_CUDA(cudaMemsetAsync(rw.hist.p + 12, 0, sizeof(unsigned long long), c.stream));      // hist[12]: max nnz(C_i) among tiny rows
     BinLists bl;
     IAS_TRY(build_bin_lists(nrows, rw.bin.p, h, bl));
+    if (rw.tiny_only) {
+        rw.tiny_identity = bl.only_bin == BIN_T;
+        if (!rw.tiny_identity) {                  // tiny + empty rows: keep the tiny bin's row list for the numeric pass
+            IAS_TRY(rw.tiny_list.alloc((size_t)bl.count[BIN_T]));
+            IAS_CUDA(cudaMemcpyAsync(rw.tiny_list.p, bl.rows_of(BIN_T), sizeof(int) * (size_t)bl.count[BIN_T], cudaMemcpyDeviceToDevice, c.stream));
+        }
+    }
     if (bl.count[BIN_T]) {
         IAS_BIN_BEGIN(BIN_T);
         int n = (int)bl.count[BIN_T];
-        IAS_LAUNCH((k_sym_tiny<AV, BV, TINY_BLOCK>), grid_for(n, TINY_BLOCK), TINY_BLOCK, 0, bl.rows_of(BIN_T), n, r0, A, B, rw.nnz_row.p, rw.b_canonical);
+        int merge = rw.max_tiny_na <= 4 ? 4 : rw.max_tiny_na <= 6 ? 6 : 8;
+        const int *rl = bl.rows_of(BIN_T);
+        if (merge == 4) IAS_LAUNCH((k_sym_tiny<AV, BV, TINY_BLOCK, 4>), grid_for(n, TINY_BLOCK), TINY_BLOCK, 0, rl, n, r0, A, B, rw.nnz_row.p, rw.b_canonical, rw.hist.p + 12);
+        else if (merge == 6) IAS_LAUNCH((k_sym_tiny<AV, BV, TINY_BLOCK, 6>), grid_for(n, TINY_BLOCK), TINY_BLOCK, 0, rl, n, r0, A, B, rw.nnz_row.p, rw.b_canonical, rw.hist.p + 12);
+        else IAS_LAUNCH((k_sym_tiny<AV, BV, TINY_BLOCK, 8>), grid_for(n, TINY_BLOCK), TINY_BLOCK, 0, rl, n, r0, A, B, rw.nnz_row.p, rw.b_canonical, rw.hist.p + 12);
         IAS_BIN_END(BIN_T);
         rw.sym_timed[BIN_T] = true;
     }
@@ -205,18 +231,26 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
 // numeric bins of local rows [b0, b1) of the range
 template <class AV, class BV>
 int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int ncols_b, const OutMap &out_in,
-                 int *c_ci, double *c_v, IasSpgemmStats *st)
+                 int *c_ci, double *c_v, IasSpgemmStats *st, int tiny_max_nnz = 0)
 {
     Ctx &c = ctx();
     int n = b1 - b0;
     if (n <= 0) return IAS_OK;
-    IAS_CUDA(cudaMemsetAsync(rw.hist.p, 0, 16 * sizeof(unsigned long long), c.stream));
-    IAS_LAUNCH(k_classify_num, grid_for(n, 256), 256, 0, n, rw.ub.p + b0, rw.nnz_row.p + b0, rw.bin.p + b0, rw.hist.p);
-    long long h[NBINS + 2];
-    IAS_TRY(read_hist(rw, NBINS + 2, h));
-    for (int b = 0; b < NBINS; ++b) rw.num_hist[b] += h[b];
+    long long h[NBINS + 2] = {0};
     BinLists bl;
-    IAS_TRY(build_bin_lists(n, rw.bin.p + b0, h, bl));
+    if (rw.tiny_only && b0 == 0 && b1 == rw.nrows && tiny_max_nnz > 0) {
+        // numeric bins == symbolic bins; the largest tiny nnz(C_i) came back with the scan total
+        h[BIN_T] = rw.sym_hist[BIN_T]; h[BIN_EMPTY] = rw.sym_hist[BIN_EMPTY]; h[NBINS] = tiny_max_nnz;
+        for (int b = 0; b < NBINS; ++b) { rw.num_hist[b] += h[b]; bl.count[b] = h[b]; }
+        bl.only_bin = rw.tiny_identity ? BIN_T : -1;
+        if (!rw.tiny_identity) { bl.list.p = rw.tiny_list.release(); bl.offset[BIN_T] = 0; }
+    } else {
+        IAS_CUDA(cudaMemsetAsync(rw.hist.p, 0, 16 * sizeof(unsigned long long), c.stream));
+        IAS_LAUNCH(k_classify_num, grid_for(n, 256), 256, 0, n, rw.ub.p + b0, rw.nnz_row.p + b0, rw.bin.p + b0, rw.hist.p);
+        IAS_TRY(read_hist(rw, NBINS + 2, h));
+        for (int b = 0; b < NBINS; ++b) rw.num_hist[b] += h[b];
+        IAS_TRY(build_bin_lists(n, rw.bin.p + b0, h, bl));
+    }
     int r0 = rw.r0 + b0;                         // lists hold indices local to [b0, b1)
     OutMap out = out_in;
     if (out.rp) out.rp += b0;
@@ -225,8 +259,9 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         IAS_BIN_BEGIN(8 + BIN_T);
         int m = (int)bl.count[BIN_T];
         int cap = std::max(1, (int)h[NBINS]);
-        auto k = k_num_tiny<AV, BV, TINY_BLOCK>;
         size_t sm = (size_t)TINY_BLOCK * cap * (sizeof(double) + sizeof(int));
+        int merge = rw.max_tiny_na <= 4 ? 4 : rw.max_tiny_na <= 6 ? 6 : 8;
+        auto k = merge == 4 ? k_num_tiny<AV, BV, TINY_BLOCK, 4> : merge == 6 ? k_num_tiny<AV, BV, TINY_BLOCK, 6> : k_num_tiny<AV, BV, TINY_BLOCK, 8>;
         IAS_TRY(opt_in_smem(k, sm));
         IAS_LAUNCH(k, grid_for(m, TINY_BLOCK), TINY_BLOCK, sm, bl.rows_of(BIN_T), m, r0, A, B, out, c_ci, c_v, cap, rw.b_canonical);
         IAS_BIN_END(8 + BIN_T);
@@ -324,8 +359,10 @@ int spgemm_materialise(const AV &av, const BV &bv, double avg_a_row, int ncols_b
     IAS_TRY(rp.alloc((size_t)nrows + 1));
     IAS_TRY(scan_row_ptr(rw.nnz_row.p, nrows, rp.p));
     IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 32, rp.p + nrows, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 33, rw.hist.p + 12, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
     IAS_CUDA(cudaStreamSynchronize(c.stream));
     long long nnz = c.h_scalars[32];
+    int tiny_max_nnz = (int)c.h_scalars[33];
     DBuf<int> ci;
     DBuf<double> cv;
     IAS_TRY(ci.alloc((size_t)nnz));
@@ -333,7 +370,7 @@ int spgemm_materialise(const AV &av, const BV &bv, double avg_a_row, int ncols_b
     IAS_CUDA(cudaEventRecord(c.ev[3], c.stream));
 
     OutMap out{rp.p, 0, nullptr, 0};
-    IAS_TRY(numeric_rows(av, bv, rw, 0, nrows, ncols_b, out, ci.p, cv.p, &local));
+    IAS_TRY(numeric_rows(av, bv, rw, 0, nrows, ncols_b, out, ci.p, cv.p, &local, tiny_max_nnz));
     IAS_CUDA(cudaEventRecord(c.ev[4], c.stream));
     IAS_CUDA(cudaStreamSynchronize(c.stream));
     collect_bin_times(rw);

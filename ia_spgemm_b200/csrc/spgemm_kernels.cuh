@@ -118,12 +118,14 @@ __global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, 
 {
     __shared__ unsigned s_cnt[NBINS];
     __shared__ unsigned long long s_sum;
+    __shared__ int s_max[2];
     if (threadIdx.x < NBINS) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x == NBINS) s_sum = 0;
+    if (threadIdx.x < 2) s_max[threadIdx.x] = 0;
     __syncthreads();
     int li = blockIdx.x * blockDim.x + threadIdx.x;
     long long ub = 0;
-    int bin = -1;
+    int bin = -1, tiny_na = 0, tiny_ub = 0;
     if (li < nrows) {
         int i = r0 + li;
         typename AV::off_t pe = A.end(i);
@@ -136,10 +138,18 @@ __global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, 
         }
         if (unsorted) g_hist[NBINS + 1] = 1;      // A (== B for A^2) is not canonical
         bin = sym_bin_of(ub);
+        tiny_na = (bin == BIN_T) ? (int)(pe - A.begin(i)) : 0;
+        tiny_ub = (bin == BIN_T) ? (int)ub : 0;
         ub_out[li] = ub > 0x7fffffffLL ? 0x7fffffff : (int)ub;
         bin_out[li] = (unsigned char)bin;
     }
+    tiny_na = __reduce_max_sync(0xffffffffu, tiny_na);
+    tiny_ub = __reduce_max_sync(0xffffffffu, tiny_ub);
+    if ((threadIdx.x & 31) == 0 && tiny_na > 0) { atomicMax(&s_max[0], tiny_na); atomicMax(&s_max[1], tiny_ub); }
     block_hist(bin, ub, s_cnt, &s_sum, g_hist);
+    // one pair of global atomics per CTA, and only when it would raise the maximum (plain read is a hint)
+    if (threadIdx.x < 2 && s_max[threadIdx.x] > 0 && (unsigned long long)s_max[threadIdx.x] > g_hist[NBINS + 2 + threadIdx.x])
+        atomicMax(&g_hist[NBINS + 2 + threadIdx.x], (unsigned long long)s_max[threadIdx.x]);
 }
 
 // one warp per row (long / skewed A rows)
@@ -172,6 +182,10 @@ __global__ void __launch_bounds__(256) k_row_ub_warp(int nrows, int r0, AV A, BV
             bin = sym_bin_of(ub);
             ub_out[li] = ub > 0x7fffffffLL ? 0x7fffffff : (int)ub;
             bin_out[li] = (unsigned char)bin;
+            if (bin == BIN_T) {
+                atomicMax(&g_hist[NBINS + 2], (unsigned long long)(pe - pa));
+                atomicMax(&g_hist[NBINS + 3], (unsigned long long)ub);
+            }
         } else {
             ub = 0;                                  // the row's total is counted once
         }
@@ -218,28 +232,32 @@ static __global__ void k_iota(int n, int *out)
 
 // ---------------------------------------------------------------- tiny rows: one thread per row
 // Two per-thread algorithms:
-//   merge   (B canonical and the A row has <= TINY_MERGE entries): the row of C is the k-way merge of the
+//   merge   (B canonical and the A row has <= MERGE entries): the row of C is the k-way merge of the
 //           sorted B rows it touches.  One cursor per A entry lives in registers (fully unrolled); every
 //           step takes the smallest head column, adds up all heads equal to it (in A order, the order
-//           CSR_MUL_CSR accumulates in, csr:150-170) and advances them.  Output comes out column sorted:
-//           no search, no sort, ~30 instructions per product instead of ~100.
+//           CSR_MUL_CSR accumulates in, csr:150-170) and advances them, prefetching the next head's
+//           column and value.  Output comes out column sorted: no search, no sort.
 //   list    (anything else): unsorted private list with linear search, insertion-sorted at the end.
-constexpr int TINY_MERGE = 8;
-
-template <class BV>
+// MERGE is a template parameter (4 / 6 / 8) picked by the host from the longest A row in the bin.
+template <class BV, int MERGE, bool WITH_VALUES>
 struct TinyCursors {
-    typename BV::off_t q[TINY_MERGE], qe[TINY_MERGE];
-    int hc[TINY_MERGE];
+    typename BV::off_t q[MERGE], qe[MERGE];
+    int hc[MERGE];
+    double hv[WITH_VALUES ? MERGE : 1];
     template <class AV>
     __device__ __forceinline__ void init(const AV &A, const BV &B, typename AV::off_t pa, int na)
     {
 #pragma unroll
-        for (int a = 0; a < TINY_MERGE; ++a) {
+        for (int a = 0; a < MERGE; ++a) {
             hc[a] = 0x7fffffff; q[a] = 0; qe[a] = 0;
+            if (WITH_VALUES) hv[a] = 0.0;
             if (a < na) {
                 int j = __ldg(A.ci + pa + a);
                 q[a] = B.begin(j); qe[a] = B.end(j);
-                if (q[a] < qe[a]) hc[a] = __ldg(B.ci + q[a]);
+                if (q[a] < qe[a]) {
+                    hc[a] = __ldg(B.ci + q[a]);
+                    if (WITH_VALUES) hv[a] = __ldg(B.v + q[a]);
+                }
             }
         }
     }
@@ -247,36 +265,67 @@ struct TinyCursors {
     {
         int m = hc[0];
 #pragma unroll
-        for (int a = 1; a < TINY_MERGE; ++a) m = min(m, hc[a]);
+        for (int a = 1; a < MERGE; ++a) m = min(m, hc[a]);
         return m;
     }
     __device__ __forceinline__ void advance(const BV &B, int a)
     {
         ++q[a];
-        hc[a] = q[a] < qe[a] ? __ldg(B.ci + q[a]) : 0x7fffffff;
+        bool more = q[a] < qe[a];
+        hc[a] = more ? __ldg(B.ci + q[a]) : 0x7fffffff;
+        if (WITH_VALUES && more) hv[a] = __ldg(B.v + q[a]);
     }
 };
 
-template <class AV, class BV, int BLOCK>
+// one merged row into (mc, mv); returns the number of distinct columns (at most `limit`)
+template <class AV, class BV, int MERGE>
+__device__ __forceinline__ int tiny_merge_numeric(const AV &A, const BV &B, typename AV::off_t pa, int na, int *mc, double *mv, int limit)
+{
+    TinyCursors<BV, MERGE, true> cur;
+    double av[MERGE];
+    cur.init(A, B, pa, na);
+#pragma unroll
+    for (int a = 0; a < MERGE; ++a) av[a] = a < na ? __ldg(A.v + pa + a) : 0.0;
+    int cnt = 0;
+    while (cnt < limit) {
+        int m = cur.head();
+        if (m == 0x7fffffff) break;
+        double acc = 0.0;
+        bool first = true;
+#pragma unroll
+        for (int a = 0; a < MERGE; ++a)
+            if (cur.hc[a] == m) {
+                double x = av[a] * cur.hv[a];
+                acc = first ? x : acc + x;
+                first = false;
+                cur.advance(B, a);
+            }
+        mc[cnt] = m; mv[cnt] = acc; ++cnt;
+    }
+    return cnt;
+}
+
+template <class AV, class BV, int BLOCK, int MERGE>
 __global__ void __launch_bounds__(BLOCK) k_sym_tiny(const int *__restrict__ rows, int nrows, int r0, AV A, BV B,
-                                                    int *__restrict__ nnz_row, int b_canonical)
+                                                    int *__restrict__ nnz_row, int b_canonical,
+                                                    unsigned long long *__restrict__ max_out /* largest nnz(C_i) seen */)
 {
     __shared__ int list[T_MAX * BLOCK];          // [slot][thread]: conflict free (list path only)
     int idx = blockIdx.x * BLOCK + threadIdx.x;
-    if (idx >= nrows) return;
+    if (idx >= nrows) return;                    // (partial last warp: the mask below is the active mask)
     int li = rows ? rows[idx] : idx;
     int i = r0 + li;
     typename AV::off_t pa = A.begin(i), pe = A.end(i);
     int na = (int)(pe - pa);
     int cnt = 0;
-    if (b_canonical && na <= TINY_MERGE) {
-        TinyCursors<BV> cur;
+    if (b_canonical && na <= MERGE) {
+        TinyCursors<BV, MERGE, false> cur;
         cur.init(A, B, pa, na);
         while (true) {
             int m = cur.head();
             if (m == 0x7fffffff) break;
 #pragma unroll
-            for (int a = 0; a < TINY_MERGE; ++a)
+            for (int a = 0; a < MERGE; ++a)
                 if (cur.hc[a] == m) cur.advance(B, a);
             ++cnt;
         }
@@ -295,9 +344,11 @@ __global__ void __launch_bounds__(BLOCK) k_sym_tiny(const int *__restrict__ rows
         }
     }
     nnz_row[li] = cnt;
+    int wmax = __reduce_max_sync(__activemask(), cnt);
+    if ((threadIdx.x & 31) == 0 && (unsigned long long)wmax > *max_out) atomicMax(max_out, (unsigned long long)wmax);
 }
 
-template <class AV, class BV, int BLOCK>
+template <class AV, class BV, int BLOCK, int MERGE>
 __global__ void __launch_bounds__(BLOCK) k_num_tiny(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
                                                     int *__restrict__ c_ci, double *__restrict__ c_v, int cap, int b_canonical)
 {
@@ -321,31 +372,12 @@ __global__ void __launch_bounds__(BLOCK) k_num_tiny(const int *__restrict__ rows
         int i = r0 + li;
         int *mc = cols + off;
         double *mv = vals + off;
-        int cnt = 0;
         typename AV::off_t pa = A.begin(i), pe = A.end(i);
         int na = (int)(pe - pa);
-        if (b_canonical && na <= TINY_MERGE) {
-            TinyCursors<BV> cur;
-            double av[TINY_MERGE];
-            cur.init(A, B, pa, na);
-#pragma unroll
-            for (int a = 0; a < TINY_MERGE; ++a) av[a] = a < na ? __ldg(A.v + pa + a) : 0.0;
-            while (cnt < n) {
-                int m = cur.head();
-                if (m == 0x7fffffff) break;
-                double acc = 0.0;
-                bool first = true;
-#pragma unroll
-                for (int a = 0; a < TINY_MERGE; ++a)
-                    if (cur.hc[a] == m) {
-                        double x = av[a] * __ldg(B.v + cur.q[a]);
-                        acc = first ? x : acc + x;
-                        first = false;
-                        cur.advance(B, a);
-                    }
-                mc[cnt] = m; mv[cnt] = acc; ++cnt;
-            }
+        if (b_canonical && na <= MERGE) {
+            tiny_merge_numeric<AV, BV, MERGE>(A, B, pa, na, mc, mv, n);
         } else {
+            int cnt = 0;
             for (typename AV::off_t p = pa; p < pe; ++p) {
                 int j = __ldg(A.ci + p);
                 double av = __ldg(A.v + p);
