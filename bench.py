@@ -246,35 +246,30 @@ def main():
     eng.set_stream(stream.cuda_stream)
 
     # ---- operands: rank 0 generates, NCCL broadcasts B (= A) once
+    from ia_spgemm_b200 import multigpu as M
     t_bcast = 0.0
+    desc = None
     if rank == 0:
         dA, desc = make_operand(eng, args, world)
-        meta = torch.tensor([dA.dev.row, dA.dev.col, dA.dev.nnz], dtype=torch.int64, device="cuda")
-    else:
-        dA, desc = None, None
-        meta = torch.zeros(3, dtype=torch.int64, device="cuda")
     if world > 1:
-        dist.broadcast(meta, 0)
-        rows, cols, nnz = (int(x) for x in meta.tolist())
-        t_rp = torch.empty(rows + 1, dtype=torch.int32, device="cuda")
-        t_ci = torch.empty(nnz, dtype=torch.int32, device="cuda")
-        t_v = torch.empty(nnz, dtype=torch.float64, device="cuda")
+        targs = (0, 0, None, None, None)
         if rank == 0:
-            eng.sync()
-            cudart = C.CDLL("libcudart.so")
+            t_rp = torch.empty(dA.dev.row + 1, dtype=torch.int32, device="cuda")
+            t_ci = torch.empty(dA.dev.nnz, dtype=torch.int32, device="cuda")
+            t_v = torch.empty(dA.dev.nnz, dtype=torch.float64, device="cuda")
             for t, ptr in ((t_rp, dA.dev.row_ind_dev), (t_ci, dA.dev.col_ind_dev), (t_v, dA.dev.values_dev)):
-                cudart.cudaMemcpy(C.c_void_p(t.data_ptr()), C.c_void_p(ptr), C.c_size_t(t.numel() * t.element_size()), C.c_int(3))
+                eng.copy(t.data_ptr(), ptr, t.numel() * t.element_size(), 2)
+            targs = (dA.dev.row, dA.dev.col, t_rp, t_ci, t_v)
             dA.close()
         torch.cuda.synchronize()
         dist.barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for t in (t_rp, t_ci, t_v):
-            dist.broadcast(t, 0)
+        rows, cols, t_rp, t_ci, t_v = M.broadcast_csr(dist, *targs, src=0, device="cuda")      # NCCL over NVLink
         e1.record()
         torch.cuda.synchronize()
         t_bcast = e0.elapsed_time(e1)
-        dA = eng.wrap_device(rows, cols, nnz, t_rp.data_ptr(), t_ci.data_ptr(), t_v.data_ptr())
+        dA = eng.wrap_device(rows, cols, int(t_ci.numel()), t_rp.data_ptr(), t_ci.data_ptr(), t_v.data_ptr())
         dA._keep = (t_rp, t_ci, t_v)
     rows, cols, nnz_a = dA.dev.row, dA.dev.col, dA.dev.nnz
 
@@ -382,10 +377,9 @@ def main():
         h_rp = torch.empty(rows + 1, dtype=torch.int32).pin_memory()
         h_ci = torch.empty(nnz_a, dtype=torch.int32).pin_memory()
         h_v = torch.empty(nnz_a, dtype=torch.float64).pin_memory()
-        cudart = C.CDLL("libcudart.so")
         torch.cuda.synchronize()
         for t, ptr in ((h_rp, dA.dev.row_ind_dev), (h_ci, dA.dev.col_ind_dev), (h_v, dA.dev.values_dev)):
-            cudart.cudaMemcpy(C.c_void_p(t.data_ptr()), C.c_void_p(ptr), C.c_size_t(t.numel() * t.element_size()), C.c_int(2))
+            eng.copy(t.data_ptr(), ptr, t.numel() * t.element_size(), 1)
         hB = (rows, cols, h_rp.numpy(), h_ci.numpy(), h_v.numpy())
         hA = hB if world == 1 else slice_rows(hB, r0, r1)
         if world > 1:

@@ -1,0 +1,234 @@
+// spgemm-gpu -- command-line front end of the B200 engine, drop-in for the reference's
+// `./spgemm-gpu A.mtx` (GPU/main.cu:30-557) and `./spgemm-cpu A.mtx B.mtx mode` (CPU/main.cpp:97-1003).
+//
+//   spgemm-gpu A.mtx                 C = A*A   (README.md:10 "All tests default calculate the square of A")
+//   spgemm-gpu A.mtx B.mtx [mode]    C = A*B; mode != 0 dumps the operands like testing_mode (CPU/main.cpp:489-497)
+//   options: --all (run every format as the reference does), --json, --gate X (default 20, GPU release),
+//            --repeat N (best of N timed runs after one warm-up; the reference times one cold run)
+//
+// Same stages as the reference main: Matrix-Market load -> density images ./imgs/img{1,2}.txt ->
+// 26 features -> format selection -> multiply -> report block (Appendix A of SURVEY.md: run_time,
+// trans_time, memory_size, verified_sum, Gflops, Speedup).  Differences, all deliberate (SURVEY
+// appendix D): file values are kept (GPU/main.cu:236-243 overwrites them with rand()%10), B := A
+// rather than A^T, and the selector is a rule on the feature vector until MatNet inference lands
+// (the reference only prints MatNet's pick and then runs everything anyway).
+// Host code only: everything numeric goes through the C ABI of libiaspgemm.so.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/stat.h>
+#include <time.h>
+
+#include <string>
+#include <vector>
+
+#include "../../../include/iaspgemm.h"
+
+static int die(const char *what)
+{
+    fprintf(stderr, "spgemm-gpu: %s: %s\n", what, ias_last_error());
+    return 1;
+}
+
+static void print_csr(const char *name, const IasCsrMatrix &M)
+{
+    printf("%s:\n", name);
+    for (int i = 0; i < M.row; ++i) {
+        for (int p = M.row_ind[i]; p < M.row_ind[i + 1]; ++p) printf("(%d,%d)=%.2f ", i, M.col_ind[p], M.values[p]);
+        printf("\n");
+    }
+    printf("\n");
+}
+
+static int write_image(const char *path, const long long *img)
+{
+    FILE *f = fopen(path, "w");
+    if (!f) return -1;
+    for (int i = 0; i < 128 * 128; ++i) fprintf(f, "%lld\n", img[i]);
+    fclose(f);
+    return 0;
+}
+
+// Rule-based stand-in for MatNet.Pred (CPU/MatNet.py:24-96): class index in the CPU numbering
+// 1 = CSR (the reference's slots 0/1 are MKL/CSR), 2 = DIA, 3 = ELL, 4 = COO.
+static int select_format(const double *f, bool dia_ok, bool ell_ok)
+{
+    double diag_fill = f[2] / (f[18] * f[0]);          // nnz / (ndiag * rows): how full the stored diagonals are
+    double ell_eff = f[24];
+    if (dia_ok && diag_fill > 0.5) return 2;
+    if (ell_ok && ell_eff > 0.9 && f[8] < 0.05) return 3;
+    return 1;
+}
+
+int main(int argc, char **argv)
+{
+    std::vector<std::string> pos;
+    bool all = false, json = false;
+    double gate = 20.0;
+    int repeat = 1;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        if (a == "--all") all = true;
+        else if (a == "--json") json = true;
+        else if (a == "--gate" && i + 1 < argc) gate = atof(argv[++i]);
+        else if (a == "--repeat" && i + 1 < argc) repeat = atoi(argv[++i]);
+        else pos.push_back(a);
+    }
+    if (pos.empty()) {
+        printf("please use command like this : ./spgemm-gpu ./sample.mtx\n");
+        return -1;
+    }
+    const std::string fa = pos[0], fb = pos.size() > 1 ? pos[1] : pos[0];
+    int testing_mode = pos.size() > 2 ? atoi(pos[2].c_str()) : 0;
+    printf("-------------- %s, %s --------------\n", fa.c_str(), fb.c_str());
+
+    IasCsrMatrix A, B;
+    int rc = ias_mtx_load(fa.c_str(), &A);
+    if (rc) { printf("F1: could not load %s (code %d)\n", fa.c_str(), rc); return rc; }
+    bool same = fa == fb;
+    if (same) B = A;
+    else if ((rc = ias_mtx_load(fb.c_str(), &B)) != 0) { printf("F2: could not load %s (code %d)\n", fb.c_str(), rc); return rc; }
+    printf("Weight Matrix (A): %dx%d: nnz = %d\n", A.row, A.col, A.nnz);
+    printf("Activation Matrix (B): %dx%d: nnz = %d\n", B.row, B.col, B.nnz);
+    if (testing_mode) { print_csr("A_csr", A); print_csr("B_csr", B); }
+    if (A.col > B.row) { printf("shape mismatch: A is %dx%d, B is %dx%d\n", A.row, A.col, B.row, B.col); return -5; }
+
+    if (ias_init(0)) return die("ias_init");
+    IasCsrMatrixDev dA, dB;
+    if (ias_upload_csr(&A, &dA)) return die("upload A");
+    if (same) dB = dA;
+    else if (ias_upload_csr(&B, &dB)) return die("upload B");
+
+    // density representation -> ./imgs/img1.txt, ./imgs/img2.txt (CPU/main.cpp:516-643)
+    std::vector<long long> img(128 * 128);
+    mkdir("imgs", 0755);
+    if (ias_density_image(&dA, img.data())) return die("density A");
+    if (write_image("./imgs/img1.txt", img.data())) fprintf(stderr, "spgemm-gpu: cannot write ./imgs/img1.txt\n");
+    if (ias_density_image(&dB, img.data())) return die("density B");
+    if (write_image("./imgs/img2.txt", img.data())) fprintf(stderr, "spgemm-gpu: cannot write ./imgs/img2.txt\n");
+    printf("------------------------------------------\n");
+
+    double feat[26];
+    if (ias_features26(&dA, &dB, feat)) return die("features");
+    long long flops = 0;
+    if (ias_getflop(&dA, &dB, &flops)) return die("GetFlop");
+
+    // conversions (timed like CPU/main.cpp:658-676: trans_time covers A and B)
+    double run[5] = {0}, trans[5] = {0}, size[5] = {0}, sum[5] = {0};
+    IasDiaDev a_dia = {}, b_dia = {};
+    IasEllDev a_ell = {}, b_ell = {};
+    IasCooDev a_coo = {}, b_coo = {};
+    struct timespec t0, t1;
+    auto now = [](struct timespec *t) { clock_gettime(CLOCK_MONOTONIC, t); };
+    auto ms = [](const struct timespec &a, const struct timespec &b) { return (b.tv_sec - a.tv_sec) * 1e3 + (b.tv_nsec - a.tv_nsec) / 1e6; };
+    now(&t0);
+    if (ias_csr_to_dia(&dA, gate, &a_dia)) return die("CSRtoDIA");
+    if (same) b_dia = a_dia; else if (ias_csr_to_dia(&dB, gate, &b_dia)) return die("CSRtoDIA");
+    now(&t1); trans[2] = ms(t0, t1);
+    now(&t0);
+    if (ias_csr_to_ell(&dA, gate, &a_ell)) return die("CSRtoELL");
+    if (same) b_ell = a_ell; else if (ias_csr_to_ell(&dB, gate, &b_ell)) return die("CSRtoELL");
+    now(&t1); trans[3] = ms(t0, t1);
+    bool dia_ok = a_dia.choice && b_dia.choice, ell_ok = a_ell.choice && b_ell.choice;
+
+    int c = select_format(feat, dia_ok, ell_ok);
+    printf("The Chosen One = Algorithm %d\n", c + 1);
+
+    auto want = [&](int k) { return all || k == c; };
+    // repeat == 1: one cold run, as the reference times it; repeat > 1: one warm-up, then the best of `repeat`
+    const int runs = repeat > 1 ? repeat + 1 : 1;
+    auto keep = [&](int r, double t, double &best) { if (r == (runs > 1 ? 1 : 0) || (r > 0 && t < best)) best = t; };
+    // Algorithm 2: CSR
+    if (want(1)) {
+        for (int r = 0; r < runs; ++r) {
+            IasCsr64Dev C;
+            IasSpgemmStats st;
+            if (ias_csr_mul_csr_dev64(&dA, &dB, &C, &st)) return die("CSR_MUL_CSR_DEV");
+            keep(r, st.ms_total, run[1]);
+            if (r == runs - 1) { ias_checksum(C.values_dev, C.nnz, &sum[1]); size[1] = ias_sizeof_csr(C.row, C.nnz); }
+            ias_free_csr64_dev(&C);
+        }
+        printf("DONE CSR\n");
+    }
+    // Algorithm 3: DIA
+    if (want(2) && dia_ok) {
+        for (int r = 0; r < runs; ++r) {
+            IasDiaDev C;
+            double t = 0;
+            if (ias_dia_mul_dia_dev(&a_dia, &b_dia, &C, &t)) return die("DIA_MUL_DIA_DEV");
+            keep(r, t, run[2]);
+            if (r == runs - 1) { ias_checksum(C.values_dev, (long long)C.row * C.num_diagonals, &sum[2]); size[2] = ias_sizeof_dia(C.row, C.col, C.num_diagonals); }
+            ias_free_dia_dev(&C);
+        }
+        printf("DONE DIA\n");
+    }
+    // Algorithm 4: ELL
+    if (want(3) && ell_ok) {
+        for (int r = 0; r < runs; ++r) {
+            IasEllDev C;
+            double t = 0;
+            if (ias_ell_mul_ell_dev(&a_ell, &b_ell, &C, &t)) return die("ELL_MUL_ELL_DEV");
+            keep(r, t, run[3]);
+            if (r == runs - 1) { ias_checksum(C.values_dev, (long long)C.row * C.max_nnz_per_row, &sum[3]); size[3] = ias_sizeof_ell(C.row, C.max_nnz_per_row); }
+            ias_free_ell_dev(&C);
+        }
+        printf("DONE ELL\n");
+    }
+    // Algorithm 5: COO
+    if (want(4)) {
+        now(&t0);
+        if (ias_csr_to_coo(&dA, &a_coo)) return die("CSRtoCOO");
+        if (same) b_coo = a_coo; else if (ias_csr_to_coo(&dB, &b_coo)) return die("CSRtoCOO");
+        now(&t1); trans[4] = ms(t0, t1);
+        for (int r = 0; r < runs; ++r) {
+            IasCooDev C;
+            double t = 0;
+            if (ias_coo_mul_coo_dev(&a_coo, &b_coo, &C, &t)) return die("COO_MUL_COO_DEV");
+            keep(r, t, run[4]);
+            if (r == runs - 1) { ias_checksum(C.values_dev, C.nnz, &sum[4]); size[4] = ias_sizeof_coo(C.row, C.nnz); }
+            ias_free_coo_dev(&C);
+        }
+        printf("DONE COO\n");
+    }
+
+    // report block, CPU/main.cpp:968-1000.  Slot 1 (MKL) is the CPU library row: not run by the GPU front end.
+    double base = run[1] > 0 ? run[1] : 0.0, max_speedup = 0.0;
+    int max_index = -1;
+    double speedup[5];
+    for (int i = 0; i < 5; ++i) {
+        speedup[i] = (run[i] == 0.0 || base == 0.0) ? 0.0 : base / run[i];
+        if (run[i] > 0 && (max_index < 0 || run[i] < run[max_index])) { max_index = i; }
+    }
+    if (max_index >= 0) max_speedup = base > 0 ? base / run[max_index] : 0.0;
+    for (int i = 0; i < 5; ++i) {
+        printf("------------------------------\n");
+        printf("Algorithm %d:\n", i + 1);
+        printf("run_time: %lf\n", run[i]);
+        printf("trans_time: %lf\n", trans[i]);
+        printf("memory_size: %lf\n", size[i]);
+        printf("verified_sum: %lf\n", sum[i]);
+        printf("Gflops: %lf\n", run[i] == 0.0 ? 0.0 : (flops * 2.0) / (run[i] * 1000000));
+        printf("Speedup: %lf\n", speedup[i]);
+    }
+    printf("------------------------------\n");
+    printf("MAX SPEED IS %lf for ALGORITHM %d\n", max_speedup, max_index + 1);
+    printf("------------------------------\n");
+    if (all) {
+        if (c == max_index) printf("Congratulate! MatNet Correct Prediction.\n");
+        else printf("Unfortunately! MatNet Incorrect Prediction.\n");
+        printf("------------------------------\n");
+    }
+    if (json) {
+        printf("{\"file_a\": \"%s\", \"file_b\": \"%s\", \"rows\": %d, \"cols\": %d, \"nnz_a\": %d, \"products\": %lld, \"chosen\": %d, \"features\": [",
+               fa.c_str(), fb.c_str(), A.row, B.col, A.nnz, flops, c + 1);
+        for (int i = 0; i < 26; ++i) printf("%s%.17g", i ? ", " : "", feat[i]);
+        printf("], \"run_ms\": [%g, %g, %g, %g, %g], \"verified_sum\": [%.17g, %.17g, %.17g, %.17g, %.17g], \"memory_size\": [%.17g, %.17g, %.17g, %.17g, %.17g]}\n",
+               run[0], run[1], run[2], run[3], run[4], sum[0], sum[1], sum[2], sum[3], sum[4], size[0], size[1], size[2], size[3], size[4]);
+    }
+    ias_free_dia_dev(&a_dia); if (!same) ias_free_dia_dev(&b_dia);
+    ias_free_ell_dev(&a_ell); if (!same) ias_free_ell_dev(&b_ell);
+    ias_free_coo_dev(&a_coo); if (!same) ias_free_coo_dev(&b_coo);
+    ias_free_csr_dev(&dA); if (!same) ias_free_csr_dev(&dB);
+    ias_free_host_csr(&A); if (!same) ias_free_host_csr(&B);
+    return 0;
+}

