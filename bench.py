@@ -309,14 +309,17 @@ def main():
 
     products_total = eng.GetFlop(dA, dA) if args.format != "csr" else 0
 
-    for _ in range(args.warmup):
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()                     # sampled from the warm-up on: the timed region alone can be a few ms
+    t_warm = time.perf_counter()
+    n_warm = 0
+    while n_warm < args.warmup or (time.perf_counter() - t_warm < 0.3 and n_warm < 200):
         st = step()
+        n_warm += 1
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = eng.kernel_launches()
     torch.cuda.synchronize()
@@ -434,9 +437,12 @@ def main():
                            "products": products, "nnz_C": nnz_c, "l2": "inputs_exceed_l2 (A %.2f GB, C %.2f GB per step vs 126 MB L2)" % (
                                bytes_csr(rows, nnz_a) / 1e9, bytes_csr(r1 - r0, st["nnz"], 8) / 1e9),
                            "parallelism": "row-block x%d, B broadcast once (%.1f ms, outside the timed region)" % (world, t_bcast) if world > 1 else "single GPU",
-                           "streaming_batches": st.get("batches", 1),
+                           "streaming_batches": st.get("batches", 1), "warmup_steps_run": n_warm,
                            "phase_ms": {k: float(np.mean([s.get(k, 0.0) for s in stats])) for k in ("ms_analyze", "ms_symbolic", "ms_scan", "ms_numeric")},
-                           "num_bin_rows": st.get("num_bin_rows"), "sym_bin_rows": st.get("sym_bin_rows")},
+                           "bins": ["empty", "tiny", "warp", "cta_s", "cta_l", "global"],
+                           "num_bin_rows": st.get("num_bin_rows"), "sym_bin_rows": st.get("sym_bin_rows"),
+                           "ms_bin_sym": [round(float(np.mean([s.get("ms_bin_sym", [0] * 6)[b] for s in stats])), 4) for b in range(6)],
+                           "ms_bin_num": [round(float(np.mean([s.get("ms_bin_num", [0] * 6)[b] for s in stats])), 4) for b in range(6)]},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
         print(json.dumps(line), flush=True)
     if world > 1:
