@@ -71,6 +71,7 @@ struct RangeWork {
     long long num_hist[8] = {0};
     int max_tiny_nnz = 0, max_nnz = 0;
     int b_canonical = 0;           // every B row strictly increasing in column (enables the merge kernels)
+    int max_warp_ub = 0;           // largest upper bound among warp-bin rows (sizes the register sort)
     int max_tiny_na = 0;           // longest A row / largest upper bound among tiny rows
     int max_tiny_ub = 0;
     bool tiny_only = false;        // every non-empty row is tiny: numeric bins == symbolic bins
@@ -146,12 +147,13 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
         IAS_CUDA(cudaMemsetAsync(rw.hist.p + NBINS + 1, 0, sizeof(unsigned long long), c.stream));
         IAS_LAUNCH((k_rows_canonical<BV>), grid_for(b_rows, 256), 256, 0, b_rows, B, rw.hist.p + NBINS + 1);
     }
-    long long h[NBINS + 4];
-    IAS_TRY(read_hist(rw, NBINS + 4, h));
+    long long h[NBINS + 5];
+    IAS_TRY(read_hist(rw, NBINS + 5, h));
     rw.products = h[NBINS];
     rw.b_canonical = (b_rows > 0 && h[NBINS + 1] == 0) ? 1 : 0;
     rw.max_tiny_na = (int)h[NBINS + 2];
     rw.max_tiny_ub = (int)h[NBINS + 3];
+    rw.max_warp_ub = (int)h[NBINS + 4];
     // every non-empty row is tiny: the numeric bins equal the symbolic ones (ub <= 32 decides), no re-classification
     rw.tiny_only = h[BIN_T] > 0 && h[BIN_T] + h[BIN_EMPTY] == nrows;
     for (int b = 0; b < NBINS; ++b) rw.sym_hist[b] = h[b];
@@ -267,33 +269,48 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         IAS_BIN_END(8 + BIN_T);
         rw.num_timed[BIN_T] = true;
     }
+    int col_bits = 1;
+    while (col_bits < 31 && (1LL << col_bits) < (long long)ncols_b) ++col_bits;
     if (bl.count[BIN_W]) {
         IAS_BIN_BEGIN(8 + BIN_W);
         int m = (int)bl.count[BIN_W];
-        auto k = k_num_hash<AV, BV, 32, 256, NUM_W_TSIZE>;
-        size_t sm = (size_t)8 * NUM_W_TSIZE * 12;
-        IAS_TRY(opt_in_smem(k, sm));
-        IAS_LAUNCH(k, grid_for(m, 8), 256, sm, bl.rows_of(BIN_W), m, r0, A, B, out, c_ci, c_v);
+        // items per lane from the largest product count of the bin; 32-bit keys when column and index fit in 31 bits
+        int max_ub = std::min(std::max(rw.max_warp_ub, T_MAX + 1), NUM_W_UB);
+        int ipl = max_ub <= 64 ? 2 : max_ub <= 128 ? 4 : max_ub <= 256 ? 8 : 16;
+        int idx_bits = ipl == 16 ? 9 : ipl == 8 ? 8 : ipl == 4 ? 7 : 6;
+        bool k32 = col_bits + idx_bits <= 31;
+        constexpr int EB = 128;                       // 4 rows per CTA
+        size_t sm = (size_t)(EB / 32) * 32 * ipl * ((k32 ? 4 : 8) + 8);
+        const int *rl = bl.rows_of(BIN_W);
+#define IAS_ESC(KT, IPL)                                                                                      \
+        do {                                                                                                  \
+            auto k = k_esc_warp<AV, BV, KT, IPL, EB, true>;                                                   \
+            IAS_TRY(opt_in_smem(k, sm));                                                                      \
+            IAS_LAUNCH(k, grid_for(m, EB / 32), EB, sm, rl, m, r0, A, B, out, (int *)nullptr, c_ci, c_v);     \
+        } while (0)
+        if (k32) { if (ipl == 2) IAS_ESC(unsigned, 2); else if (ipl == 4) IAS_ESC(unsigned, 4); else if (ipl == 8) IAS_ESC(unsigned, 8); else IAS_ESC(unsigned, 16); }
+        else     { if (ipl == 2) IAS_ESC(unsigned long long, 2); else if (ipl == 4) IAS_ESC(unsigned long long, 4); else if (ipl == 8) IAS_ESC(unsigned long long, 8); else IAS_ESC(unsigned long long, 16); }
+#undef IAS_ESC
         IAS_BIN_END(8 + BIN_W);
         rw.num_timed[BIN_W] = true;
     }
     if (bl.count[BIN_B1]) {
         IAS_BIN_BEGIN(8 + BIN_B1);
         int m = (int)bl.count[BIN_B1];
-        auto k = k_num_hash<AV, BV, 256, 256, NUM_B1_TSIZE>;
-        size_t sm = (size_t)NUM_B1_TSIZE * 12;
+        auto k = k_num_hash_cta<AV, BV, 512, NUM_B1_TSIZE>;
+        size_t sm = NumHashSmem<512, NUM_B1_TSIZE>::BYTES;
         IAS_TRY(opt_in_smem(k, sm));
-        IAS_LAUNCH(k, m, 256, sm, bl.rows_of(BIN_B1), m, r0, A, B, out, c_ci, c_v);
+        IAS_LAUNCH(k, m, 512, sm, bl.rows_of(BIN_B1), m, r0, A, B, out, c_ci, c_v, col_bits);
         IAS_BIN_END(8 + BIN_B1);
         rw.num_timed[BIN_B1] = true;
     }
     if (bl.count[BIN_B2]) {
         IAS_BIN_BEGIN(8 + BIN_B2);
         int m = (int)bl.count[BIN_B2];
-        auto k = k_num_hash<AV, BV, 1024, 1024, NUM_B2_TSIZE>;
-        size_t sm = (size_t)NUM_B2_TSIZE * 12;
+        auto k = k_num_hash_cta<AV, BV, 1024, NUM_B2_TSIZE>;
+        size_t sm = NumHashSmem<1024, NUM_B2_TSIZE>::BYTES;
         IAS_TRY(opt_in_smem(k, sm));
-        IAS_LAUNCH(k, m, 1024, sm, bl.rows_of(BIN_B2), m, r0, A, B, out, c_ci, c_v);
+        IAS_LAUNCH(k, m, 1024, sm, bl.rows_of(BIN_B2), m, r0, A, B, out, c_ci, c_v, col_bits);
         IAS_BIN_END(8 + BIN_B2);
         rw.num_timed[BIN_B2] = true;
     }

@@ -34,7 +34,7 @@ constexpr int SYM_W_UB = 512, SYM_W_TSIZE = 1024;
 constexpr int SYM_B1_UB = 4096, SYM_B1_TSIZE = 8192;
 constexpr int SYM_B2_UB = 24576, SYM_B2_TSIZE = 49152;
 // numeric bins by exact nnz(C_i)
-constexpr int NUM_W_NNZ = 512, NUM_W_TSIZE = 1024;
+constexpr int NUM_W_UB = 512;
 constexpr int NUM_B1_NNZ = 4096, NUM_B1_TSIZE = 8192;
 constexpr int NUM_B2_NNZ = 12288, NUM_B2_TSIZE = 16384;
 
@@ -51,7 +51,7 @@ __host__ __device__ __forceinline__ int num_bin_of(int ub, int nnz)
 {
     if (nnz == 0) return BIN_EMPTY;
     if (ub <= T_MAX) return BIN_T;
-    if (nnz <= NUM_W_NNZ) return BIN_W;
+    if (ub <= NUM_W_UB) return BIN_W;                 // expand-sort-compress in registers holds every product
     if (nnz <= NUM_B1_NNZ) return BIN_B1;
     if (nnz <= NUM_B2_NNZ) return BIN_B2;
     return BIN_G;
@@ -118,10 +118,10 @@ __global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, 
 {
     __shared__ unsigned s_cnt[NBINS];
     __shared__ unsigned long long s_sum;
-    __shared__ int s_max[2];
+    __shared__ int s_max[3];
     if (threadIdx.x < NBINS) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x == NBINS) s_sum = 0;
-    if (threadIdx.x < 2) s_max[threadIdx.x] = 0;
+    if (threadIdx.x < 3) s_max[threadIdx.x] = 0;
     __syncthreads();
     int li = blockIdx.x * blockDim.x + threadIdx.x;
     long long ub = 0;
@@ -139,16 +139,20 @@ __global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, 
         if (unsorted) g_hist[NBINS + 1] = 1;      // A (== B for A^2) is not canonical
         bin = sym_bin_of(ub);
         tiny_na = (bin == BIN_T) ? (int)(pe - A.begin(i)) : 0;
-        tiny_ub = (bin == BIN_T) ? (int)ub : 0;
+        tiny_ub = (bin == BIN_T) ? (int)ub : (bin == BIN_W ? -(int)ub : 0);   // negative: a warp-bin row
         ub_out[li] = ub > 0x7fffffffLL ? 0x7fffffff : (int)ub;
         bin_out[li] = (unsigned char)bin;
     }
+    int warp_ub = __reduce_max_sync(0xffffffffu, tiny_ub < 0 ? -tiny_ub : 0);
     tiny_na = __reduce_max_sync(0xffffffffu, tiny_na);
-    tiny_ub = __reduce_max_sync(0xffffffffu, tiny_ub);
-    if ((threadIdx.x & 31) == 0 && tiny_na > 0) { atomicMax(&s_max[0], tiny_na); atomicMax(&s_max[1], tiny_ub); }
+    tiny_ub = __reduce_max_sync(0xffffffffu, tiny_ub > 0 ? tiny_ub : 0);
+    if ((threadIdx.x & 31) == 0) {
+        if (tiny_na > 0) { atomicMax(&s_max[0], tiny_na); atomicMax(&s_max[1], tiny_ub); }
+        if (warp_ub > 0) atomicMax(&s_max[2], warp_ub);
+    }
     block_hist(bin, ub, s_cnt, &s_sum, g_hist);
-    // one pair of global atomics per CTA, and only when it would raise the maximum (plain read is a hint)
-    if (threadIdx.x < 2 && s_max[threadIdx.x] > 0 && (unsigned long long)s_max[threadIdx.x] > g_hist[NBINS + 2 + threadIdx.x])
+    // one global atomic per CTA and statistic, and only when it would raise the maximum (plain read is a hint)
+    if (threadIdx.x < 3 && s_max[threadIdx.x] > 0 && (unsigned long long)s_max[threadIdx.x] > g_hist[NBINS + 2 + threadIdx.x])
         atomicMax(&g_hist[NBINS + 2 + threadIdx.x], (unsigned long long)s_max[threadIdx.x]);
 }
 
@@ -183,9 +187,10 @@ __global__ void __launch_bounds__(256) k_row_ub_warp(int nrows, int r0, AV A, BV
             ub_out[li] = ub > 0x7fffffffLL ? 0x7fffffff : (int)ub;
             bin_out[li] = (unsigned char)bin;
             if (bin == BIN_T) {
-                atomicMax(&g_hist[NBINS + 2], (unsigned long long)(pe - pa));
-                atomicMax(&g_hist[NBINS + 3], (unsigned long long)ub);
+                if ((unsigned long long)(pe - pa) > g_hist[NBINS + 2]) atomicMax(&g_hist[NBINS + 2], (unsigned long long)(pe - pa));
+                if ((unsigned long long)ub > g_hist[NBINS + 3]) atomicMax(&g_hist[NBINS + 3], (unsigned long long)ub);
             }
+            if (bin == BIN_W && (unsigned long long)ub > g_hist[NBINS + 4]) atomicMax(&g_hist[NBINS + 4], (unsigned long long)ub);
         } else {
             ub = 0;                                  // the row's total is counted once
         }
@@ -436,6 +441,142 @@ __device__ __forceinline__ void group_sync()
     if (TPR == 32) __syncwarp(); else __syncthreads();
 }
 
+// ---- product iterator shared by the warp / CTA / global kernels
+// A warp walks the A row in chunks of 32 entries: lane l fetches entry l (column j, value, start and
+// length of B row j) in one coalesced + one gathered access, so the a_ci -> b_rp -> b_ci dependency
+// chain is paid once per 32 entries instead of once per entry.  B rows of LONG_ROW or more entries are
+// strided by the whole warp; the short ones are flattened: their products are numbered 0..T-1 with a
+// warp scan and lane t finds its (entry, offset) with a 5-step shuffle search, so lanes stay busy on
+// power-law operands whose B rows are mostly a handful of entries.  f(q, a_value, pidx) is called once
+// per product with q = index into B.ci / B.v and pidx = dense arrival index of the product within this
+// warp's share of the row.  Returns the number of products visited.  All 32 lanes must call this together.
+constexpr int LONG_ROW = 24;
+
+template <bool NEED_VALUES, class AV, class BV, class F>
+__device__ __forceinline__ int warp_products(const AV &A, const BV &B, typename AV::off_t pa, typename AV::off_t pe,
+                                             int w, int nw, int lane, F &&f)
+{
+    typedef typename AV::off_t aoff;
+    typedef typename BV::off_t boff;
+    int pcount = 0;
+    for (aoff base = pa + (aoff)w * 32; base < pe; base += (aoff)nw * 32) {
+        aoff p = base + lane;
+        int len = 0;
+        boff qb = 0;
+        double av = 0.0;
+        if (p < pe) {
+            int j = __ldg(A.ci + p);
+            qb = B.begin(j);
+            len = (int)(B.end(j) - qb);
+            if (NEED_VALUES) av = __ldg(A.v + p);
+        }
+        unsigned longmask = __ballot_sync(0xffffffffu, len >= LONG_ROW);
+        while (longmask) {
+            int src = __ffs(longmask) - 1;
+            longmask &= longmask - 1;
+            boff sqb = __shfl_sync(0xffffffffu, qb, src);
+            int slen = __shfl_sync(0xffffffffu, len, src);
+            double sav = NEED_VALUES ? __shfl_sync(0xffffffffu, av, src) : 0.0;
+            for (int t = lane; t < slen; t += 32) f(sqb + t, sav, pcount + t);
+            pcount += slen;
+        }
+        int slen = len >= LONG_ROW ? 0 : len;
+        int incl = slen;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+        int total = __shfl_sync(0xffffffffu, incl, 31);
+        boff rel = qb - (boff)(incl - slen);          // q = rel + t for the products of this lane's entry
+        for (int t0 = 0; t0 < total; t0 += 32) {
+            int t = t0 + lane;
+            int src = 0;                                // smallest lane whose inclusive count exceeds t
+#pragma unroll
+            for (int step = 16; step > 0; step >>= 1) {
+                int v = __shfl_sync(0xffffffffu, incl, src + step - 1);
+                if (v <= t) src += step;
+            }
+            src = min(src, 31);
+            boff srel = __shfl_sync(0xffffffffu, rel, src);
+            double sav = NEED_VALUES ? __shfl_sync(0xffffffffu, av, src) : 0.0;
+            if (t < total) f(srel + t, sav, pcount + t);
+        }
+        pcount += total;
+    }
+    return pcount;
+}
+
+// ---- the same for a whole CTA: balanced over all threads.
+// ncu on R-MAT showed CTA-per-row kernels issuing 3 % of the time, the rest spent at barriers behind
+// the one warp that drew a hub row.  Here the A row is taken in tiles of BLOCK entries: thread t loads
+// entry t, a block scan numbers the tile's products 0..T-1, and thread t processes products t, t+BLOCK,
+// ... finding the owning entry by binary search in shared memory (skipped while it stays inside the
+// same B row, i.e. almost always on hub rows).  Every thread gets the same number of products.
+template <class BV, int BLOCK>
+struct CtaTile {
+    typedef cub::BlockScan<int, BLOCK> Scan;
+    typename Scan::TempStorage scan;
+    int incl[BLOCK];
+    typename BV::off_t rel[BLOCK];
+    double av[BLOCK];
+};
+
+template <bool NEED_VALUES, int BLOCK, class AV, class BV, class F>
+__device__ __forceinline__ void cta_products(const AV &A, const BV &B, typename AV::off_t pa, typename AV::off_t pe,
+                                             CtaTile<BV, BLOCK> &tile, F &&f)
+{
+    typedef typename AV::off_t aoff;
+    typedef typename BV::off_t boff;
+    const int tid = threadIdx.x;
+    for (aoff base = pa; base < pe; base += BLOCK) {
+        aoff p = base + tid;
+        int len = 0;
+        boff qb = 0;
+        double av = 0.0;
+        if (p < pe) {
+            int j = __ldg(A.ci + p);
+            qb = B.begin(j);
+            len = (int)(B.end(j) - qb);
+            if (NEED_VALUES) av = __ldg(A.v + p);
+        }
+        int incl;
+        typename CtaTile<BV, BLOCK>::Scan(tile.scan).InclusiveSum(len, incl);
+        tile.incl[tid] = incl;
+        tile.rel[tid] = qb - (boff)(incl - len);
+        if (NEED_VALUES) tile.av[tid] = av;
+        __syncthreads();
+        const int total = tile.incl[BLOCK - 1];
+        int e = 0, lo_t = 0, hi_t = tile.incl[0];          // products [lo_t, hi_t) belong to entry e
+        for (int t = tid; t < total; t += BLOCK) {
+            if (t >= hi_t) {
+                int lo = e + 1, hi = BLOCK - 1;            // smallest entry whose inclusive count exceeds t
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (tile.incl[mid] <= t) lo = mid + 1; else hi = mid; }
+                e = lo;
+                hi_t = tile.incl[e];
+                lo_t = tile.incl[e - 1];
+            }
+            (void)lo_t;
+            f(tile.rel[e] + t, NEED_VALUES ? tile.av[e] : 0.0);
+        }
+        __syncthreads();                                   // the tile arrays are rewritten by the next pass
+    }
+}
+
+template <int TSIZE>
+__device__ __forceinline__ unsigned hash_insert_key(int *keys, int k, int &fresh)
+{
+    unsigned s = __umulhi(hash_col(k), (unsigned)TSIZE);
+    while (true) {
+        int cur = keys[s];
+        if (cur == k) break;
+        if (cur == -1) {
+            int old = atomicCAS(&keys[s], -1, k);
+            if (old == -1) { ++fresh; break; }
+            if (old == k) break;
+        }
+        s = (s + 1 == TSIZE) ? 0 : s + 1;
+    }
+    return s;
+}
+
 template <class AV, class BV, int TPR, int BLOCK, int TSIZE>
 __global__ void __launch_bounds__(BLOCK) k_sym_hash(const int *__restrict__ rows, int nrows, int r0, AV A, BV B,
                                                     int *__restrict__ nnz_row)
@@ -453,24 +594,15 @@ __global__ void __launch_bounds__(BLOCK) k_sym_hash(const int *__restrict__ rows
     int li = rows ? rows[idx] : idx;
     int i = r0 + li;
     int cnt = 0;
-    typename AV::off_t pe = A.end(i);
-    for (typename AV::off_t p = A.begin(i) + w; p < pe; p += NW) {
-        int j = __ldg(A.ci + p);
-        typename BV::off_t qe = B.end(j);
-        for (typename BV::off_t q = B.begin(j) + lane; q < qe; q += 32) {
-            int k = __ldg(B.ci + q);
-            unsigned s = __umulhi(hash_col(k), (unsigned)TSIZE);
-            while (true) {
-                int cur = keys[s];
-                if (cur == k) break;
-                if (cur == -1) {
-                    int old = atomicCAS(&keys[s], -1, k);
-                    if (old == -1) { ++cnt; break; }
-                    if (old == k) break;
-                }
-                s = (s + 1 == TSIZE) ? 0 : s + 1;
-            }
-        }
+    if (TPR == 32) {
+        warp_products<false>(A, B, A.begin(i), A.end(i), 0, 1, lane, [&](typename BV::off_t q, double, int) {
+            hash_insert_key<TSIZE>(keys, __ldg(B.ci + q), cnt);
+        });
+    } else {
+        __shared__ CtaTile<BV, TPR == 32 ? 32 : BLOCK> tile;
+        cta_products<false, TPR == 32 ? 32 : BLOCK>(A, B, A.begin(i), A.end(i), tile, [&](typename BV::off_t q, double) {
+            hash_insert_key<TSIZE>(keys, __ldg(B.ci + q), cnt);
+        });
     }
     cnt = warp_sum(cnt);
     if (TPR == 32) {
@@ -482,90 +614,183 @@ __global__ void __launch_bounds__(BLOCK) k_sym_hash(const int *__restrict__ rows
     }
 }
 
-template <class AV, class BV, int TPR, int BLOCK, int TSIZE>
-__global__ void __launch_bounds__(BLOCK) k_num_hash(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
-                                                    int *__restrict__ c_ci, double *__restrict__ c_v)
+// ---- CTA per row: hash SPA in shared memory, then a block radix sort of (column, slot) pairs.
+// The table is never compacted: empty slots carry key 0xffffffff and sort behind every column, the
+// sorted keys come back striped so the CTA writes the row with fully coalesced stores, and each value
+// is fetched from its slot.  The sort's scratch aliases the key table (keys are in registers by then).
+template <int BLOCK, int TSIZE>
+struct NumHashSmem {
+    static constexpr int IPT = TSIZE / BLOCK;
+    typedef cub::BlockRadixSort<unsigned, BLOCK, IPT, unsigned> Sort;
+    static constexpr size_t KEY_BYTES = sizeof(typename Sort::TempStorage) > (size_t)TSIZE * 4 ? sizeof(typename Sort::TempStorage) : (size_t)TSIZE * 4;
+    static constexpr size_t BYTES = (size_t)TSIZE * 8 + ((KEY_BYTES + 15) / 16) * 16;
+};
+
+template <class AV, class BV, int BLOCK, int TSIZE>
+__global__ void __launch_bounds__(BLOCK) k_num_hash_cta(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
+                                                        int *__restrict__ c_ci, double *__restrict__ c_v, int col_bits)
 {
-    extern __shared__ unsigned char smem_raw[];
-    constexpr int NW = TPR / 32;
-    constexpr int GROUPS = BLOCK / TPR;
-    __shared__ int s_wcount[NW > 1 ? NW : 1];
-    int g = threadIdx.x / TPR, t = threadIdx.x % TPR, w = t >> 5, lane = t & 31;
-    int idx = blockIdx.x * GROUPS + g;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    typedef NumHashSmem<BLOCK, TSIZE> SM;
+    typedef typename SM::Sort Sort;
+    constexpr int IPT = SM::IPT;
+    double *vals = reinterpret_cast<double *>(smem_raw);
+    int *keys = reinterpret_cast<int *>(smem_raw + (size_t)TSIZE * 8);
+    typename Sort::TempStorage &sort_tmp = *reinterpret_cast<typename Sort::TempStorage *>(smem_raw + (size_t)TSIZE * 8);
+    int idx = blockIdx.x;
     if (idx >= nrows) return;
-    double *vals = reinterpret_cast<double *>(smem_raw) + (size_t)g * TSIZE;
-    int *keys = reinterpret_cast<int *>(reinterpret_cast<double *>(smem_raw) + (size_t)GROUPS * TSIZE) + (size_t)g * TSIZE;
-    for (int s = t; s < TSIZE; s += TPR) { keys[s] = -1; vals[s] = 0.0; }
-    group_sync<TPR>();
+    int t = threadIdx.x;
+    for (int s = t; s < TSIZE; s += BLOCK) { keys[s] = -1; vals[s] = 0.0; }
+    __syncthreads();
     int li = rows ? rows[idx] : idx;
     int i = r0 + li;
-    typename AV::off_t pe = A.end(i);
-    for (typename AV::off_t p = A.begin(i) + w; p < pe; p += NW) {
-        int j = __ldg(A.ci + p);
-        double av = __ldg(A.v + p);
-        typename BV::off_t qe = B.end(j);
-        for (typename BV::off_t q = B.begin(j) + lane; q < qe; q += 32) {
-            int k = __ldg(B.ci + q);
-            double x = av * __ldg(B.v + q);
-            unsigned s = __umulhi(hash_col(k), (unsigned)TSIZE);
-            while (true) {
-                int cur = keys[s];
-                if (cur == k) break;
-                if (cur == -1) {
-                    int old = atomicCAS(&keys[s], -1, k);
-                    if (old == -1 || old == k) break;
-                }
-                s = (s + 1 == TSIZE) ? 0 : s + 1;
-            }
-            atomicAdd(&vals[s], x);
-        }
-    }
-    group_sync<TPR>();
-
-    // in-place compaction: occupied slots move to the front (write index never passes read index)
-    int n_out = 0;
-    for (int base = 0; base < TSIZE; base += TPR) {
-        int k = keys[base + t];
-        double x = vals[base + t];
-        bool valid = (k != -1);
-        unsigned m = __ballot_sync(0xffffffffu, valid);
-        int wpre = 0, chunk = __popc(m);
-        if (NW > 1) {
-            if (lane == 0) s_wcount[w] = chunk;
-            __syncthreads();
-            chunk = 0;
-            for (int u = 0; u < NW; ++u) { int c = s_wcount[u]; if (u < w) wpre += c; chunk += c; }
-        } else {
-            __syncwarp();
-        }
-        int pos = n_out + wpre + __popc(m & ((1u << lane) - 1u));
-        if (valid) { keys[pos] = k; vals[pos] = x; }
-        n_out += chunk;
-        group_sync<TPR>();
-    }
-    // bitonic sort of the first P2 >= n_out entries by column (padding keys sort last)
-    int p2 = 1;
-    while (p2 < n_out) p2 <<= 1;
-    for (int s = n_out + t; s < p2; s += TPR) keys[s] = 0x7fffffff;
-    group_sync<TPR>();
-    for (int kk = 2; kk <= p2; kk <<= 1) {
-        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
-            for (int e = t; e < (p2 >> 1); e += TPR) {
-                int a = ((e & ~(jj - 1)) << 1) | (e & (jj - 1));
-                int b = a | jj;
-                int ka = keys[a], kb = keys[b];
-                bool up = ((a & kk) == 0);
-                if ((ka > kb) == up) {
-                    keys[a] = kb; keys[b] = ka;
-                    double va = vals[a], vb = vals[b];
-                    vals[a] = vb; vals[b] = va;
-                }
-            }
-            group_sync<TPR>();
-        }
-    }
+    int fresh = 0;
+    __shared__ CtaTile<BV, BLOCK> tile;
+    cta_products<true, BLOCK>(A, B, A.begin(i), A.end(i), tile, [&](typename BV::off_t q, double av) {
+        unsigned s = hash_insert_key<TSIZE>(keys, __ldg(B.ci + q), fresh);
+        atomicAdd(&vals[s], av * __ldg(B.v + q));
+    });
+    __syncthreads();
+    unsigned k[IPT], slot[IPT];
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) { slot[r] = t * IPT + r; k[r] = (unsigned)keys[t * IPT + r]; }
+    __syncthreads();                                   // every key is in registers: the table may be overwritten
+    Sort(sort_tmp).SortBlockedToStriped(k, slot, 0, col_bits + 1);
+    int n = out.count(li);
     long long gs = out.start(li);
-    for (int e = t; e < n_out; e += TPR) { c_ci[gs + e] = keys[e]; c_v[gs + e] = vals[e]; }
+#pragma unroll
+    for (int r = 0; r < IPT; ++r) {
+        int pos = r * BLOCK + t;
+        if (pos < n) { c_ci[gs + pos] = (int)k[r]; c_v[gs + pos] = vals[slot[r]]; }
+    }
+}
+
+// ---- warp per row, at most 32*IPL products: expand - sort - compress entirely in registers.
+// Every product gets the key (column << IDX_BITS | arrival index); a bitonic network over the warp's
+// 32*IPL register-resident keys sorts by column and, inside a column, by arrival order (the order
+// CSR_MUL_CSR accumulates in); a segmented scan adds up equal columns and the last product of each
+// column writes the entry.  Values wait in shared memory (8 B per product) and are fetched by index.
+template <class KeyT>
+__device__ __forceinline__ void cex(KeyT &a, KeyT &b, bool up)
+{
+    KeyT lo = a < b ? a : b, hi = a < b ? b : a;
+    a = up ? lo : hi; b = up ? hi : lo;
+}
+
+template <class KeyT, int IPL>
+__device__ __forceinline__ void warp_bitonic_sort(KeyT (&key)[IPL], int lane)
+{
+    // element index e = lane*IPL + r (blocked); ascending overall
+    constexpr int N = 32 * IPL;
+#pragma unroll
+    for (int kk = 2; kk <= N; kk <<= 1) {
+#pragma unroll
+        for (int jj = kk >> 1; jj > 0; jj >>= 1) {
+            if (jj >= IPL) {
+                int lj = jj / IPL;                                   // partner lane distance
+                bool lower = (lane & lj) == 0;
+#pragma unroll
+                for (int r = 0; r < IPL; ++r) {
+                    int e = lane * IPL + r;
+                    bool up = (e & kk) == 0;
+                    KeyT other = __shfl_xor_sync(0xffffffffu, key[r], lj);
+                    bool keep_min = (lower == up);
+                    key[r] = keep_min ? (key[r] < other ? key[r] : other) : (key[r] < other ? other : key[r]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < IPL; ++r) {
+                    if ((r & jj) == 0) {
+                        int e = lane * IPL + r;
+                        cex(key[r], key[r | jj], (e & kk) == 0);
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <class AV, class BV, class KeyT, int IPL, int BLOCK, bool NUMERIC>
+__global__ void __launch_bounds__(BLOCK) k_esc_warp(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
+                                                    int *__restrict__ nnz_row, int *__restrict__ c_ci, double *__restrict__ c_v)
+{
+    constexpr int N = 32 * IPL;
+    constexpr int IDX_BITS = NUMERIC ? (IPL == 16 ? 9 : IPL == 8 ? 8 : IPL == 4 ? 7 : 6) : 0;
+    constexpr int WARPS = BLOCK / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int idx = blockIdx.x * WARPS + w;
+    if (idx >= nrows) return;
+    KeyT *skeys = reinterpret_cast<KeyT *>(smem_raw) + (size_t)w * N;
+    double *svals = reinterpret_cast<double *>(smem_raw + (size_t)WARPS * N * sizeof(KeyT)) + (size_t)w * N;
+    int li = rows ? rows[idx] : idx;
+    int i = r0 + li;
+    const KeyT PAD = ~(KeyT)0;
+    for (int s = lane; s < N; s += 32) skeys[s] = PAD;
+    __syncwarp();
+    warp_products<NUMERIC>(A, B, A.begin(i), A.end(i), 0, 1, lane, [&](typename BV::off_t q, double av, int pos) {
+        if (pos < N) {                                  // always true: the host sizes IPL from the largest ub of the bin
+            skeys[pos] = ((KeyT)(unsigned)__ldg(B.ci + q) << IDX_BITS) | (KeyT)(NUMERIC ? pos : 0);
+            if (NUMERIC) svals[pos] = av * __ldg(B.v + q);
+        }
+    });
+    __syncwarp();
+    KeyT key[IPL];
+#pragma unroll
+    for (int r = 0; r < IPL; ++r) key[r] = skeys[lane * IPL + r];
+    warp_bitonic_sort<KeyT, IPL>(key, lane);
+    // neighbours: column of the element after my last one (for tail detection)
+    KeyT next_first = __shfl_down_sync(0xffffffffu, key[0], 1);
+    if (lane == 31) next_first = PAD;
+    int tails = 0;
+    bool is_tail[IPL];
+#pragma unroll
+    for (int r = 0; r < IPL; ++r) {
+        KeyT nxt = r + 1 < IPL ? key[r + 1] : next_first;
+        is_tail[r] = key[r] != PAD && (nxt == PAD || (nxt >> IDX_BITS) != (key[r] >> IDX_BITS));
+        tails += is_tail[r];
+    }
+    int tincl = tails;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, tincl, o); if (lane >= o) tincl += u; }
+    if (!NUMERIC) {
+        if (lane == 31) nnz_row[li] = tincl;
+        return;
+    }
+    // segmented sums: heads are elements whose predecessor has another column
+    KeyT prev_last = __shfl_up_sync(0xffffffffu, key[IPL - 1], 1);
+    double v[IPL];
+    bool head[IPL];
+    bool any_head = false;
+    double tail_sum = 0.0;                             // sum since the last head in this lane (all items if none)
+#pragma unroll
+    for (int r = 0; r < IPL; ++r) {
+        bool valid = key[r] != PAD;
+        KeyT prv = r > 0 ? key[r - 1] : prev_last;
+        head[r] = valid && ((r == 0 && lane == 0) || (prv >> IDX_BITS) != (key[r] >> IDX_BITS));
+        v[r] = valid ? svals[(unsigned)(key[r] & (((KeyT)1 << IDX_BITS) - 1))] : 0.0;
+        tail_sum = head[r] ? v[r] : tail_sum + v[r];
+        any_head |= head[r];
+    }
+    // carry from the lanes to the left, stopping at the nearest lane that contains a head
+    double carry = tail_sum;
+    bool flag = any_head;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        double uc = __shfl_up_sync(0xffffffffu, carry, o);
+        bool uf = __shfl_up_sync(0xffffffffu, flag, o);
+        if (lane >= o && !flag) { carry += uc; flag = uf; }
+    }
+    double carry_in = __shfl_up_sync(0xffffffffu, carry, 1);
+    if (lane == 0) carry_in = 0.0;
+    long long gs = out.start(li);
+    int opos = tincl - tails;
+    double run = carry_in;
+#pragma unroll
+    for (int r = 0; r < IPL; ++r) {
+        run = head[r] ? v[r] : run + v[r];
+        if (is_tail[r]) { c_ci[gs + opos] = (int)(key[r] >> IDX_BITS); c_v[gs + opos] = run; ++opos; }
+    }
 }
 
 // ---------------------------------------------------------------- global rows: bitmap + rank in L2
@@ -626,6 +851,7 @@ __global__ void __launch_bounds__(BLOCK) k_sym_global(const int *__restrict__ ro
 {
     constexpr int NW = BLOCK / 32;
     __shared__ int s_row, s_cnt;
+    __shared__ CtaTile<BV, BLOCK> tile;
     unsigned *bm = work + (size_t)blockIdx.x * L.slot_words;
     unsigned *summary = bm + (size_t)L.words * 2;
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -637,12 +863,8 @@ __global__ void __launch_bounds__(BLOCK) k_sym_global(const int *__restrict__ ro
         int li = rows ? rows[idx] : idx;
         int i = r0 + li;
         int cnt = 0;
-        typename AV::off_t pe = A.end(i);
-        for (typename AV::off_t p = A.begin(i) + w; p < pe; p += NW) {
-            int j = __ldg(A.ci + p);
-            typename BV::off_t qe = B.end(j);
-            for (typename BV::off_t q = B.begin(j) + lane; q < qe; q += 32) g_mark(bm, summary, __ldg(B.ci + q), cnt);
-        }
+        cta_products<false, BLOCK>(A, B, A.begin(i), A.end(i), tile,
+                                   [&](typename BV::off_t q, double) { g_mark(bm, summary, __ldg(B.ci + q), cnt); });
         cnt = warp_sum(cnt);
         if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
         __syncthreads();
@@ -661,6 +883,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
     typedef cub::BlockScan<unsigned, BLOCK> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
     __shared__ int s_row;
+    __shared__ CtaTile<BV, BLOCK> tile;
     unsigned *bm = work + (size_t)blockIdx.x * L.slot_words;
     unsigned *prefix = bm + L.words;
     unsigned *summary = prefix + L.words;
@@ -677,11 +900,8 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
         typename AV::off_t pa = A.begin(i), pe = A.end(i);
         // 1. mark the columns of the row
         int dummy = 0;
-        for (typename AV::off_t p = pa + w; p < pe; p += NW) {
-            int j = __ldg(A.ci + p);
-            typename BV::off_t qe = B.end(j);
-            for (typename BV::off_t q = B.begin(j) + lane; q < qe; q += 32) g_mark(bm, summary, __ldg(B.ci + q), dummy);
-        }
+        cta_products<false, BLOCK>(A, B, pa, pe, tile,
+                                   [&](typename BV::off_t q, double) { g_mark(bm, summary, __ldg(B.ci + q), dummy); });
         __syncthreads();
         // 2a. population of every 1024-column block, exclusive scan over blocks
         int per = (L.blocks + BLOCK - 1) / BLOCK;
@@ -722,18 +942,13 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
         __threadfence();         // the zeroed value slots must be in L2 before any RED lands on them
         __syncthreads();
         // 3. accumulate every product at the rank of its column
-        for (typename AV::off_t p = pa + w; p < pe; p += NW) {
-            int j = __ldg(A.ci + p);
-            double av = __ldg(A.v + p);
-            typename BV::off_t qe = B.end(j);
-            for (typename BV::off_t q = B.begin(j) + lane; q < qe; q += 32) {
-                int k = __ldg(B.ci + q);
-                double x = av * __ldg(B.v + q);
-                int wi = k >> 5;
-                unsigned below = __ldcg(bm + wi) & ((1u << (k & 31)) - 1u);
-                atomicAdd(c_v + gs + __ldcg(prefix + wi) + __popc(below), x);
-            }
-        }
+        cta_products<true, BLOCK>(A, B, pa, pe, tile, [&](typename BV::off_t q, double av) {
+            int k = __ldg(B.ci + q);
+            double x = av * __ldg(B.v + q);
+            int wi = k >> 5;
+            unsigned below = __ldcg(bm + wi) & ((1u << (k & 31)) - 1u);
+            atomicAdd(c_v + gs + __ldcg(prefix + wi) + __popc(below), x);
+        });
         __syncthreads();
         // 4. leave the slot clean for the next row
         g_clear<BLOCK>(bm, summary, L);
