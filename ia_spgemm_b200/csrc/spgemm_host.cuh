@@ -108,11 +108,20 @@ inline int read_hist(RangeWork &rw, int n, long long *out)
     return IAS_OK;
 }
 
+// Global rows run as persistent CTAs, one workspace slot each.  Two 512-thread CTAs per SM while all slots
+// together stay around the L2 size; one 1024-thread CTA per SM when the slots are large (R-MAT scale >= 22:
+// 1 MB per slot), so that the bitmap / rank cells keep hitting in L2.
+inline bool g_wide(int ncols)
+{
+    GLayout L = GLayout::make(ncols);
+    return (double)L.slot_words * 4.0 * 2.0 * ctx().sm_count > 160e6;
+}
+
 inline int ensure_gwork(RangeWork &rw, int ncols, long long nrows_g)
 {
     if (nrows_g <= 0) return IAS_OK;
     GLayout L = GLayout::make(ncols);
-    int slots = (int)std::min<long long>(nrows_g, 2LL * ctx().sm_count);
+    int slots = (int)std::min<long long>(nrows_g, (g_wide(ncols) ? 1LL : 2LL) * ctx().sm_count);
     if (rw.gslots >= slots && rw.gwork.p) return IAS_OK;
     IAS_TRY(rw.gwork.alloc((size_t)slots * L.slot_words));
     IAS_CUDA(cudaMemsetAsync(rw.gwork.p, 0, (size_t)slots * L.slot_words * sizeof(unsigned), ctx().stream));
@@ -136,10 +145,15 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
     IAS_CUDA(cudaMemsetAsync(rw.hist.p, 0, 16 * sizeof(unsigned long long), c.stream));
     IAS_CUDA(cudaMemsetAsync(rw.nnz_row.p, 0, sizeof(int) * ((size_t)nrows + 1), c.stream));
     if (nrows == 0) return IAS_OK;
-    if (avg_a_row > 8.0)
-        IAS_LAUNCH((k_row_ub_warp<AV, BV>), grid_for((long long)nrows * 32, 256), 256, 0, nrows, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p);
-    else
-        IAS_LAUNCH((k_row_ub_thread<AV, BV>), grid_for(nrows, 256), 256, 0, nrows, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p);
+    {
+        DBuf<int> long_list, long_count;
+        IAS_TRY(long_list.alloc(nrows));
+        IAS_TRY(long_count.alloc(1));
+        IAS_CUDA(cudaMemsetAsync(long_count.p, 0, sizeof(int), c.stream));
+        IAS_LAUNCH((k_row_ub_thread<AV, BV>), grid_for(nrows, 256), 256, 0, nrows, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p, long_list.p, long_count.p);
+        if (avg_a_row * nrows > LONG_A)        // some row can be long only if the operand has that many entries at all
+            IAS_LAUNCH((k_row_ub_long<AV, BV>), c.sm_count * 8, 256, 0, long_list.p, long_count.p, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p);
+    }
     // canonical B: the analyze kernel has just checked the rows of A it walked; that covers B only when B is A
     // and the range is the whole matrix, otherwise B gets its own pass (4 B per entry of B)
     bool covered = b_is_a && r0 == 0 && r1 == b_rows;
@@ -218,8 +232,12 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
         int n = (int)bl.count[BIN_G];
         IAS_TRY(ensure_gwork(rw, ncols_b, n));
         IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
-        IAS_LAUNCH((k_sym_global<AV, BV, G_BLOCK>), rw.gslots, G_BLOCK, 0, bl.rows_of(BIN_G), n, r0, A, B, rw.nnz_row.p, rw.gwork.p,
-                   GLayout::make(ncols_b), rw.cursor.p);
+        if (g_wide(ncols_b))
+            IAS_LAUNCH((k_sym_global<AV, BV, 1024>), rw.gslots, 1024, 0, bl.rows_of(BIN_G), n, r0, A, B, rw.nnz_row.p, rw.gwork.p,
+                       GLayout::make(ncols_b), rw.cursor.p);
+        else
+            IAS_LAUNCH((k_sym_global<AV, BV, G_BLOCK>), rw.gslots, G_BLOCK, 0, bl.rows_of(BIN_G), n, r0, A, B, rw.nnz_row.p, rw.gwork.p,
+                       GLayout::make(ncols_b), rw.cursor.p);
         IAS_BIN_END(BIN_G);
         rw.sym_timed[BIN_G] = true;
     }
@@ -319,8 +337,12 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         int m = (int)bl.count[BIN_G];
         IAS_TRY(ensure_gwork(rw, ncols_b, m));
         IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
-        IAS_LAUNCH((k_num_global<AV, BV, G_BLOCK>), rw.gslots, G_BLOCK, 0, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
-                   GLayout::make(ncols_b), rw.cursor.p);
+        if (g_wide(ncols_b))
+            IAS_LAUNCH((k_num_global<AV, BV, 1024>), rw.gslots, 1024, 0, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
+                       GLayout::make(ncols_b), rw.cursor.p);
+        else
+            IAS_LAUNCH((k_num_global<AV, BV, G_BLOCK>), rw.gslots, G_BLOCK, 0, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
+                       GLayout::make(ncols_b), rw.cursor.p);
         IAS_BIN_END(8 + BIN_G);
         rw.num_timed[BIN_G] = true;
     }

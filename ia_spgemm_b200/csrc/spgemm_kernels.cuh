@@ -110,11 +110,15 @@ __device__ __forceinline__ void block_hist(int bin, long long ub, unsigned *s_cn
     if (threadIdx.x == NBINS && *s_sum) atomicAdd(&g_hist[NBINS], *s_sum);
 }
 
-// one thread per row (short A rows)
+// one thread per row; rows with more than LONG_A entries are deferred to k_row_ub_long (a thread would
+// crawl through a 100 000-entry R-MAT hub row while its 255 neighbours idle)
+constexpr int LONG_A = 64;
+
 template <class AV, class BV>
 __global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, BV B, int *__restrict__ ub_out,
                                                        unsigned char *__restrict__ bin_out,
-                                                       unsigned long long *__restrict__ g_hist /*NBINS + 1*/)
+                                                       unsigned long long *__restrict__ g_hist /*16 slots*/,
+                                                       int *__restrict__ long_list, int *__restrict__ long_count)
 {
     __shared__ unsigned s_cnt[NBINS];
     __shared__ unsigned long long s_sum;
@@ -128,20 +132,24 @@ __global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, 
     int bin = -1, tiny_na = 0, tiny_ub = 0;
     if (li < nrows) {
         int i = r0 + li;
-        typename AV::off_t pe = A.end(i);
-        int prev = -1, unsorted = 0;
-        for (typename AV::off_t p = A.begin(i); p < pe; ++p) {
-            int j = __ldg(A.ci + p);
-            unsorted |= (j <= prev);
-            prev = j;
-            ub += B.len(j);
+        typename AV::off_t pa = A.begin(i), pe = A.end(i);
+        if (pe - pa > LONG_A) {
+            long_list[atomicAdd(long_count, 1)] = li;
+        } else {
+            int prev = -1, unsorted = 0;
+            for (typename AV::off_t p = pa; p < pe; ++p) {
+                int j = __ldg(A.ci + p);
+                unsorted |= (j <= prev);
+                prev = j;
+                ub += B.len(j);
+            }
+            if (unsorted) g_hist[NBINS + 1] = 1;      // A (== B for A^2) is not canonical
+            bin = sym_bin_of(ub);
+            tiny_na = (bin == BIN_T) ? (int)(pe - pa) : 0;
+            tiny_ub = (bin == BIN_T) ? (int)ub : (bin == BIN_W ? -(int)ub : 0);   // negative: a warp-bin row
+            ub_out[li] = ub > 0x7fffffffLL ? 0x7fffffff : (int)ub;
+            bin_out[li] = (unsigned char)bin;
         }
-        if (unsorted) g_hist[NBINS + 1] = 1;      // A (== B for A^2) is not canonical
-        bin = sym_bin_of(ub);
-        tiny_na = (bin == BIN_T) ? (int)(pe - A.begin(i)) : 0;
-        tiny_ub = (bin == BIN_T) ? (int)ub : (bin == BIN_W ? -(int)ub : 0);   // negative: a warp-bin row
-        ub_out[li] = ub > 0x7fffffffLL ? 0x7fffffff : (int)ub;
-        bin_out[li] = (unsigned char)bin;
     }
     int warp_ub = __reduce_max_sync(0xffffffffu, tiny_ub < 0 ? -tiny_ub : 0);
     tiny_na = __reduce_max_sync(0xffffffffu, tiny_na);
@@ -156,10 +164,10 @@ __global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, 
         atomicMax(&g_hist[NBINS + 2 + threadIdx.x], (unsigned long long)s_max[threadIdx.x]);
 }
 
-// one warp per row (long / skewed A rows)
+// the deferred long rows: one warp per row, persistent grid
 template <class AV, class BV>
-__global__ void __launch_bounds__(256) k_row_ub_warp(int nrows, int r0, AV A, BV B, int *__restrict__ ub_out,
-                                                     unsigned char *__restrict__ bin_out,
+__global__ void __launch_bounds__(256) k_row_ub_long(const int *__restrict__ long_list, const int *__restrict__ long_count, int r0,
+                                                     AV A, BV B, int *__restrict__ ub_out, unsigned char *__restrict__ bin_out,
                                                      unsigned long long *__restrict__ g_hist)
 {
     __shared__ unsigned s_cnt[NBINS];
@@ -167,13 +175,14 @@ __global__ void __launch_bounds__(256) k_row_ub_warp(int nrows, int r0, AV A, BV
     if (threadIdx.x < NBINS) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x == NBINS) s_sum = 0;
     __syncthreads();
-    int lane = threadIdx.x & 31;
-    int li = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    long long ub = 0;
-    int bin = -1;
-    if (li < nrows) {
+    const int lane = threadIdx.x & 31;
+    const int n = *long_count;
+    const int nwarps = (gridDim.x * blockDim.x) >> 5;
+    for (int idx = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; idx < n; idx += nwarps) {
+        int li = long_list[idx];
         int i = r0 + li;
         typename AV::off_t pa = A.begin(i), pe = A.end(i);
+        long long ub = 0;
         int unsorted = 0;
         for (typename AV::off_t p = pa + lane; p < pe; p += 32) {
             int j = __ldg(A.ci + p);
@@ -183,19 +192,17 @@ __global__ void __launch_bounds__(256) k_row_ub_warp(int nrows, int r0, AV A, BV
         if (unsorted) g_hist[NBINS + 1] = 1;
         ub = warp_sum(ub);
         if (lane == 0) {
-            bin = sym_bin_of(ub);
+            int bin = sym_bin_of(ub);                      // never tiny: more than LONG_A entries
             ub_out[li] = ub > 0x7fffffffLL ? 0x7fffffff : (int)ub;
             bin_out[li] = (unsigned char)bin;
-            if (bin == BIN_T) {
-                if ((unsigned long long)(pe - pa) > g_hist[NBINS + 2]) atomicMax(&g_hist[NBINS + 2], (unsigned long long)(pe - pa));
-                if ((unsigned long long)ub > g_hist[NBINS + 3]) atomicMax(&g_hist[NBINS + 3], (unsigned long long)ub);
-            }
+            atomicAdd(&s_cnt[bin], 1u);
+            if (ub) atomicAdd(&s_sum, (unsigned long long)ub);
             if (bin == BIN_W && (unsigned long long)ub > g_hist[NBINS + 4]) atomicMax(&g_hist[NBINS + 4], (unsigned long long)ub);
-        } else {
-            ub = 0;                                  // the row's total is counted once
         }
     }
-    block_hist(bin, ub, s_cnt, &s_sum, g_hist);
+    __syncthreads();
+    if (threadIdx.x < NBINS && s_cnt[threadIdx.x]) atomicAdd(&g_hist[threadIdx.x], (unsigned long long)s_cnt[threadIdx.x]);
+    if (threadIdx.x == NBINS && s_sum) atomicAdd(&g_hist[NBINS], s_sum);
 }
 
 // numeric bins from exact counts; also the largest nnz(C_i) among tiny rows (sizes k_num_tiny's smem)
@@ -582,9 +589,8 @@ __global__ void __launch_bounds__(BLOCK) k_sym_hash(const int *__restrict__ rows
                                                     int *__restrict__ nnz_row)
 {
     extern __shared__ unsigned char smem_raw[];
-    constexpr int NW = TPR / 32;
     __shared__ int s_cnt;
-    int g = threadIdx.x / TPR, t = threadIdx.x % TPR, w = t >> 5, lane = t & 31;
+    int g = threadIdx.x / TPR, t = threadIdx.x % TPR, lane = t & 31;
     int idx = blockIdx.x * (BLOCK / TPR) + g;
     if (idx >= nrows) return;                       // whole group leaves together
     int *keys = reinterpret_cast<int *>(smem_raw) + (size_t)g * TSIZE;
@@ -795,8 +801,7 @@ __global__ void __launch_bounds__(BLOCK) k_esc_warp(const int *__restrict__ rows
 
 // ---------------------------------------------------------------- global rows: bitmap + rank in L2
 // Workspace of one slot (all 32-bit words, zero between rows except prefix/blkpref):
-//   bm[words]       column bitmap                      words   = ceil(ncols/32) rounded up to 32
-//   prefix[words]   output rank of each word's first bit
+//   wp[words]       {bitmap word, output rank of its first bit}   words = ceil(ncols/32) rounded up to 32
 //   summary[sumw]   one bit per block of 32 bitmap words (= 1024 columns)
 //   blkpref[blocks] output rank of each block           blocks = words/32, sumw = ceil(blocks/32)
 struct GLayout {
@@ -813,13 +818,15 @@ struct GLayout {
     }
 };
 
-__device__ __forceinline__ void g_mark(unsigned *bm, unsigned *summary, int k, int &cnt)
+// bitmap word and rank prefix of the same 32 columns share one 8-byte cell {bits, rank}: the accumulate
+// pass needs both and gets them with a single L2 access (the global path is bound by L2 transactions)
+__device__ __forceinline__ void g_mark(uint2 *wp, unsigned *summary, int k, int &cnt)
 {
     int w = k >> 5;
     unsigned bit = 1u << (k & 31);
-    unsigned cur = __ldcg(bm + w);
+    unsigned cur = __ldcg(&wp[w].x);
     if (!(cur & bit)) {
-        unsigned old = atomicOr(bm + w, bit);
+        unsigned old = atomicOr(&wp[w].x, bit);
         if (!(old & bit)) {
             ++cnt;
             if (old == 0) atomicOr(summary + (w >> 10), 1u << ((w >> 5) & 31));
@@ -828,7 +835,7 @@ __device__ __forceinline__ void g_mark(unsigned *bm, unsigned *summary, int k, i
 }
 
 template <int BLOCK>
-__device__ __forceinline__ void g_clear(unsigned *bm, unsigned *summary, const GLayout &L)
+__device__ __forceinline__ void g_clear(uint2 *wp, unsigned *summary, const GLayout &L)
 {
     for (int sw = threadIdx.x; sw < L.sumw; sw += BLOCK) {
         unsigned m = __ldcg(summary + sw);
@@ -837,9 +844,9 @@ __device__ __forceinline__ void g_clear(unsigned *bm, unsigned *summary, const G
         while (m) {
             int b = __ffs(m) - 1;
             m &= m - 1;
-            uint4 *p = reinterpret_cast<uint4 *>(bm + ((size_t)sw * 32 + b) * 32);
+            uint4 *p = reinterpret_cast<uint4 *>(wp + ((size_t)sw * 32 + b) * 32);
 #pragma unroll
-            for (int x = 0; x < 8; ++x) p[x] = make_uint4(0, 0, 0, 0);
+            for (int x = 0; x < 16; ++x) p[x] = make_uint4(0, 0, 0, 0);
         }
     }
 }
@@ -849,12 +856,11 @@ __global__ void __launch_bounds__(BLOCK) k_sym_global(const int *__restrict__ ro
                                                       int *__restrict__ nnz_row, unsigned *__restrict__ work, GLayout L,
                                                       int *__restrict__ cursor)
 {
-    constexpr int NW = BLOCK / 32;
     __shared__ int s_row, s_cnt;
     __shared__ CtaTile<BV, BLOCK> tile;
-    unsigned *bm = work + (size_t)blockIdx.x * L.slot_words;
-    unsigned *summary = bm + (size_t)L.words * 2;
-    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint2 *wp = reinterpret_cast<uint2 *>(work + (size_t)blockIdx.x * L.slot_words);
+    unsigned *summary = reinterpret_cast<unsigned *>(wp + L.words);
+    int lane = threadIdx.x & 31;
     while (true) {
         if (threadIdx.x == 0) { s_row = atomicAdd(cursor, 1); s_cnt = 0; }
         __syncthreads();
@@ -864,12 +870,12 @@ __global__ void __launch_bounds__(BLOCK) k_sym_global(const int *__restrict__ ro
         int i = r0 + li;
         int cnt = 0;
         cta_products<false, BLOCK>(A, B, A.begin(i), A.end(i), tile,
-                                   [&](typename BV::off_t q, double) { g_mark(bm, summary, __ldg(B.ci + q), cnt); });
+                                   [&](typename BV::off_t q, double) { g_mark(wp, summary, __ldg(B.ci + q), cnt); });
         cnt = warp_sum(cnt);
         if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
         __syncthreads();
         if (threadIdx.x == 0) nnz_row[li] = s_cnt;
-        g_clear<BLOCK>(bm, summary, L);
+        g_clear<BLOCK>(wp, summary, L);
         __syncthreads();
     }
 }
@@ -884,9 +890,8 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
     __shared__ typename Scan::TempStorage scan_tmp;
     __shared__ int s_row;
     __shared__ CtaTile<BV, BLOCK> tile;
-    unsigned *bm = work + (size_t)blockIdx.x * L.slot_words;
-    unsigned *prefix = bm + L.words;
-    unsigned *summary = prefix + L.words;
+    uint2 *wp = reinterpret_cast<uint2 *>(work + (size_t)blockIdx.x * L.slot_words);
+    unsigned *summary = reinterpret_cast<unsigned *>(wp + L.words);
     unsigned *blkpref = summary + L.sumw;
     int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
     while (true) {
@@ -901,7 +906,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
         // 1. mark the columns of the row
         int dummy = 0;
         cta_products<false, BLOCK>(A, B, pa, pe, tile,
-                                   [&](typename BV::off_t q, double) { g_mark(bm, summary, __ldg(B.ci + q), dummy); });
+                                   [&](typename BV::off_t q, double) { g_mark(wp, summary, __ldg(B.ci + q), dummy); });
         __syncthreads();
         // 2a. population of every 1024-column block, exclusive scan over blocks
         int per = (L.blocks + BLOCK - 1) / BLOCK;
@@ -910,9 +915,9 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
         for (int b = b0; b < b1; ++b) {
             unsigned c = 0;
             if ((__ldcg(summary + (b >> 5)) >> (b & 31)) & 1u) {
-                const uint4 *p4 = reinterpret_cast<const uint4 *>(bm + (size_t)b * 32);
+                const uint4 *p4 = reinterpret_cast<const uint4 *>(wp + (size_t)b * 32);
 #pragma unroll
-                for (int x = 0; x < 8; ++x) { uint4 u = __ldcg(p4 + x); c += __popc(u.x) + __popc(u.y) + __popc(u.z) + __popc(u.w); }
+                for (int x = 0; x < 16; ++x) { uint4 u = __ldcg(p4 + x); c += __popc(u.x) + __popc(u.z); }
             }
             blkpref[b] = c;
             local += c;
@@ -925,12 +930,12 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
         for (int b = w; b < L.blocks; b += NW) {
             if (!((__ldcg(summary + (b >> 5)) >> (b & 31)) & 1u)) continue;
             int wi = b * 32 + lane;
-            unsigned word = __ldcg(bm + wi);
+            unsigned word = __ldcg(&wp[wi].x);
             unsigned c = __popc(word), incl = c;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
             unsigned rank = __ldcg(blkpref + b) + incl - c;
-            prefix[wi] = rank;
+            wp[wi].y = rank;
             while (word) {
                 int bit = __ffs(word) - 1;
                 word &= word - 1;
@@ -941,17 +946,17 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
         }
         __threadfence();         // the zeroed value slots must be in L2 before any RED lands on them
         __syncthreads();
-        // 3. accumulate every product at the rank of its column
+        // 3. accumulate every product at the rank of its column: one 8-byte L2 read + one RED.F64
         cta_products<true, BLOCK>(A, B, pa, pe, tile, [&](typename BV::off_t q, double av) {
             int k = __ldg(B.ci + q);
             double x = av * __ldg(B.v + q);
-            int wi = k >> 5;
-            unsigned below = __ldcg(bm + wi) & ((1u << (k & 31)) - 1u);
-            atomicAdd(c_v + gs + __ldcg(prefix + wi) + __popc(below), x);
+            uint2 cell = __ldcg(wp + (k >> 5));
+            unsigned below = cell.x & ((1u << (k & 31)) - 1u);
+            atomicAdd(c_v + gs + cell.y + __popc(below), x);
         });
         __syncthreads();
         // 4. leave the slot clean for the next row
-        g_clear<BLOCK>(bm, summary, L);
+        g_clear<BLOCK>(wp, summary, L);
         __syncthreads();
     }
 }
