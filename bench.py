@@ -370,8 +370,15 @@ def main():
         b = int(np.argmax(bins))
         dom_name, dom_ms = names[b], float(bins[b])
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0
+    # dram__bytes_read.sum + dram__bytes_write.sum of that kernel, per launch, from the committed ncu --set full capture
+    traffic = None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        traffic = tj.get(workload_name(args, world), {}).get(dom_name.split("<")[0])
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes": alg_bytes,
+                "traffic": traffic, "peak_source": peak_src, "kernel_ms": dom_ms, "algorithmic_bytes": alg_bytes,
                 "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / peak}
 
     # ---- e2e: host operands in pinned memory -> C in pinned host memory, copies inside the timed region

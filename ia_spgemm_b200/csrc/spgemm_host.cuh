@@ -117,11 +117,11 @@ inline bool g_wide(int ncols)
     return (double)L.slot_words * 4.0 * 2.0 * ctx().sm_count > 160e6;
 }
 
-inline int ensure_gwork(RangeWork &rw, int ncols, long long nrows_g)
+inline int ensure_gwork(RangeWork &rw, int ncols, long long nrows_g, bool one_per_sm = false)
 {
     if (nrows_g <= 0) return IAS_OK;
     GLayout L = GLayout::make(ncols);
-    int slots = (int)std::min<long long>(nrows_g, (g_wide(ncols) ? 1LL : 2LL) * ctx().sm_count);
+    int slots = (int)std::min<long long>(nrows_g, ((one_per_sm || g_wide(ncols)) ? 1LL : 2LL) * ctx().sm_count);
     if (rw.gslots >= slots && rw.gwork.p) return IAS_OK;
     IAS_TRY(rw.gwork.alloc((size_t)slots * L.slot_words));
     IAS_CUDA(cudaMemsetAsync(rw.gwork.p, 0, (size_t)slots * L.slot_words * sizeof(unsigned), ctx().stream));
@@ -335,14 +335,16 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
     if (bl.count[BIN_G]) {
         IAS_BIN_BEGIN(8 + BIN_G);
         int m = (int)bl.count[BIN_G];
-        IAS_TRY(ensure_gwork(rw, ncols_b, m));
+        IAS_TRY(ensure_gwork(rw, ncols_b, m, true));
         IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
-        if (g_wide(ncols_b))
-            IAS_LAUNCH((k_num_global<AV, BV, 1024>), rw.gslots, 1024, 0, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
-                       GLayout::make(ncols_b), rw.cursor.p);
-        else
-            IAS_LAUNCH((k_num_global<AV, BV, G_BLOCK>), rw.gslots, G_BLOCK, 0, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
-                       GLayout::make(ncols_b), rw.cursor.p);
+        {
+            auto k = k_num_global<AV, BV, 1024>;
+            int win = 24576;                                   // 192 KB tile of fp64 partial sums
+            size_t sm = (size_t)win * sizeof(double);
+            IAS_TRY(opt_in_smem(k, sm));
+            IAS_LAUNCH(k, rw.gslots, 1024, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p, GLayout::make(ncols_b),
+                       rw.cursor.p, win, rw.b_canonical, getenv("IAS_G_DBG") ? atoi(getenv("IAS_G_DBG")) : 0);
+        }
         IAS_BIN_END(8 + BIN_G);
         rw.num_timed[BIN_G] = true;
     }

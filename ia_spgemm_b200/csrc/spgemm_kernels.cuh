@@ -514,9 +514,8 @@ __device__ __forceinline__ int warp_products(const AV &A, const BV &B, typename 
 // ---- the same for a whole CTA: balanced over all threads.
 // ncu on R-MAT showed CTA-per-row kernels issuing 3 % of the time, the rest spent at barriers behind
 // the one warp that drew a hub row.  Here the A row is taken in tiles of BLOCK entries: thread t loads
-// entry t, a block scan numbers the tile's products 0..T-1, and thread t processes products t, t+BLOCK,
-// ... finding the owning entry by binary search in shared memory (skipped while it stays inside the
-// same B row, i.e. almost always on hub rows).  Every thread gets the same number of products.
+// entry t, a block scan numbers the tile's products 0..T-1, and the products are dealt out evenly to the
+// warps (see the loop below).  Every warp gets the same number of products.
 template <class BV, int BLOCK>
 struct CtaTile {
     typedef cub::BlockScan<int, BLOCK> Scan;
@@ -526,9 +525,36 @@ struct CtaTile {
     double av[BLOCK];
 };
 
-template <bool NEED_VALUES, int BLOCK, class AV, class BV, class F>
+struct NoRestrict {
+    template <class O>
+    __device__ __forceinline__ void operator()(O &, int &) const {}
+};
+
+// columns of a sorted B row restricted to [c_lo, c_hi): two lower bounds
+template <class BV>
+struct ColumnWindow {
+    const BV &B;
+    int c_lo, c_hi;
+    __device__ __forceinline__ typename BV::off_t lower(typename BV::off_t b, int len, int c) const
+    {
+        int lo = 0, hi = len;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(B.ci + b + mid) < c) lo = mid + 1; else hi = mid; }
+        return b + lo;
+    }
+    __device__ __forceinline__ void operator()(typename BV::off_t &qb, int &len) const
+    {
+        if (len == 0) return;
+        typename BV::off_t s = lower(qb, len, c_lo);
+        typename BV::off_t e = c_hi == 0x7fffffff ? qb + len : lower(qb, len, c_hi);
+        qb = s; len = (int)(e - s);
+    }
+};
+
+constexpr int PB = 4;      // products per lane and trip in cta_products
+
+template <bool NEED_VALUES, int BLOCK, class AV, class BV, class F, class R = NoRestrict>
 __device__ __forceinline__ void cta_products(const AV &A, const BV &B, typename AV::off_t pa, typename AV::off_t pe,
-                                             CtaTile<BV, BLOCK> &tile, F &&f)
+                                             CtaTile<BV, BLOCK> &tile, F &&f, const R &restrict_range = R())
 {
     typedef typename AV::off_t aoff;
     typedef typename BV::off_t boff;
@@ -542,6 +568,7 @@ __device__ __forceinline__ void cta_products(const AV &A, const BV &B, typename 
             int j = __ldg(A.ci + p);
             qb = B.begin(j);
             len = (int)(B.end(j) - qb);
+            restrict_range(qb, len);
             if (NEED_VALUES) av = __ldg(A.v + p);
         }
         int incl;
@@ -550,18 +577,39 @@ __device__ __forceinline__ void cta_products(const AV &A, const BV &B, typename 
         tile.rel[tid] = qb - (boff)(incl - len);
         if (NEED_VALUES) tile.av[tid] = av;
         __syncthreads();
+        // every warp takes an equal, contiguous share of the tile's products; its lanes take consecutive
+        // products (coalesced B reads).  The owning entry is found once per warp by binary search and then
+        // followed forward: on hub rows the scan loop exits at once, on short rows it advances a few entries.
         const int total = tile.incl[BLOCK - 1];
-        int e = 0, lo_t = 0, hi_t = tile.incl[0];          // products [lo_t, hi_t) belong to entry e
-        for (int t = tid; t < total; t += BLOCK) {
-            if (t >= hi_t) {
-                int lo = e + 1, hi = BLOCK - 1;            // smallest entry whose inclusive count exceeds t
-                while (lo < hi) { int mid = (lo + hi) >> 1; if (tile.incl[mid] <= t) lo = mid + 1; else hi = mid; }
-                e = lo;
-                hi_t = tile.incl[e];
-                lo_t = tile.incl[e - 1];
+        constexpr int NWARPS = BLOCK / 32;
+        const int wid = tid >> 5, lane = tid & 31;
+        const int share = ((total + NWARPS - 1) / NWARPS + 31) & ~31;
+        const int t_begin = wid * share, t_end = min(total, t_begin + share);
+        if (t_begin < t_end) {
+            int lo = 0, hi = BLOCK - 1;                    // smallest entry whose inclusive count exceeds t_begin
+            while (lo < hi) { int mid = (lo + hi) >> 1; if (tile.incl[mid] <= t_begin) lo = mid + 1; else hi = mid; }
+            int e = lo;
+            // PB products per lane and trip: f receives them together so that it can issue all its loads
+            // before the first dependent use (the kernels are bound by L2 latency, not by issue slots)
+            for (int t0 = t_begin; t0 < t_end; t0 += 32 * PB) {
+                typename BV::off_t q[PB];
+                double pav[PB];
+                unsigned valid = 0;
+                int me = e;
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    int t = t0 + 32 * u + lane;
+                    q[u] = 0; pav[u] = 0.0;
+                    if (t < t_end) {
+                        while (tile.incl[me] <= t) ++me;
+                        q[u] = tile.rel[me] + t;
+                        if (NEED_VALUES) pav[u] = tile.av[me];
+                        valid |= 1u << u;
+                    }
+                }
+                f(q, pav, valid);
+                e = __shfl_sync(0xffffffffu, me, 31);      // lane 31 holds the furthest entry reached in this trip
             }
-            (void)lo_t;
-            f(tile.rel[e] + t, NEED_VALUES ? tile.av[e] : 0.0);
         }
         __syncthreads();                                   // the tile arrays are rewritten by the next pass
     }
@@ -606,8 +654,14 @@ __global__ void __launch_bounds__(BLOCK) k_sym_hash(const int *__restrict__ rows
         });
     } else {
         __shared__ CtaTile<BV, TPR == 32 ? 32 : BLOCK> tile;
-        cta_products<false, TPR == 32 ? 32 : BLOCK>(A, B, A.begin(i), A.end(i), tile, [&](typename BV::off_t q, double) {
-            hash_insert_key<TSIZE>(keys, __ldg(B.ci + q), cnt);
+        cta_products<false, TPR == 32 ? 32 : BLOCK>(A, B, A.begin(i), A.end(i), tile,
+                                                    [&](const typename BV::off_t (&q)[PB], const double (&)[PB], unsigned valid) {
+            int k[PB];
+#pragma unroll
+            for (int u = 0; u < PB; ++u) k[u] = (valid >> u) & 1u ? __ldg(B.ci + q[u]) : -1;
+#pragma unroll
+            for (int u = 0; u < PB; ++u)
+                if (k[u] >= 0) hash_insert_key<TSIZE>(keys, k[u], cnt);
         });
     }
     cnt = warp_sum(cnt);
@@ -652,9 +706,18 @@ __global__ void __launch_bounds__(BLOCK) k_num_hash_cta(const int *__restrict__ 
     int i = r0 + li;
     int fresh = 0;
     __shared__ CtaTile<BV, BLOCK> tile;
-    cta_products<true, BLOCK>(A, B, A.begin(i), A.end(i), tile, [&](typename BV::off_t q, double av) {
-        unsigned s = hash_insert_key<TSIZE>(keys, __ldg(B.ci + q), fresh);
-        atomicAdd(&vals[s], av * __ldg(B.v + q));
+    cta_products<true, BLOCK>(A, B, A.begin(i), A.end(i), tile,
+                              [&](const typename BV::off_t (&q)[PB], const double (&av)[PB], unsigned valid) {
+        int k[PB];
+        double x[PB];
+#pragma unroll
+        for (int u = 0; u < PB; ++u) {
+            k[u] = -1; x[u] = 0.0;
+            if ((valid >> u) & 1u) { k[u] = __ldg(B.ci + q[u]); x[u] = av[u] * __ldg(B.v + q[u]); }
+        }
+#pragma unroll
+        for (int u = 0; u < PB; ++u)
+            if (k[u] >= 0) { unsigned s = hash_insert_key<TSIZE>(keys, k[u], fresh); atomicAdd(&vals[s], x[u]); }
     });
     __syncthreads();
     unsigned k[IPT], slot[IPT];
@@ -804,6 +867,8 @@ __global__ void __launch_bounds__(BLOCK) k_esc_warp(const int *__restrict__ rows
 //   wp[words]       {bitmap word, output rank of its first bit}   words = ceil(ncols/32) rounded up to 32
 //   summary[sumw]   one bit per block of 32 bitmap words (= 1024 columns)
 //   blkpref[blocks] output rank of each block           blocks = words/32, sumw = ceil(blocks/32)
+//   wsum[blocks]    which of a block's 32 words are non-zero: the per-row scans read 4 bytes per block and
+//                   only the populated cells instead of the whole 8*cols/32-byte cell array
 struct GLayout {
     int words, blocks, sumw;
     size_t slot_words;          // words + words + sumw + blocks
@@ -813,42 +878,61 @@ struct GLayout {
         long long w = ((long long)ncols + 31) / 32;
         w = (w + 31) / 32 * 32;
         g.words = (int)w; g.blocks = g.words / 32; g.sumw = (g.blocks + 31) / 32;
-        g.slot_words = ((size_t)g.words * 2 + g.sumw + g.blocks + 31) / 32 * 32;   // keeps every slot 128-byte aligned
+        g.slot_words = ((size_t)g.words * 2 + g.sumw + 2 * (size_t)g.blocks + 31) / 32 * 32;   // keeps every slot 128-byte aligned
         return g;
     }
 };
 
 // bitmap word and rank prefix of the same 32 columns share one 8-byte cell {bits, rank}: the accumulate
 // pass needs both and gets them with a single L2 access (the global path is bound by L2 transactions)
-__device__ __forceinline__ void g_mark(uint2 *wp, unsigned *summary, int k, int &cnt)
+// a word that turns non-zero registers itself in its block's word mask, a block that turns non-zero in the summary
+__device__ __forceinline__ void g_first_touch(unsigned *summary, unsigned *wsum, int w)
 {
-    int w = k >> 5;
-    unsigned bit = 1u << (k & 31);
-    unsigned cur = __ldcg(&wp[w].x);
-    if (!(cur & bit)) {
-        unsigned old = atomicOr(&wp[w].x, bit);
-        if (!(old & bit)) {
-            ++cnt;
-            if (old == 0) atomicOr(summary + (w >> 10), 1u << ((w >> 5) & 31));
+    unsigned oldm = atomicOr(wsum + (w >> 5), 1u << (w & 31));
+    if (oldm == 0) atomicOr(summary + (w >> 10), 1u << ((w >> 5) & 31));
+}
+
+// PB products at once: all column loads, then all cell loads, then the (rare) atomics
+template <class BV>
+__device__ __forceinline__ void g_mark_batch(const BV &B, uint2 *wp, unsigned *summary, unsigned *wsum,
+                                             const typename BV::off_t (&q)[PB], unsigned valid, int &cnt)
+{
+    int k[PB];
+    unsigned cur[PB];
+#pragma unroll
+    for (int u = 0; u < PB; ++u) k[u] = (valid >> u) & 1u ? __ldg(B.ci + q[u]) : -1;
+#pragma unroll
+    for (int u = 0; u < PB; ++u) cur[u] = k[u] >= 0 ? __ldcg(&wp[k[u] >> 5].x) : 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < PB; ++u) {
+        if (k[u] < 0) continue;
+        int w = k[u] >> 5;
+        unsigned bit = 1u << (k[u] & 31);
+        if (!(cur[u] & bit)) {
+            unsigned old = atomicOr(&wp[w].x, bit);
+            if (!(old & bit)) {
+                ++cnt;
+                if (old == 0) g_first_touch(summary, wsum, w);
+            }
         }
     }
 }
 
+// zero exactly the cells that were touched (found through wsum), one thread per 1024-column block: the
+// per-row passes over the workspace are latency bound, so every thread issues its block's accesses at once
 template <int BLOCK>
-__device__ __forceinline__ void g_clear(uint2 *wp, unsigned *summary, const GLayout &L)
+__device__ __forceinline__ void g_clear(uint2 *wp, unsigned *summary, unsigned *wsum, const GLayout &L)
 {
-    for (int sw = threadIdx.x; sw < L.sumw; sw += BLOCK) {
-        unsigned m = __ldcg(summary + sw);
+    for (int b = threadIdx.x; b < L.blocks; b += BLOCK) {
+        unsigned m = __ldcg(wsum + b);
         if (!m) continue;
-        summary[sw] = 0;
-        while (m) {
-            int b = __ffs(m) - 1;
-            m &= m - 1;
-            uint4 *p = reinterpret_cast<uint4 *>(wp + ((size_t)sw * 32 + b) * 32);
+        wsum[b] = 0;
+        uint2 *cell = wp + (size_t)b * 32;
 #pragma unroll
-            for (int x = 0; x < 16; ++x) p[x] = make_uint4(0, 0, 0, 0);
-        }
+        for (int x = 0; x < 32; ++x)
+            if ((m >> x) & 1u) cell[x] = make_uint2(0, 0);
     }
+    for (int sw = threadIdx.x; sw < L.sumw; sw += BLOCK) summary[sw] = 0;
 }
 
 template <class AV, class BV, int BLOCK>
@@ -860,6 +944,7 @@ __global__ void __launch_bounds__(BLOCK) k_sym_global(const int *__restrict__ ro
     __shared__ CtaTile<BV, BLOCK> tile;
     uint2 *wp = reinterpret_cast<uint2 *>(work + (size_t)blockIdx.x * L.slot_words);
     unsigned *summary = reinterpret_cast<unsigned *>(wp + L.words);
+    unsigned *wsum = summary + L.sumw + L.blocks;
     int lane = threadIdx.x & 31;
     while (true) {
         if (threadIdx.x == 0) { s_row = atomicAdd(cursor, 1); s_cnt = 0; }
@@ -870,93 +955,137 @@ __global__ void __launch_bounds__(BLOCK) k_sym_global(const int *__restrict__ ro
         int i = r0 + li;
         int cnt = 0;
         cta_products<false, BLOCK>(A, B, A.begin(i), A.end(i), tile,
-                                   [&](typename BV::off_t q, double) { g_mark(wp, summary, __ldg(B.ci + q), cnt); });
+                                   [&](const typename BV::off_t (&q)[PB], const double (&)[PB], unsigned valid) {
+                                       g_mark_batch(B, wp, summary, wsum, q, valid, cnt);
+                                   });
         cnt = warp_sum(cnt);
         if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
         __syncthreads();
         if (threadIdx.x == 0) nnz_row[li] = s_cnt;
-        g_clear<BLOCK>(wp, summary, L);
+        g_clear<BLOCK>(wp, summary, wsum, L);
         __syncthreads();
     }
 }
 
+// Numeric pass of a global row.  The values are NOT accumulated in global memory: with hundreds of
+// rows in flight the value segments (up to 16 MB each at R-MAT scale 22) thrash the L2 and every RED
+// becomes an HBM round trip.  Instead the row is cut into windows of WIN consecutive ranks; a window's
+// values live in a dense shared-memory tile indexed by rank, products are added with shared-memory
+// atomics, and the tile is written out once, coalesced.  With canonical B only the part of each B row
+// inside the window's column range is visited (two binary searches per A entry and window); most
+// global rows need one or two windows.
 template <class AV, class BV, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
                                                       int *__restrict__ c_ci, double *__restrict__ c_v,
-                                                      unsigned *__restrict__ work, GLayout L, int *__restrict__ cursor)
+                                                      unsigned *__restrict__ work, GLayout L, int *__restrict__ cursor,
+                                                      int win, int b_canonical, int dbg)
 {
-    constexpr int NW = BLOCK / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *acc = reinterpret_cast<double *>(smem_raw);           // win entries
     typedef cub::BlockScan<unsigned, BLOCK> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
-    __shared__ int s_row;
+    __shared__ int s_row, s_lo, s_hi;
+    __shared__ unsigned s_carry;
     __shared__ CtaTile<BV, BLOCK> tile;
     uint2 *wp = reinterpret_cast<uint2 *>(work + (size_t)blockIdx.x * L.slot_words);
     unsigned *summary = reinterpret_cast<unsigned *>(wp + L.words);
-    unsigned *blkpref = summary + L.sumw;
-    int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    unsigned *wsum = summary + L.sumw + L.blocks;
     while (true) {
-        if (threadIdx.x == 0) s_row = atomicAdd(cursor, 1);
+        if (threadIdx.x == 0) { s_row = atomicAdd(cursor, 1); s_carry = 0; }
         __syncthreads();
         int idx = s_row;
         if (idx >= nrows) break;
         int li = rows ? rows[idx] : idx;
         int i = r0 + li;
         long long gs = out.start(li);
+        const int n = out.count(li);
         typename AV::off_t pa = A.begin(i), pe = A.end(i);
         // 1. mark the columns of the row
         int dummy = 0;
         cta_products<false, BLOCK>(A, B, pa, pe, tile,
-                                   [&](typename BV::off_t q, double) { g_mark(wp, summary, __ldg(B.ci + q), dummy); });
+                                   [&](const typename BV::off_t (&q)[PB], const double (&)[PB], unsigned valid) {
+                                       g_mark_batch(B, wp, summary, wsum, q, valid, dummy);
+                                   });
         __syncthreads();
-        // 2a. population of every 1024-column block, exclusive scan over blocks
-        int per = (L.blocks + BLOCK - 1) / BLOCK;
-        int b0 = threadIdx.x * per, b1 = min(b0 + per, L.blocks);
-        unsigned local = 0;
-        for (int b = b0; b < b1; ++b) {
+        // 2. ranks.  One thread per 1024-column block: fetch the block's populated words in one burst (32
+        //    independent predicated loads), block-scan the populations, then write each word's rank and emit
+        //    the sorted column list.
+        for (int bb = 0; bb < L.blocks; bb += BLOCK) {
+            const int b = bb + threadIdx.x;
+            unsigned m = b < L.blocks ? __ldcg(wsum + b) : 0u;
+            const uint2 *cell = wp + (size_t)b * 32;
+            unsigned word[32];
             unsigned c = 0;
-            if ((__ldcg(summary + (b >> 5)) >> (b & 31)) & 1u) {
-                const uint4 *p4 = reinterpret_cast<const uint4 *>(wp + (size_t)b * 32);
 #pragma unroll
-                for (int x = 0; x < 16; ++x) { uint4 u = __ldcg(p4 + x); c += __popc(u.x) + __popc(u.z); }
+            for (int x = 0; x < 32; ++x) {
+                word[x] = (m >> x) & 1u ? __ldcg(&cell[x].x) : 0u;
+                c += __popc(word[x]);
             }
-            blkpref[b] = c;
-            local += c;
-        }
-        unsigned tbase;
-        Scan(scan_tmp).ExclusiveSum(local, tbase);
-        for (int b = b0; b < b1; ++b) { unsigned c = blkpref[b]; blkpref[b] = tbase; tbase += c; }
-        __syncthreads();
-        // 2b. per-word ranks; emit the sorted column list and zero the value slots
-        for (int b = w; b < L.blocks; b += NW) {
-            if (!((__ldcg(summary + (b >> 5)) >> (b & 31)) & 1u)) continue;
-            int wi = b * 32 + lane;
-            unsigned word = __ldcg(&wp[wi].x);
-            unsigned c = __popc(word), incl = c;
+            unsigned excl, tile_total;
+            Scan(scan_tmp).ExclusiveSum(c, excl, tile_total);
+            __syncthreads();                               // scan_tmp is reused by the next trip
+            unsigned rank = s_carry + excl;                 // s_carry: entries of the blocks of earlier trips
+            if (m) {
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { unsigned u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-            unsigned rank = __ldcg(blkpref + b) + incl - c;
-            wp[wi].y = rank;
-            while (word) {
-                int bit = __ffs(word) - 1;
-                word &= word - 1;
-                c_ci[gs + rank] = wi * 32 + bit;
-                c_v[gs + rank] = 0.0;
-                ++rank;
+                for (int x = 0; x < 32; ++x) {
+                    unsigned wd = word[x];
+                    if (!wd) continue;
+                    wp[(size_t)b * 32 + x].y = rank;
+                    while (wd) {
+                        int bit = __ffs(wd) - 1;
+                        wd &= wd - 1;
+                        c_ci[gs + rank] = (b * 32 + x) * 32 + bit;
+                        ++rank;
+                    }
+                }
             }
+            __syncthreads();
+            if (threadIdx.x == 0) s_carry += tile_total;
+            __syncthreads();
         }
-        __threadfence();         // the zeroed value slots must be in L2 before any RED lands on them
+        __threadfence();          // window bounds below are read back from c_ci by another thread
         __syncthreads();
-        // 3. accumulate every product at the rank of its column: one 8-byte L2 read + one RED.F64
-        cta_products<true, BLOCK>(A, B, pa, pe, tile, [&](typename BV::off_t q, double av) {
-            int k = __ldg(B.ci + q);
-            double x = av * __ldg(B.v + q);
-            uint2 cell = __ldcg(wp + (k >> 5));
-            unsigned below = cell.x & ((1u << (k & 31)) - 1u);
-            atomicAdd(c_v + gs + cell.y + __popc(below), x);
-        });
-        __syncthreads();
+        // 3. one window of `win` ranks at a time: accumulate in the shared-memory tile, then write it out
+        for (int wbase = 0; wbase < n; wbase += win) {
+            const int wn = min(win, n - wbase);
+            if (threadIdx.x == 0) {
+                s_lo = wbase == 0 ? 0 : __ldcg(c_ci + gs + wbase);
+                s_hi = wbase + win < n ? __ldcg(c_ci + gs + wbase + win) : 0x7fffffff;
+            }
+            for (int t = threadIdx.x; t < wn; t += BLOCK) acc[t] = 0.0;
+            __syncthreads();
+            const int c_lo = s_lo, c_hi = s_hi;
+            auto add = [&](const typename BV::off_t (&q)[PB], const double (&av)[PB], unsigned valid) {
+                int k[PB];
+                double x[PB];
+                uint2 cell[PB];
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    k[u] = -1; x[u] = 0.0;
+                    if ((valid >> u) & 1u) { k[u] = __ldg(B.ci + q[u]); x[u] = av[u] * __ldg(B.v + q[u]); }
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    if (k[u] < c_lo || k[u] >= c_hi) k[u] = -1;
+                    cell[u] = k[u] >= 0 ? __ldcg(wp + (k[u] >> 5)) : make_uint2(0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    if (k[u] < 0) continue;
+                    unsigned below = cell[u].x & ((1u << (k[u] & 31)) - 1u);
+                    if (dbg & 1) acc[(int)(cell[u].y + __popc(below)) - wbase] = x[u];
+                    else atomicAdd(&acc[(int)(cell[u].y + __popc(below)) - wbase], x[u]);
+                }
+            };
+            if (dbg & 4) { }
+            else if (b_canonical && n > win && !(dbg & 2)) cta_products<true, BLOCK>(A, B, pa, pe, tile, add, ColumnWindow<BV>{B, c_lo, c_hi});
+            else cta_products<true, BLOCK>(A, B, pa, pe, tile, add);
+            __syncthreads();
+            for (int t = threadIdx.x; t < wn; t += BLOCK) c_v[gs + wbase + t] = acc[t];
+            __syncthreads();
+        }
         // 4. leave the slot clean for the next row
-        g_clear<BLOCK>(wp, summary, L);
+        g_clear<BLOCK>(wp, summary, wsum, L);
         __syncthreads();
     }
 }
