@@ -343,7 +343,7 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
             size_t sm = (size_t)win * sizeof(double);
             IAS_TRY(opt_in_smem(k, sm));
             IAS_LAUNCH(k, rw.gslots, 1024, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p, GLayout::make(ncols_b),
-                       rw.cursor.p, win, rw.b_canonical, getenv("IAS_G_DBG") ? atoi(getenv("IAS_G_DBG")) : 0);
+                       rw.cursor.p, win, rw.b_canonical);
         }
         IAS_BIN_END(8 + BIN_G);
         rw.num_timed[BIN_G] = true;

@@ -978,7 +978,7 @@ template <class AV, class BV, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
                                                       int *__restrict__ c_ci, double *__restrict__ c_v,
                                                       unsigned *__restrict__ work, GLayout L, int *__restrict__ cursor,
-                                                      int win, int b_canonical, int dbg)
+                                                      int win, int b_canonical)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *acc = reinterpret_cast<double *>(smem_raw);           // win entries
@@ -1073,12 +1073,10 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
                 for (int u = 0; u < PB; ++u) {
                     if (k[u] < 0) continue;
                     unsigned below = cell[u].x & ((1u << (k[u] & 31)) - 1u);
-                    if (dbg & 1) acc[(int)(cell[u].y + __popc(below)) - wbase] = x[u];
-                    else atomicAdd(&acc[(int)(cell[u].y + __popc(below)) - wbase], x[u]);
+                    atomicAdd(&acc[(int)(cell[u].y + __popc(below)) - wbase], x[u]);
                 }
             };
-            if (dbg & 4) { }
-            else if (b_canonical && n > win && !(dbg & 2)) cta_products<true, BLOCK>(A, B, pa, pe, tile, add, ColumnWindow<BV>{B, c_lo, c_hi});
+            if (b_canonical && n > win) cta_products<true, BLOCK>(A, B, pa, pe, tile, add, ColumnWindow<BV>{B, c_lo, c_hi});
             else cta_products<true, BLOCK>(A, B, pa, pe, tile, add);
             __syncthreads();
             for (int t = threadIdx.x; t < wn; t += BLOCK) c_v[gs + wbase + t] = acc[t];
