@@ -226,6 +226,9 @@ def main():
         args.stream = True
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
 
+    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
+    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
+        os.environ["NCCL_DEBUG"] = "WARN"
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -24,6 +24,10 @@ struct Ctx {
     // pinned host arena for ias_csr_mul_csr_host results (grow only)
     void *h_arena = nullptr;
     size_t h_arena_bytes = 0;
+    // last operand whose rows were checked for strictly increasing columns (see ias_forget_operand)
+    const void *canon_ci = nullptr, *canon_rp = nullptr;
+    long long canon_rows = -1, canon_nnz = -1;
+    int canon_flag = 0;
     // small pinned scratch for scalar read-backs
     long long *h_scalars = nullptr;     // 64 entries
 };

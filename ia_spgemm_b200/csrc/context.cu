@@ -119,9 +119,17 @@ int ias_upload_csr(const IasCsrMatrix *h, IasCsrMatrixDev *d)
     return IAS_OK;
 }
 
+int ias_forget_operand(const IasCsrMatrixDev *m)
+{
+    Ctx &c = ctx();
+    if (!m || c.canon_ci == (const void *)m->col_ind_dev) { c.canon_ci = nullptr; c.canon_rows = c.canon_nnz = -1; }
+    return IAS_OK;
+}
+
 int ias_free_csr_dev(IasCsrMatrixDev *m)
 {
     if (!m) return IAS_OK;
+    ias_forget_operand(m);
     dfree(m->row_ind_dev); dfree(m->col_ind_dev); dfree(m->values_dev);
     m->row_ind_dev = nullptr; m->col_ind_dev = nullptr; m->values_dev = nullptr;
     return IAS_OK;

@@ -26,7 +26,7 @@ int mul_rows(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1,
     if (!C) return fail(IAS_E_ARG, "NULL result");
     double avg = A->row ? (double)A->nnz / A->row : 0.0;
     bool same = A->row_ind_dev == B->row_ind_dev && A->col_ind_dev == B->col_ind_dev;
-    return spgemm_materialise(view(A), view(B), avg, B->col, r0, r1, C, st, same, B->row);
+    return spgemm_materialise(view(A), view(B), avg, B->col, r0, r1, C, st, same, B->row, B->nnz);
 }
 
 __global__ void k_narrow_rp(int n, const long long *in, int *out)
@@ -88,7 +88,7 @@ int ias_csr_mul_csr_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, i
     CsrView av = view(A), bv = view(B);
     double avg = A->row ? (double)A->nnz / A->row : 0.0;
     bool same = A->row_ind_dev == B->row_ind_dev && A->col_ind_dev == B->col_ind_dev;
-    IAS_TRY(symbolic_range(av, bv, r0, r1, B->col, avg, rw, &local, same, B->row));
+    IAS_TRY(symbolic_range(av, bv, r0, r1, B->col, avg, rw, &local, same, B->row, B->nnz));
     IAS_CUDA(cudaEventRecord(c.ev[2], c.stream));
     DBuf<long long> rp;
     IAS_TRY(rp.alloc((size_t)nrows + 1));

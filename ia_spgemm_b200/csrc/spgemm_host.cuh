@@ -133,7 +133,7 @@ inline int ensure_gwork(RangeWork &rw, int ncols, long long nrows_g, bool one_pe
 // analysis + symbolic over [r0, r1): fills rw.ub, rw.nnz_row (exact nnz(C_i)), products
 template <class AV, class BV>
 int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double avg_a_row, RangeWork &rw, IasSpgemmStats *st,
-                   bool b_is_a = false, int b_rows = 0)
+                   bool b_is_a = false, int b_rows = 0, long long b_nnz = -1)
 {
     Ctx &c = ctx();
     int nrows = r1 - r0;
@@ -157,7 +157,10 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
     // canonical B: the analyze kernel has just checked the rows of A it walked; that covers B only when B is A
     // and the range is the whole matrix, otherwise B gets its own pass (4 B per entry of B)
     bool covered = b_is_a && r0 == 0 && r1 == b_rows;
-    if (!covered && b_rows > 0) {
+    // B's canonical flag is remembered per operand (pointers + shape), so repeated row-block multiplies
+    // against the same B (multi-GPU, streaming callers) pay the 4 B/entry pass once
+    bool cached = !covered && b_nnz >= 0 && c.canon_ci == (const void *)B.ci && c.canon_rows == b_rows && c.canon_nnz == b_nnz;
+    if (!covered && !cached && b_rows > 0) {
         IAS_CUDA(cudaMemsetAsync(rw.hist.p + NBINS + 1, 0, sizeof(unsigned long long), c.stream));
         IAS_LAUNCH((k_rows_canonical<BV>), grid_for(b_rows, 256), 256, 0, b_rows, B, rw.hist.p + NBINS + 1);
     }
@@ -165,6 +168,8 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
     IAS_TRY(read_hist(rw, NBINS + 5, h));
     rw.products = h[NBINS];
     rw.b_canonical = (b_rows > 0 && h[NBINS + 1] == 0) ? 1 : 0;
+    if (cached) rw.b_canonical = c.canon_flag;
+    else if (b_nnz >= 0 && b_rows > 0) { c.canon_ci = (const void *)B.ci; c.canon_rows = b_rows; c.canon_nnz = b_nnz; c.canon_flag = rw.b_canonical; }
     rw.max_tiny_na = (int)h[NBINS + 2];
     rw.max_tiny_ub = (int)h[NBINS + 3];
     rw.max_warp_ub = (int)h[NBINS + 4];
@@ -380,7 +385,7 @@ inline double ev_ms(int a, int b)
 // of C, numeric pass, sort; operands already resident.
 template <class AV, class BV>
 int spgemm_materialise(const AV &av, const BV &bv, double avg_a_row, int ncols_b, int r0, int r1, IasCsr64Dev *C,
-                       IasSpgemmStats *st, bool b_is_a = false, int b_rows = 0)
+                       IasSpgemmStats *st, bool b_is_a = false, int b_rows = 0, long long b_nnz = -1)
 {
     Ctx &c = ctx();
     long long l0 = c.launches;
@@ -393,7 +398,7 @@ int spgemm_materialise(const AV &av, const BV &bv, double avg_a_row, int ncols_b
     IAS_CUDA(cudaEventRecord(c.ev[0], c.stream));
     IAS_CUDA(cudaEventRecord(c.ev[1], c.stream));
     RangeWork rw;
-    IAS_TRY(symbolic_range(av, bv, r0, r1, ncols_b, avg_a_row, rw, &local, b_is_a, b_rows));
+    IAS_TRY(symbolic_range(av, bv, r0, r1, ncols_b, avg_a_row, rw, &local, b_is_a, b_rows, b_nnz));
     IAS_CUDA(cudaEventRecord(c.ev[2], c.stream));
 
     DBuf<long long> rp;

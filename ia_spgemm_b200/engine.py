@@ -82,7 +82,7 @@ ABI_SYMBOLS = [
     "ias_init", "ias_set_stream", "ias_sync", "ias_last_error", "ias_version", "ias_device_info",
     "ias_kernel_launches",
     "ias_upload_csr", "ias_free_csr_dev", "ias_free_csr64_dev", "ias_download_csr64", "ias_download_csr",
-    "ias_csr_is_canonical", "ias_copy",
+    "ias_csr_is_canonical", "ias_copy", "ias_forget_operand",
     "ias_csr_mul_csr_dev64", "ias_csr_mul_csr_dev", "ias_csr_mul_csr_rows_dev64", "ias_csr_mul_csr_stream",
     "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_partition_rows", "ias_checksum",
     "ias_structure_hash",
@@ -211,6 +211,9 @@ class Engine:
     def copy(self, dst_ptr, src_ptr, nbytes, kind):
         """kind: 0 host->device, 1 device->host, 2 device->device."""
         self._ck(self.lib.ias_copy(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), nbytes, kind))
+
+    def forget_operand(self, A=None):
+        self.lib.ias_forget_operand(C.byref(A.dev) if A is not None else None)
 
     def is_canonical(self, A):
         r = C.c_int()

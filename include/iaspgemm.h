@@ -132,6 +132,10 @@ int ias_download_csr(const IasCsrMatrixDev *dev, int *row_ptr, int *col_ind, dou
 /* raw copies on the engine stream, synchronous: kind 0 = host->device, 1 = device->host, 2 = device->device
  * (DevUpload / DevDownload, GPU/detail/common.h:79-97, without the exit(1)) */
 int ias_copy(void *dst, const void *src, size_t bytes, int kind);
+/* The engine remembers, per B operand (pointer + shape), whether its rows are canonical.  A caller that
+ * rewrites an operand's device arrays IN PLACE must call this before the next multiply (ias_free_csr_dev
+ * does it for engine-owned operands; NULL forgets everything). */
+int ias_forget_operand(const IasCsrMatrixDev *m);
 /* canonical = every row strictly increasing in column (sorted, duplicate free) */
 int ias_csr_is_canonical(const IasCsrMatrixDev *m, int *canonical);
 

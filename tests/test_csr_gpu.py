@@ -219,3 +219,18 @@ def test_launch_counter_moves(eng):
     _, st = eng.CSR_MUL_CSR_DEV(dA, dA, download=False)
     assert eng.kernel_launches() - before == st["kernel_launches"] > 0
     dA.close()
+
+
+def test_canonical_flag_cache_is_invalidated(eng, oracle):
+    """Row-block multiplies remember whether B is canonical; freeing or forgetting the operand drops that."""
+    for sort_columns in (True, False, True, False):        # the pool hands the same addresses out again
+        A = W.random_sparse(300, 300, 0.03, seed=11, sort_columns=sort_columns)
+        dA = eng.upload(*A)
+        want = sort_rows(*_oracle(oracle, A))
+        for _ in range(2):                                  # second call hits the cache
+            (rp, ci, v), st = eng.CSR_MUL_CSR_DEV(dA, dA, rows=(100, 250))
+            assert np.array_equal(rp, want[0][100:251] - want[0][100])
+            assert np.array_equal(ci, want[1][want[0][100]:want[0][250]])
+            assert np.allclose(v, want[2][want[0][100]:want[0][250]], rtol=1e-12, atol=1e-15)
+        eng.forget_operand(dA)
+        dA.close()
