@@ -150,7 +150,7 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
         IAS_TRY(long_list.alloc(nrows));
         IAS_TRY(long_count.alloc(1));
         IAS_CUDA(cudaMemsetAsync(long_count.p, 0, sizeof(int), c.stream));
-        IAS_LAUNCH((k_row_ub_thread<AV, BV>), grid_for(nrows, 256), 256, 0, nrows, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p, long_list.p, long_count.p);
+        IAS_LAUNCH((k_row_ub_thread<AV, BV>), grid_for(nrows, 256), 256, 0, nrows, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p, long_list.p, long_count.p, rw.nnz_row.p);
         if (avg_a_row * nrows > LONG_A)        // some row can be long only if the operand has that many entries at all
             IAS_LAUNCH((k_row_ub_long<AV, BV>), c.sm_count * 8, 256, 0, long_list.p, long_count.p, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p);
     }
@@ -181,7 +181,9 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
         st->products = rw.products;
         for (int b = 0; b < 8; ++b) st->sym_bin_rows[b] = b < NBINS ? rw.sym_hist[b] : 0;
     }
-    IAS_CUDA(cudaMemsetAsync(rw.hist.p + 12, 0, sizeof(unsigned long long), c.stream));      // hist[12]: max nnz(C_i) among tiny rows
+    // hist[12] = largest nnz(C_i) among tiny rows (sizes k_num_tiny's staging); the analyze kernel has already
+    // counted the tiny rows optimistically: those counts stand if B is canonical and no tiny row exceeds 8 entries
+    const bool tiny_counted = rw.b_canonical && rw.max_tiny_na <= 8;
     BinLists bl;
     IAS_TRY(build_bin_lists(nrows, rw.bin.p, h, bl));
     if (rw.tiny_only) {
@@ -191,7 +193,7 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
             IAS_CUDA(cudaMemcpyAsync(rw.tiny_list.p, bl.rows_of(BIN_T), sizeof(int) * (size_t)bl.count[BIN_T], cudaMemcpyDeviceToDevice, c.stream));
         }
     }
-    if (bl.count[BIN_T]) {
+    if (bl.count[BIN_T] && !tiny_counted) {
         IAS_BIN_BEGIN(BIN_T);
         int n = (int)bl.count[BIN_T];
         int merge = rw.max_tiny_na <= 4 ? 4 : rw.max_tiny_na <= 6 ? 6 : 8;

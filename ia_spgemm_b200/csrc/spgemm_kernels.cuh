@@ -90,6 +90,45 @@ struct OutMap {
     __device__ __forceinline__ int count(int li) const { return rp ? (int)(rp[li + 1] - rp[li]) : nnz_row[li]; }
 };
 
+// ---------------------------------------------------------------- cursors of the tiny-row k-way merge (see "tiny rows" below)
+template <class BV, int MERGE, bool WITH_VALUES>
+struct TinyCursors {
+    typename BV::off_t q[MERGE], qe[MERGE];
+    int hc[MERGE];
+    double hv[WITH_VALUES ? MERGE : 1];
+    template <class AV>
+    __device__ __forceinline__ void init(const AV &A, const BV &B, typename AV::off_t pa, int na)
+    {
+#pragma unroll
+        for (int a = 0; a < MERGE; ++a) {
+            hc[a] = 0x7fffffff; q[a] = 0; qe[a] = 0;
+            if (WITH_VALUES) hv[a] = 0.0;
+            if (a < na) {
+                int j = __ldg(A.ci + pa + a);
+                q[a] = B.begin(j); qe[a] = B.end(j);
+                if (q[a] < qe[a]) {
+                    hc[a] = __ldg(B.ci + q[a]);
+                    if (WITH_VALUES) hv[a] = __ldg(B.v + q[a]);
+                }
+            }
+        }
+    }
+    __device__ __forceinline__ int head() const
+    {
+        int m = hc[0];
+#pragma unroll
+        for (int a = 1; a < MERGE; ++a) m = min(m, hc[a]);
+        return m;
+    }
+    __device__ __forceinline__ void advance(const BV &B, int a)
+    {
+        ++q[a];
+        bool more = q[a] < qe[a];
+        hc[a] = more ? __ldg(B.ci + q[a]) : 0x7fffffff;
+        if (WITH_VALUES && more) hv[a] = __ldg(B.v + q[a]);
+    }
+};
+
 // ---------------------------------------------------------------- analyze
 // block-level histogram of bins + sum of products.  Shared atomics are 32-bit and warp-aggregated:
 // a 64-bit shared atomicAdd is a CAS loop, and with every row of a CTA in the same bin (Poisson,
@@ -118,18 +157,19 @@ template <class AV, class BV>
 __global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, BV B, int *__restrict__ ub_out,
                                                        unsigned char *__restrict__ bin_out,
                                                        unsigned long long *__restrict__ g_hist /*16 slots*/,
-                                                       int *__restrict__ long_list, int *__restrict__ long_count)
+                                                       int *__restrict__ long_list, int *__restrict__ long_count,
+                                                       int *__restrict__ nnz_row /* optimistic tiny-row counts */)
 {
     __shared__ unsigned s_cnt[NBINS];
     __shared__ unsigned long long s_sum;
-    __shared__ int s_max[3];
+    __shared__ int s_max[4];
     if (threadIdx.x < NBINS) s_cnt[threadIdx.x] = 0;
     if (threadIdx.x == NBINS) s_sum = 0;
-    if (threadIdx.x < 3) s_max[threadIdx.x] = 0;
+    if (threadIdx.x < 4) s_max[threadIdx.x] = 0;
     __syncthreads();
     int li = blockIdx.x * blockDim.x + threadIdx.x;
     long long ub = 0;
-    int bin = -1, tiny_na = 0, tiny_ub = 0;
+    int bin = -1, tiny_na = 0, tiny_ub = 0, tiny_cnt = 0;
     if (li < nrows) {
         int i = r0 + li;
         typename AV::off_t pa = A.begin(i), pe = A.end(i);
@@ -149,8 +189,28 @@ __global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, 
             tiny_ub = (bin == BIN_T) ? (int)ub : (bin == BIN_W ? -(int)ub : 0);   // negative: a warp-bin row
             ub_out[li] = ub > 0x7fffffffLL ? 0x7fffffff : (int)ub;
             bin_out[li] = (unsigned char)bin;
+            // Tiny rows with few A entries: count nnz(C_i) right here with the k-way merge, ASSUMING B is canonical
+            // (A's and B's lines are in L1 now).  The host keeps these counts only if the whole of B turns out
+            // canonical and no tiny row has more than 8 entries; otherwise k_sym_tiny recomputes the bin.
+            if (bin == BIN_T && tiny_na <= 8) {
+                TinyCursors<BV, 8, false> cur;
+                cur.init(A, B, pa, tiny_na);
+                int cnt = 0;
+                while (cnt < T_MAX) {
+                    int m = cur.head();
+                    if (m == 0x7fffffff) break;
+#pragma unroll
+                    for (int a = 0; a < 8; ++a)
+                        if (cur.hc[a] == m) cur.advance(B, a);
+                    ++cnt;
+                }
+                nnz_row[li] = cnt;
+                tiny_cnt = cnt;
+            }
         }
     }
+    tiny_cnt = __reduce_max_sync(0xffffffffu, tiny_cnt);
+    if ((threadIdx.x & 31) == 0 && tiny_cnt > 0) atomicMax(&s_max[3], tiny_cnt);
     int warp_ub = __reduce_max_sync(0xffffffffu, tiny_ub < 0 ? -tiny_ub : 0);
     tiny_na = __reduce_max_sync(0xffffffffu, tiny_na);
     tiny_ub = __reduce_max_sync(0xffffffffu, tiny_ub > 0 ? tiny_ub : 0);
@@ -162,6 +222,7 @@ __global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, 
     // one global atomic per CTA and statistic, and only when it would raise the maximum (plain read is a hint)
     if (threadIdx.x < 3 && s_max[threadIdx.x] > 0 && (unsigned long long)s_max[threadIdx.x] > g_hist[NBINS + 2 + threadIdx.x])
         atomicMax(&g_hist[NBINS + 2 + threadIdx.x], (unsigned long long)s_max[threadIdx.x]);
+    if (threadIdx.x == 3 && s_max[3] > 0 && (unsigned long long)s_max[3] > g_hist[12]) atomicMax(&g_hist[12], (unsigned long long)s_max[3]);
 }
 
 // the deferred long rows: one warp per row, persistent grid
@@ -251,44 +312,6 @@ static __global__ void k_iota(int n, int *out)
 //           column and value.  Output comes out column sorted: no search, no sort.
 //   list    (anything else): unsorted private list with linear search, insertion-sorted at the end.
 // MERGE is a template parameter (4 / 6 / 8) picked by the host from the longest A row in the bin.
-template <class BV, int MERGE, bool WITH_VALUES>
-struct TinyCursors {
-    typename BV::off_t q[MERGE], qe[MERGE];
-    int hc[MERGE];
-    double hv[WITH_VALUES ? MERGE : 1];
-    template <class AV>
-    __device__ __forceinline__ void init(const AV &A, const BV &B, typename AV::off_t pa, int na)
-    {
-#pragma unroll
-        for (int a = 0; a < MERGE; ++a) {
-            hc[a] = 0x7fffffff; q[a] = 0; qe[a] = 0;
-            if (WITH_VALUES) hv[a] = 0.0;
-            if (a < na) {
-                int j = __ldg(A.ci + pa + a);
-                q[a] = B.begin(j); qe[a] = B.end(j);
-                if (q[a] < qe[a]) {
-                    hc[a] = __ldg(B.ci + q[a]);
-                    if (WITH_VALUES) hv[a] = __ldg(B.v + q[a]);
-                }
-            }
-        }
-    }
-    __device__ __forceinline__ int head() const
-    {
-        int m = hc[0];
-#pragma unroll
-        for (int a = 1; a < MERGE; ++a) m = min(m, hc[a]);
-        return m;
-    }
-    __device__ __forceinline__ void advance(const BV &B, int a)
-    {
-        ++q[a];
-        bool more = q[a] < qe[a];
-        hc[a] = more ? __ldg(B.ci + q[a]) : 0x7fffffff;
-        if (WITH_VALUES && more) hv[a] = __ldg(B.v + q[a]);
-    }
-};
-
 // one merged row into (mc, mv); returns the number of distinct columns (at most `limit`)
 template <class AV, class BV, int MERGE>
 __device__ __forceinline__ int tiny_merge_numeric(const AV &A, const BV &B, typename AV::off_t pa, int na, int *mc, double *mv, int limit)
