@@ -120,10 +120,9 @@ def host_operand(args):
 def cpu_sample_rows(A, target_products=6e8):
     """A contiguous row block of about target_products intermediate products, starting at rows/3
     (the whole matrix when it is that small)."""
+    from ia_spgemm_b200.multigpu import per_row_products
     rows, cols, rp, ci, v = A
-    lens = np.diff(rp).astype(np.int64)
-    per_row = np.add.reduceat(lens[ci], rp[:-1].astype(np.int64))
-    per_row[lens == 0] = 0
+    per_row = per_row_products(rp, ci, rp)
     total = int(per_row.sum())
     if total <= target_products * 1.5:
         return 0, rows, total
@@ -363,13 +362,16 @@ def main():
         dom_name, dom_ms = "ell pipeline (k_num_*)", float(np.mean([s["ms_total"] for s in stats]))
     else:
         nrows_blk = r1 - r0
-        a_blk_nnz = nnz_a if world == 1 else None
-        # bytes_alg(CSR) = bytes(A block) + touched B rows (every column of A non-empty for P/U: bytes(B)) + bytes(C), SURVEY 8(d)
-        if a_blk_nnz is None:
-            a_blk_nnz = int(nnz_a * (nrows_blk / max(rows, 1)))
-        alg_bytes = bytes_csr(nrows_blk, a_blk_nnz) + bytes_csr(rows, nnz_a) + bytes_csr(nrows_blk, st["nnz"], 8)
+        # bytes_alg(CSR) = bytes(A block) + bytes of the B rows it references at least once + bytes(C block), SURVEY 8(d);
+        # this rank's block (N=1: the whole job)
+        a_rp = np.zeros(2, dtype=np.int32)
+        eng.copy(a_rp.ctypes.data, dA.dev.row_ind_dev + 4 * r0, 4, 1)
+        eng.copy(a_rp.ctypes.data + 4, dA.dev.row_ind_dev + 4 * r1, 4, 1)
+        a_blk_nnz = int(a_rp[1]) - int(a_rp[0])
+        touched_b = eng.touched_b_bytes(dA, dA, rows=(r0, r1))
+        alg_bytes = bytes_csr(nrows_blk, a_blk_nnz) + touched_b + bytes_csr(nrows_blk, st["nnz"], 8)
         bins = np.array([[s["ms_bin_num"][b] for b in range(6)] for s in stats]).mean(axis=0)
-        names = ["-", "k_num_tiny", "k_num_hash<warp>", "k_num_hash<cta256>", "k_num_hash<cta1024>", "k_num_global"]
+        names = ["-", "k_num_tiny", "k_esc_warp", "k_num_hash_cta<512,8192>", "k_num_hash_cta<1024,16384>", "k_num_global"]
         b = int(np.argmax(bins))
         dom_name, dom_ms = names[b], float(bins[b])
     achieved = alg_bytes / (dom_ms * 1e-3) / 1e9 if dom_ms > 0 else 0.0

@@ -274,6 +274,53 @@ __global__ void k_split(int nrows, const long long *__restrict__ incl, int parts
 }
 }  // namespace
 
+namespace {
+__global__ void __launch_bounds__(256) k_mark_columns(long long n, const int *__restrict__ ci, unsigned *__restrict__ bitmap)
+{
+    long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    int j = ci[p];
+    unsigned bit = 1u << (j & 31);
+    if (!(bitmap[j >> 5] & bit)) atomicOr(bitmap + (j >> 5), bit);
+}
+__global__ void __launch_bounds__(256) k_touched_bytes(int b_rows, const unsigned *__restrict__ bitmap, const int *__restrict__ b_rp,
+                                                       unsigned long long *__restrict__ out)
+{
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    long long mine = 0;
+    if (j < b_rows && ((bitmap[j >> 5] >> (j & 31)) & 1u)) mine = 4 + 12LL * (b_rp[j + 1] - b_rp[j]);
+    mine = warp_sum(mine);
+    if ((threadIdx.x & 31) == 0 && mine) atomicAdd(out, (unsigned long long)mine);
+}
+}  // namespace
+
+int ias_touched_b_bytes(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, long long *bytes)
+{
+    IAS_TRY(ensure_init());
+    IAS_TRY(check_operands(A, B, r0, r1));
+    if (!bytes) return fail(IAS_E_ARG, "NULL");
+    Ctx &c = ctx();
+    *bytes = 0;
+    int h_rp[2] = {0, 0};
+    IAS_CUDA(cudaMemcpyAsync(&h_rp[0], A->row_ind_dev + r0, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaMemcpyAsync(&h_rp[1], A->row_ind_dev + r1, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    long long n = (long long)h_rp[1] - h_rp[0];
+    if (n <= 0 || B->row == 0) return IAS_OK;
+    size_t words = ((size_t)B->row + 31) / 32;
+    DBuf<unsigned> bitmap;
+    DBuf<unsigned long long> out;
+    IAS_TRY(bitmap.alloc(words));
+    IAS_TRY(out.alloc(1));
+    IAS_CUDA(cudaMemsetAsync(bitmap.p, 0, words * sizeof(unsigned), c.stream));
+    IAS_CUDA(cudaMemsetAsync(out.p, 0, sizeof(unsigned long long), c.stream));
+    IAS_LAUNCH(k_mark_columns, grid_for(n, 256), 256, 0, n, A->col_ind_dev + h_rp[0], bitmap.p);
+    IAS_LAUNCH(k_touched_bytes, grid_for(B->row, 256), 256, 0, B->row, bitmap.p, B->row_ind_dev, out.p);
+    IAS_CUDA(cudaMemcpyAsync(bytes, out.p, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    return IAS_OK;
+}
+
 static int row_products_scan(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, DBuf<long long> &incl)
 {
     IAS_TRY(incl.alloc((size_t)A->row + 1));

@@ -84,7 +84,7 @@ ABI_SYMBOLS = [
     "ias_upload_csr", "ias_free_csr_dev", "ias_free_csr64_dev", "ias_download_csr64", "ias_download_csr",
     "ias_csr_is_canonical", "ias_copy", "ias_forget_operand",
     "ias_csr_mul_csr_dev64", "ias_csr_mul_csr_dev", "ias_csr_mul_csr_rows_dev64", "ias_csr_mul_csr_stream",
-    "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_partition_rows", "ias_checksum",
+    "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_touched_b_bytes", "ias_partition_rows", "ias_checksum",
     "ias_structure_hash",
     "ias_csr_to_dia", "ias_dia_mul_dia_dev", "ias_download_dia", "ias_free_dia_dev",
     "ias_csr_to_ell", "ias_ell_mul_ell_dev", "ias_download_ell", "ias_free_ell_dev",
@@ -292,6 +292,12 @@ class Engine:
         p = C.c_longlong()
         self._ck(self.lib.ias_getflop(C.byref(A.dev), C.byref(B.dev), C.byref(p)))
         return p.value
+
+    def touched_b_bytes(self, A, B, rows=None):
+        r0, r1 = rows if rows is not None else (0, A.dev.row)
+        b = C.c_longlong()
+        self._ck(self.lib.ias_touched_b_bytes(C.byref(A.dev), C.byref(B.dev), C.c_int(r0), C.c_int(r1), C.byref(b)))
+        return b.value
 
     def partition_rows(self, A, B, parts):
         b = (C.c_int * (parts + 1))()

@@ -167,6 +167,9 @@ int ias_release_host(void);
 
 /* GetFlop, CPU/detail/csr/common_csr.h:290-304 */
 int ias_getflop(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, long long *products);
+/* bytes of the B rows referenced at least once by rows [row_begin,row_end) of A: 4*|T| + 12*sum len(B_j), j in T
+ * (the "touched B rows" term of the algorithmic-bytes model) */
+int ias_touched_b_bytes(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int row_begin, int row_end, long long *bytes);
 /* work-balanced contiguous row blocks: bounds[0..parts] with equal shares of products */
 int ias_partition_rows(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int parts, int *bounds);
 /* getsum_csr, csr_dev:264-273 (verified_sum) */

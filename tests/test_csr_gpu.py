@@ -234,3 +234,15 @@ def test_canonical_flag_cache_is_invalidated(eng, oracle):
             assert np.allclose(v, want[2][want[0][100]:want[0][250]], rtol=1e-12, atol=1e-15)
         eng.forget_operand(dA)
         dA.close()
+
+
+def test_touched_b_bytes(eng):
+    """Algorithmic-bytes helper: 4*|T| + 12*sum len(B_j) over the columns referenced by an A row block."""
+    A = W.rmat(10, 8, seed=7)
+    dA = eng.upload(*A)
+    rows, cols, rp, ci, v = A
+    lens = np.diff(rp).astype(np.int64)
+    for r0, r1 in ((0, rows), (100, 300), (5, 5)):
+        T = np.unique(ci[rp[r0]:rp[r1]])
+        assert eng.touched_b_bytes(dA, dA, rows=(r0, r1)) == int(4 * len(T) + 12 * lens[T].sum())
+    dA.close()
