@@ -1,0 +1,101 @@
+"""Parity at BASELINE.json's full sizes through size-independent properties, and against the oracle on
+sampled row blocks where the whole product is too large for the CPU."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from ia_spgemm_b200 import workloads as W
+from util import abs_product, assert_csr_parity, sort_rows
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from ia_spgemm_b200.engine import get_engine
+    return get_engine()
+
+
+def test_poisson_4096_closed_forms(eng):
+    """configs[1]: nnz(A), products and nnz(C) have closed forms; sum(C) = |A*1|^2 = 16 + 4(N-2) because the
+    row sums of the 5-point operator are 0 inside, 1 on edges and 2 in corners; rows come out strictly sorted."""
+    from ia_spgemm_b200.engine import CsrMatrixDev, DeviceCsr
+    N = 4096
+    dA = eng.gen_poisson2d(N)
+    nnz_a, products, nnz_c = W.poisson_counts(N)
+    assert dA.nnz == nnz_a
+    assert eng.GetFlop(dA, dA) == products
+    cdev, ms = CsrMatrixDev(), C.c_double()
+    eng._ck(eng.lib.ias_csr_mul_csr_dev(C.byref(dA.dev), C.byref(dA.dev), C.byref(cdev), C.byref(ms)))
+    Cm = DeviceCsr(eng, cdev)
+    assert Cm.nnz == nnz_c
+    assert eng.is_canonical(Cm)                                   # every row strictly increasing in column
+    total = eng.checksum_ptr(cdev.values_dev, cdev.nnz)
+    assert total == pytest.approx(16 + 4 * (N - 2), rel=1e-12)
+    f = eng.GetInfo1(Cm)
+    assert (f[4], f[5]) == (13, 6)                                # interior rows 13 entries, corner rows 6
+    Cm.close()
+    # the DIA path stores the same matrix (plus explicit zeros on 13 diagonals)
+    d = eng.CSRtoDIA(dA, gate=20.0)
+    assert d.choice and d.num_diagonals == 5
+    c, _ = eng.DIA_MUL_DIA_DEV(d, d)
+    assert c.num_diagonals == 13
+    assert eng.checksum_ptr(c.values_dev, c.row * c.num_diagonals) == pytest.approx(total, rel=1e-12)
+    eng.free_dia(c); eng.free_dia(d)
+    # streaming and row blocks agree with the materialised run
+    st = eng.csr_mul_csr_stream(dA, dA, budget_bytes=600 * 10**6)
+    assert st["nnz"] == nnz_c and st["products"] == products and st["batches"] > 1
+    assert st["checksum"] == pytest.approx(total, rel=1e-11)
+    b = eng.partition_rows(dA, dA, 8)
+    assert sum(eng.CSR_MUL_CSR_DEV(dA, dA, rows=(x, y), download=False)[1]["nnz"] for x, y in zip(b, b[1:])) == nnz_c
+    dA.close()
+
+
+def test_rmat18_sampled_row_blocks_against_oracle(eng, oracle):
+    """R-MAT scale 18: the head rows (global bin, several windows per row), a middle block and the tail,
+    each compared entry by entry with CSR_MUL_CSR(A[r0:r1,:], A) on the CPU."""
+    A = W.rmat(18, 16, seed=1)
+    rows, cols, rp, ci, v = A
+    dA = eng.gen_rmat(18, 16, seed=1)
+    assert dA.nnz == int(rp[-1])
+    for r0, r1 in ((0, 48), (3000, 3400), (rows // 2, rows // 2 + 4000), (rows - 20000, rows)):
+        s, e = int(rp[r0]), int(rp[r1])
+        blk_rp = (rp[r0:r1 + 1] - rp[r0]).astype(np.int32)
+        want = oracle.csr_mul_csr(r1 - r0, cols, blk_rp, ci[s:e], v[s:e], rp, ci, v)
+        got, st = eng.CSR_MUL_CSR_DEV(dA, dA, rows=(r0, r1))
+        assert_csr_parity(got, want)                    # values are positive: the entry itself is the scale
+        assert st["products"] == oracle.getflop(blk_rp, ci[s:e], rp)
+    dA.close()
+
+
+def test_rmat16_streaming_equals_materialised(eng):
+    dA = eng.gen_rmat(16, 16, seed=1)
+    c64, st = eng.CSR_MUL_CSR_DEV(dA, dA, keep=True)
+    h = eng.structure_hash(c64)
+    s = eng.checksum_ptr(c64.values_dev, c64.nnz)
+    eng.free_csr64(c64)
+    d = eng.csr_mul_csr_stream(dA, dA, budget_bytes=400 * 10**6, want_row_nnz=True)
+    assert d["batches"] > 2 and d["nnz"] == st["nnz"] and d["structure_hash"] == h
+    assert d["checksum"] == pytest.approx(s, rel=1e-11)
+    assert int(d["row_nnz"].sum()) == st["nnz"]
+    dA.close()
+
+
+def test_uniform_full_size_properties(eng):
+    """configs[2]: 8M x 8M, 16 distinct columns per row: products = 2^11 * 10^6 exactly, every row of C has at
+    most 256 entries, nnz(C) <= products, ELL path agrees on nnz and checksum."""
+    n = 8_000_000
+    dA = eng.gen_uniform(n, 16, seed=1)
+    assert eng.is_canonical(dA)
+    st = eng.csr_mul_csr_stream(dA, dA, want_row_nnz=True)
+    assert st["products"] == n * 256
+    assert st["nnz"] <= st["products"] and st["nnz"] > 0.9999 * st["products"]
+    assert int(st["row_nnz"].max()) <= 256 and int(st["row_nnz"].min()) >= 200
+    e = eng.CSRtoELL(dA, gate=20.0)
+    assert e.choice and e.max_nnz_per_row == 16
+    c, _ = eng.ELL_MUL_ELL_DEV(e, e)
+    assert c.nnz == st["nnz"] and c.max_nnz_per_row == int(st["row_nnz"].max())
+    assert eng.checksum_ptr(c.values_dev, c.row * c.max_nnz_per_row) == pytest.approx(st["checksum"], rel=1e-11)
+    eng.free_ell(c); eng.free_ell(e)
+    dA.close()
