@@ -32,8 +32,19 @@ sys.path.insert(0, ROOT)
 HBM_FALLBACK_GBS = 6650.0          # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
 
 
+_JSON_FD = None
+
+
 def log(*a):
     print(*a, file=sys.stderr, flush=True)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
 
 
 def measured_peak():
@@ -193,7 +204,7 @@ def run_reference(args, rank, world):
             "cpu_baseline": {"value": val, "unit": "GFLOP/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": val, "unit": "GFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_name(args, world):
@@ -225,9 +236,12 @@ def main():
         args.stream = True
     args.warmup = max(args.warmup, 3) if args.impl == "engine" else args.warmup
 
-    # NCCL prints its version banner on stdout when NCCL_DEBUG=VERSION; stdout carries exactly one JSON line
-    if os.environ.get("NCCL_DEBUG", "").upper() in ("VERSION", ""):
-        os.environ["NCCL_DEBUG"] = "WARN"
+    # stdout carries exactly one JSON line: libraries that write to fd 1 (NCCL prints its version banner there
+    # when NCCL_DEBUG is set) are sent to stderr, the JSON line goes to the saved descriptor
+    global _JSON_FD
+    sys.stdout.flush()
+    _JSON_FD = os.dup(1)
+    os.dup2(2, 1)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -456,7 +470,7 @@ def main():
                            "ms_bin_sym": [round(float(np.mean([s.get("ms_bin_sym", [0] * 6)[b] for s in stats])), 4) for b in range(6)],
                            "ms_bin_num": [round(float(np.mean([s.get("ms_bin_num", [0] * 6)[b] for s in stats])), 4) for b in range(6)]},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

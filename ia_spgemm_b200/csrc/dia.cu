@@ -59,44 +59,48 @@ __global__ void __launch_bounds__(256) k_fill_dia(int rows, const int *__restric
 }
 
 // C[d][i] = sum over pairs (a,b) of diagonal d:  A[a][i] * B[b][i + offA[a]]   (dia:162-193)
-// pair tables live in shared memory; one thread per row, all diagonals of the row in one pass.
+// ncu on the first version (per-pair offset lookups, four 64-bit bound checks): 1635 instructions per row,
+// issue slots 81 % busy -- instruction bound at 48 % of the HBM roofline.  Now every pair carries its two
+// base indices and the row interval on which it contributes (all computed on the host), and a thread owns
+// two rows, so a pair costs one 24-byte shared-memory read, two compares and two loads + one FMA per row.
+struct DiaPair {
+    long long a0;      // a * rows                : A value index = a0 + i
+    long long b0;      // b * rows(B) + offA[a]   : B value index = b0 + i
+    int lo, hi;        // the pair contributes on rows lo <= i < hi
+    int pad0, pad1;
+};
+
 template <int BLOCK, bool TABLES_IN_SMEM>
-__global__ void __launch_bounds__(BLOCK) k_dia_mul_dia(int rows, int a_cols, int b_cols, int a_nd, int b_nd, int c_nd,
-                                                       const int *__restrict__ a_off, const int *__restrict__ b_off,
-                                                       const double *__restrict__ a_val, const double *__restrict__ b_val,
+__global__ void __launch_bounds__(BLOCK) k_dia_mul_dia(int rows, int c_nd, const double *__restrict__ a_val,
+                                                       const double *__restrict__ b_val,
                                                        const int *__restrict__ pair_start /* c_nd+1 */,
-                                                       const unsigned *__restrict__ pairs /* a<<16 | b */, int npairs,
+                                                       const DiaPair *__restrict__ pairs, int npairs,
                                                        double *__restrict__ c_val)
 {
-    extern __shared__ int sm[];
-    const int *s_start = pair_start, *s_aoff = a_off, *s_boff = b_off;
-    const unsigned *s_pairs = pairs;
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const DiaPair *s_pairs = pairs;
+    const int *s_start = pair_start;
     if (TABLES_IN_SMEM) {                      // the usual case: a few diagonals, tables of a few hundred bytes
-        int *w_start = sm;                         // c_nd + 1
-        int *w_aoff = w_start + c_nd + 1;          // a_nd
-        int *w_boff = w_aoff + a_nd;               // b_nd
-        unsigned *w_pairs = reinterpret_cast<unsigned *>(w_boff + b_nd);   // npairs
-        for (int t = threadIdx.x; t <= c_nd; t += BLOCK) w_start[t] = pair_start[t];
-        for (int t = threadIdx.x; t < a_nd; t += BLOCK) w_aoff[t] = a_off[t];
-        for (int t = threadIdx.x; t < b_nd; t += BLOCK) w_boff[t] = b_off[t];
+        DiaPair *w_pairs = reinterpret_cast<DiaPair *>(sm_raw);
+        int *w_start = reinterpret_cast<int *>(w_pairs + npairs);
         for (int t = threadIdx.x; t < npairs; t += BLOCK) w_pairs[t] = pairs[t];
+        for (int t = threadIdx.x; t <= c_nd; t += BLOCK) w_start[t] = pair_start[t];
         __syncthreads();
-        s_start = w_start; s_aoff = w_aoff; s_boff = w_boff; s_pairs = w_pairs;
+        s_pairs = w_pairs; s_start = w_start;
     }
-    const int b_rows = a_cols;
-    for (long long i = (long long)blockIdx.x * BLOCK + threadIdx.x; i < rows; i += (long long)gridDim.x * BLOCK) {
+    for (long long base = (long long)blockIdx.x * (2 * BLOCK); base < rows; base += (long long)gridDim.x * (2 * BLOCK)) {
+        const long long i0 = base + threadIdx.x, i1 = i0 + BLOCK;
+        const bool v0 = i0 < rows, v1 = i1 < rows;
         for (int d = 0; d < c_nd; ++d) {
-            double acc = 0.0;
-            int pe = s_start[d + 1];
+            double acc0 = 0.0, acc1 = 0.0;
+            const int pe = s_start[d + 1];
             for (int p = s_start[d]; p < pe; ++p) {
-                unsigned ab = s_pairs[p];
-                int a = ab >> 16, b = ab & 0xffff;
-                long long j = i + s_aoff[a];
-                long long k = j + s_boff[b];
-                if (j >= 0 && j < a_cols && k >= 0 && k < b_cols)
-                    acc += __ldg(a_val + (size_t)a * rows + i) * __ldg(b_val + (size_t)b * b_rows + j);
+                const DiaPair P = s_pairs[p];
+                if (i0 >= P.lo && i0 < P.hi) acc0 += __ldg(a_val + P.a0 + i0) * __ldg(b_val + P.b0 + i0);
+                if (i1 >= P.lo && i1 < P.hi) acc1 += __ldg(a_val + P.a0 + i1) * __ldg(b_val + P.b0 + i1);
             }
-            c_val[(size_t)d * rows + i] = acc;
+            if (v0) c_val[(size_t)d * rows + i0] = acc0;
+            if (v1) c_val[(size_t)d * rows + i1] = acc1;
         }
     }
 }
@@ -207,7 +211,7 @@ int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, do
     if (!ao.empty()) IAS_CUDA(cudaMemcpyAsync(ao.data(), A->diagonal_offsets_dev, sizeof(int) * ao.size(), cudaMemcpyDeviceToHost, s));
     if (!bo.empty()) IAS_CUDA(cudaMemcpyAsync(bo.data(), B->diagonal_offsets_dev, sizeof(int) * bo.size(), cudaMemcpyDeviceToHost, s));
     IAS_CUDA(cudaStreamSynchronize(s));
-    struct Pair { long long off; unsigned ab; };
+    struct Pair { long long off; DiaPair dp; };
     std::vector<Pair> pairs;
     pairs.reserve(ao.size() * bo.size());
     for (size_t a = 0; a < ao.size(); ++a)
@@ -215,14 +219,15 @@ int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, do
             long long oa = ao[a], ob = bo[b];
             long long lo = std::max<long long>(0, std::max(-oa, -oa - ob));
             long long hi = std::min<long long>(A->row, std::min<long long>((long long)A->col - oa, (long long)B->col - oa - ob));
-            if (lo < hi) pairs.push_back({oa + ob, (unsigned)((a << 16) | b)});
+            if (lo < hi)
+                pairs.push_back({oa + ob, DiaPair{(long long)a * A->row, (long long)b * B->row + oa, (int)lo, (int)hi, 0, 0}});
         }
     std::stable_sort(pairs.begin(), pairs.end(), [](const Pair &x, const Pair &y) { return x.off < y.off; });
     std::vector<int> c_off, pstart;
-    std::vector<unsigned> pab(pairs.size());
+    std::vector<DiaPair> pab(pairs.size());
     for (size_t p = 0; p < pairs.size(); ++p) {
         if (p == 0 || pairs[p].off != pairs[p - 1].off) { c_off.push_back((int)pairs[p].off); pstart.push_back((int)p); }
-        pab[p] = pairs[p].ab;
+        pab[p] = pairs[p].dp;
     }
     pstart.push_back((int)pairs.size());
     int c_nd = (int)c_off.size();
@@ -230,7 +235,7 @@ int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, do
 
     int span = A->row + B->col - 1;
     DBuf<int> di, off, d_pstart;
-    DBuf<unsigned> d_pairs;
+    DBuf<DiaPair> d_pairs;
     DBuf<double> val;
     IAS_TRY(di.alloc((size_t)std::max(span, 1)));
     IAS_TRY(off.alloc((size_t)std::max(c_nd, 1)));
@@ -243,19 +248,17 @@ int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, do
         IAS_LAUNCH(k_scatter_diag_ind, grid_for(c_nd, 256), 256, 0, c_nd, A->row, off.p, di.p);     // dia:150-158
     }
     IAS_CUDA(cudaMemcpyAsync(d_pstart.p, pstart.data(), sizeof(int) * pstart.size(), cudaMemcpyHostToDevice, s));
-    if (!pab.empty()) IAS_CUDA(cudaMemcpyAsync(d_pairs.p, pab.data(), sizeof(unsigned) * pab.size(), cudaMemcpyHostToDevice, s));
+    if (!pab.empty()) IAS_CUDA(cudaMemcpyAsync(d_pairs.p, pab.data(), sizeof(DiaPair) * pab.size(), cudaMemcpyHostToDevice, s));
 
-    size_t sm = sizeof(int) * ((size_t)c_nd + 1 + ao.size() + bo.size() + pab.size());
+    size_t sm = sizeof(DiaPair) * pab.size() + sizeof(int) * ((size_t)c_nd + 1);
     if (A->row && c_nd) {
         constexpr int BLOCK = 256;
-        unsigned grid = (unsigned)std::min<long long>(grid_for(A->row, BLOCK), (long long)c.sm_count * 8 * 64);
+        unsigned grid = (unsigned)std::min<long long>(grid_for(A->row, 2 * BLOCK), (long long)c.sm_count * 8 * 64);
         if (sm <= 32 * 1024) {
-            IAS_LAUNCH((k_dia_mul_dia<BLOCK, true>), grid, BLOCK, sm, A->row, A->col, B->col, (int)ao.size(), (int)bo.size(), c_nd,
-                       A->diagonal_offsets_dev, B->diagonal_offsets_dev, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p,
+            IAS_LAUNCH((k_dia_mul_dia<BLOCK, true>), grid, BLOCK, sm, A->row, c_nd, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p,
                        (int)pab.size(), val.p);
         } else {                               // many diagonals: the tables stay in global memory (L1/L2 resident)
-            IAS_LAUNCH((k_dia_mul_dia<BLOCK, false>), grid, BLOCK, 0, A->row, A->col, B->col, (int)ao.size(), (int)bo.size(), c_nd,
-                       A->diagonal_offsets_dev, B->diagonal_offsets_dev, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p,
+            IAS_LAUNCH((k_dia_mul_dia<BLOCK, false>), grid, BLOCK, 0, A->row, c_nd, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p,
                        (int)pab.size(), val.p);
         }
     }
