@@ -442,6 +442,30 @@ def main():
                "ms_per_step": e_ms, "ms_h2d": h2d, "ms_d2h": d2h, "api": "ias_csr_mul_csr_host (CSR_MUL_CSR on host operands)"}
         eng.lib.ias_release_host()
 
+    # ---- the structured-format kernel the front end would select for this operand (reported beside the CSR number)
+    also = None
+    if world == 1 and args.format == "csr" and args.workload == "poisson":
+        try:
+            d_dia = eng.CSRtoDIA(dA, gate=20.0)
+            if d_dia.choice:
+                for _ in range(3):
+                    c, _ms = eng.DIA_MUL_DIA_DEV(d_dia, d_dia); eng.free_dia(c)
+                torch.cuda.synchronize()
+                ev0.record(stream)
+                for _ in range(args.steps):
+                    c, k_ms = eng.DIA_MUL_DIA_DEV(d_dia, d_dia); nd_c = c.num_diagonals; eng.free_dia(c)
+                ev1.record(stream)
+                torch.cuda.synchronize()
+                dia_ms = ev0.elapsed_time(ev1) / args.steps
+                dia_bytes = 8.0 * rows * (2 * d_dia.num_diagonals + nd_c)
+                also = {"dia_path": {"ms_per_step": dia_ms, "value": 2.0 * products / (dia_ms * 1e6), "unit": "GFLOP/s",
+                                     "kernel": "k_dia_mul_dia", "algorithmic_bytes": dia_bytes,
+                                     "frac_of_hbm_peak": dia_bytes / (dia_ms * 1e-3) / 1e9 / peak,
+                                     "note": "DIA x DIA on the same operand (what spgemm-gpu's selector runs for banded inputs)"}}
+            eng.free_dia(d_dia)
+        except Exception as ex:
+            also = {"dia_path": {"error": repr(ex)}}
+
     # ---- CPU baseline: the reference's own CPU path on the host cores (rank 0, N=1)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -470,6 +494,8 @@ def main():
                            "ms_bin_sym": [round(float(np.mean([s.get("ms_bin_sym", [0] * 6)[b] for s in stats])), 4) for b in range(6)],
                            "ms_bin_num": [round(float(np.mean([s.get("ms_bin_num", [0] * 6)[b] for s in stats])), 4) for b in range(6)]},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks}
+        if also:
+            line["also"] = also
         emit(line)
     if world > 1:
         dist.destroy_process_group()
