@@ -287,8 +287,9 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         int m = (int)bl.count[BIN_T];
         int cap = std::max(1, (int)h[NBINS]);
         size_t sm = (size_t)TINY_BLOCK * cap * (sizeof(double) + sizeof(int));
-        int merge = rw.max_tiny_na <= 4 ? 4 : rw.max_tiny_na <= 6 ? 6 : 8;
-        auto k = merge == 4 ? k_num_tiny<AV, BV, TINY_BLOCK, 4> : merge == 6 ? k_num_tiny<AV, BV, TINY_BLOCK, 6> : k_num_tiny<AV, BV, TINY_BLOCK, 8>;
+        int merge = rw.max_tiny_na <= 4 ? 4 : rw.max_tiny_na <= 5 ? 5 : rw.max_tiny_na <= 6 ? 6 : 8;
+        auto k = merge == 4 ? k_num_tiny<AV, BV, TINY_BLOCK, 4> : merge == 5 ? k_num_tiny<AV, BV, TINY_BLOCK, 5>
+               : merge == 6 ? k_num_tiny<AV, BV, TINY_BLOCK, 6> : k_num_tiny<AV, BV, TINY_BLOCK, 8>;
         IAS_TRY(opt_in_smem(k, sm));
         IAS_LAUNCH(k, grid_for(m, TINY_BLOCK), TINY_BLOCK, sm, bl.rows_of(BIN_T), m, r0, A, B, out, c_ci, c_v, cap, rw.b_canonical);
         IAS_BIN_END(8 + BIN_T);

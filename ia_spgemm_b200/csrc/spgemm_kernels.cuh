@@ -129,6 +129,24 @@ struct TinyCursors {
     }
 };
 
+// number of distinct columns of one tiny row (symbolic k-way merge)
+template <class AV, class BV, int MERGE>
+__device__ __forceinline__ int tiny_merge_count(const AV &A, const BV &B, typename AV::off_t pa, int na)
+{
+    TinyCursors<BV, MERGE, false> cur;
+    cur.init(A, B, pa, na);
+    int cnt = 0;
+    while (cnt < T_MAX) {
+        int m = cur.head();
+        if (m == 0x7fffffff) break;
+#pragma unroll
+        for (int a = 0; a < MERGE; ++a)
+            if (cur.hc[a] == m) cur.advance(B, a);
+        ++cnt;
+    }
+    return cnt;
+}
+
 // ---------------------------------------------------------------- analyze
 // block-level histogram of bins + sum of products.  Shared atomics are 32-bit and warp-aggregated:
 // a 64-bit shared atomicAdd is a CAS loop, and with every row of a CTA in the same bin (Poisson,
@@ -193,17 +211,7 @@ __global__ void __launch_bounds__(256) k_row_ub_thread(int nrows, int r0, AV A, 
             // (A's and B's lines are in L1 now).  The host keeps these counts only if the whole of B turns out
             // canonical and no tiny row has more than 8 entries; otherwise k_sym_tiny recomputes the bin.
             if (bin == BIN_T && tiny_na <= 8) {
-                TinyCursors<BV, 8, false> cur;
-                cur.init(A, B, pa, tiny_na);
-                int cnt = 0;
-                while (cnt < T_MAX) {
-                    int m = cur.head();
-                    if (m == 0x7fffffff) break;
-#pragma unroll
-                    for (int a = 0; a < 8; ++a)
-                        if (cur.hc[a] == m) cur.advance(B, a);
-                    ++cnt;
-                }
+                int cnt = tiny_na <= 5 ? tiny_merge_count<AV, BV, 5>(A, B, pa, tiny_na) : tiny_merge_count<AV, BV, 8>(A, B, pa, tiny_na);
                 nnz_row[li] = cnt;
                 tiny_cnt = cnt;
             }
