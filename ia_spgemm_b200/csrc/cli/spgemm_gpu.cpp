@@ -4,7 +4,8 @@
 //   spgemm-gpu A.mtx                 C = A*A   (README.md:10 "All tests default calculate the square of A")
 //   spgemm-gpu A.mtx B.mtx [mode]    C = A*B; mode != 0 dumps the operands like testing_mode (CPU/main.cpp:489-497)
 //   options: --all (run every format as the reference does), --json, --gate X (default 20, GPU release),
-//            --repeat N (best of N timed runs after one warm-up; the reference times one cold run)
+//            --repeat N (best of N timed runs after one warm-up; the reference times one cold run),
+//            --transpose-b (B := A^T, what GPU/main.cu:261-269 computes), --write-c FILE (CSR result as .mtx)
 //
 // Same stages as the reference main: Matrix-Market load -> density images ./imgs/img{1,2}.txt ->
 // 26 features -> format selection -> multiply -> report block (Appendix A of SURVEY.md: run_time,
@@ -63,13 +64,16 @@ static int select_format(const double *f, bool dia_ok, bool ell_ok)
 int main(int argc, char **argv)
 {
     std::vector<std::string> pos;
-    bool all = false, json = false;
+    bool all = false, json = false, transpose_b = false;
+    std::string write_c;
     double gate = 20.0;
     int repeat = 1;
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "--all") all = true;
         else if (a == "--json") json = true;
+        else if (a == "--transpose-b") transpose_b = true;
+        else if (a == "--write-c" && i + 1 < argc) write_c = argv[++i];
         else if (a == "--gate" && i + 1 < argc) gate = atof(argv[++i]);
         else if (a == "--repeat" && i + 1 < argc) repeat = atoi(argv[++i]);
         else pos.push_back(a);
@@ -86,17 +90,22 @@ int main(int argc, char **argv)
     int rc = ias_mtx_load(fa.c_str(), &A);
     if (rc) { printf("F1: could not load %s (code %d)\n", fa.c_str(), rc); return rc; }
     bool same = fa == fb;
+    const bool host_same = same;               // B's host arrays alias A's
     if (same) B = A;
     else if ((rc = ias_mtx_load(fb.c_str(), &B)) != 0) { printf("F2: could not load %s (code %d)\n", fb.c_str(), rc); return rc; }
     printf("Weight Matrix (A): %dx%d: nnz = %d\n", A.row, A.col, A.nnz);
     printf("Activation Matrix (B): %dx%d: nnz = %d\n", B.row, B.col, B.nnz);
     if (testing_mode) { print_csr("A_csr", A); print_csr("B_csr", B); }
-    if (A.col > B.row) { printf("shape mismatch: A is %dx%d, B is %dx%d\n", A.row, A.col, B.row, B.col); return -5; }
+    if (!transpose_b && A.col > B.row) { printf("shape mismatch: A is %dx%d, B is %dx%d\n", A.row, A.col, B.row, B.col); return -5; }
 
     if (ias_init(0)) return die("ias_init");
     IasCsrMatrixDev dA, dB;
     if (ias_upload_csr(&A, &dA)) return die("upload A");
-    if (same) dB = dA;
+    if (transpose_b) {                         // the GPU release's operand: B := A^T
+        if (ias_csr_transpose(&dA, &dB)) return die("transpose");
+        same = false;
+        printf("Activation Matrix (B := A^T): %dx%d: nnz = %d\n", dB.row, dB.col, dB.nnz);
+    } else if (same) dB = dA;
     else if (ias_upload_csr(&B, &dB)) return die("upload B");
 
     // density representation -> ./imgs/img1.txt, ./imgs/img2.txt (CPU/main.cpp:516-643)
@@ -134,7 +143,7 @@ int main(int argc, char **argv)
     int c = select_format(feat, dia_ok, ell_ok);
     printf("The Chosen One = Algorithm %d\n", c + 1);
 
-    auto want = [&](int k) { return all || k == c; };
+    auto want = [&](int k) { return all || k == c || (k == 1 && !write_c.empty()); };
     // repeat == 1: one cold run, as the reference times it; repeat > 1: one warm-up, then the best of `repeat`
     const int runs = repeat > 1 ? repeat + 1 : 1;
     auto keep = [&](int r, double t, double &best) { if (r == (runs > 1 ? 1 : 0) || (r > 0 && t < best)) best = t; };
@@ -145,7 +154,10 @@ int main(int argc, char **argv)
             IasSpgemmStats st;
             if (ias_csr_mul_csr_dev64(&dA, &dB, &C, &st)) return die("CSR_MUL_CSR_DEV");
             keep(r, st.ms_total, run[1]);
-            if (r == runs - 1) { ias_checksum(C.values_dev, C.nnz, &sum[1]); size[1] = ias_sizeof_csr(C.row, C.nnz); }
+            if (r == runs - 1) {
+                ias_checksum(C.values_dev, C.nnz, &sum[1]); size[1] = ias_sizeof_csr(C.row, C.nnz);
+                if (!write_c.empty() && ias_mtx_write_csr64(write_c.c_str(), &C, 0)) return die("write C");
+            }
             ias_free_csr64_dev(&C);
         }
         printf("DONE CSR\n");
@@ -220,7 +232,7 @@ int main(int argc, char **argv)
     }
     if (json) {
         printf("{\"file_a\": \"%s\", \"file_b\": \"%s\", \"rows\": %d, \"cols\": %d, \"nnz_a\": %d, \"products\": %lld, \"chosen\": %d, \"features\": [",
-               fa.c_str(), fb.c_str(), A.row, B.col, A.nnz, flops, c + 1);
+               fa.c_str(), fb.c_str(), A.row, dB.col, A.nnz, flops, c + 1);
         for (int i = 0; i < 26; ++i) printf("%s%.17g", i ? ", " : "", feat[i]);
         printf("], \"run_ms\": [%g, %g, %g, %g, %g], \"verified_sum\": [%.17g, %.17g, %.17g, %.17g, %.17g], \"memory_size\": [%.17g, %.17g, %.17g, %.17g, %.17g]}\n",
                run[0], run[1], run[2], run[3], run[4], sum[0], sum[1], sum[2], sum[3], sum[4], size[0], size[1], size[2], size[3], size[4]);
@@ -229,6 +241,6 @@ int main(int argc, char **argv)
     ias_free_ell_dev(&a_ell); if (!same) ias_free_ell_dev(&b_ell);
     ias_free_coo_dev(&a_coo); if (!same) ias_free_coo_dev(&b_coo);
     ias_free_csr_dev(&dA); if (!same) ias_free_csr_dev(&dB);
-    ias_free_host_csr(&A); if (!same) ias_free_host_csr(&B);
+    ias_free_host_csr(&A); if (!host_same) ias_free_host_csr(&B);
     return 0;
 }

@@ -92,7 +92,7 @@ ABI_SYMBOLS = [
     "ias_density_image", "ias_getinfo1", "ias_getinfo2", "ias_getinfo3", "ias_count_diagonals",
     "ias_max_row_nnz", "ias_features26",
     "ias_sizeof_csr", "ias_sizeof_dia", "ias_sizeof_ell", "ias_sizeof_coo",
-    "ias_mtx_load", "ias_free_host_csr",
+    "ias_mtx_load", "ias_free_host_csr", "ias_mtx_write_csr64", "ias_csr_transpose",
     "ias_gen_poisson2d", "ias_gen_uniform", "ias_gen_rmat",
 ]
 
@@ -211,6 +211,15 @@ class Engine:
     def copy(self, dst_ptr, src_ptr, nbytes, kind):
         """kind: 0 host->device, 1 device->host, 2 device->device."""
         self._ck(self.lib.ias_copy(C.c_void_p(dst_ptr), C.c_void_p(src_ptr), nbytes, kind))
+
+    def transpose(self, A):
+        """B := A^T on device (GPU/main.cu:261-269 does it with mkl_dcsrcsc on the host)."""
+        d = CsrMatrixDev()
+        self._ck(self.lib.ias_csr_transpose(C.byref(A.dev), C.byref(d)))
+        return DeviceCsr(self, d)
+
+    def mtx_write(self, path, c64, row_base=0):
+        self._ck(self.lib.ias_mtx_write_csr64(path.encode(), C.byref(c64), C.c_int(row_base)))
 
     def forget_operand(self, A=None):
         self.lib.ias_forget_operand(C.byref(A.dev) if A is not None else None)

@@ -222,11 +222,18 @@ double ias_sizeof_dia(int rows, int cols, int num_diagonals);
 double ias_sizeof_ell(int rows, int width);
 double ias_sizeof_coo(int rows, long long nnz);
 
+/* ---------------------------------------------------------------- transpose (A * A^T mode of GPU/main.cu:261-269) */
+/* B := A^T on device (the reference calls mkl_dcsrcsc on the host); the result is canonical */
+int ias_csr_transpose(const IasCsrMatrixDev *A, IasCsrMatrixDev *At);
+
 /* ---------------------------------------------------------------- Matrix-Market front end */
 /* loader of CPU/main.cpp:143-458 (banner: CPU/mmio.h:254-337): returns 0 or the reference's
  * exit codes -1 (open) -2 (banner) -3 (complex) -4 (size line); arrays are malloc'd. */
 int ias_mtx_load(const char *path, IasCsrMatrix *out);
 void ias_free_host_csr(IasCsrMatrix *m);
+/* writes a result as "coordinate real general" (mm_write_mtx_crd, CPU/mmio.h:445-486, which the reference
+ * never calls); row_base shifts the row indices of a row block */
+int ias_mtx_write_csr64(const char *path, const IasCsr64Dev *C, int row_base);
 
 /* ---------------------------------------------------------------- synthetic operands (device) */
 /* BASELINE.json configs, bit-identical to ia_spgemm_b200/workloads.py */

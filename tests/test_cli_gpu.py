@@ -56,3 +56,17 @@ def test_cli_errors(tmp_path):
     p = tmp_path / "cplx.mtx"
     p.write_text("%%MatrixMarket matrix coordinate complex general\n1 1 1\n1 1 1.0 0.0\n")
     assert _run([str(p)], str(tmp_path)).returncode == 253                # -3
+
+
+def test_cli_transpose_b_and_write_c(golden, mtx_dir, tmp_path):
+    """--transpose-b reproduces the GPU release's operand (B := A^T): dia.mtx gives the screenshot's 152 bytes."""
+    out = str(tmp_path / "c.mtx")
+    r = _run([os.path.join(mtx_dir, "dia.mtx"), "--transpose-b", "--write-c", out, "--json"], str(tmp_path))
+    assert r.returncode == 0, r.stdout + r.stderr
+    j = json.loads(r.stdout.strip().splitlines()[-1])
+    assert j["products"] == 13 and j["memory_size"][1] == 152.0
+    lines = open(out).read().strip().splitlines()
+    assert lines[0].startswith("%%MatrixMarket matrix coordinate real general") and lines[1].split() == ["4", "4", "10"]
+    assert len(lines) == 12
+    r = _run([os.path.join(mtx_dir, "Trec5.mtx"), "--transpose-b", "--all"], str(tmp_path))     # rectangular 3x7: A*A^T is 3x3
+    assert r.returncode == 0 and "DONE CSR" in r.stdout

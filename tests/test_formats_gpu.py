@@ -271,3 +271,68 @@ def test_device_generators_are_bit_identical_to_numpy(eng):
         assert np.array_equal(rp, host[2]) and np.array_equal(ci, host[3]) and np.array_equal(v, host[4])
         assert eng.is_canonical(dev)
         dev.close()
+
+
+# ---------------------------------------------------------------- transpose / A * A^T (GPU/main.cu:261-269) / writer
+@pytest.mark.parametrize("name", SQUARE + RECT)
+def test_a_times_a_transpose_bundled(eng, oracle, mtx_dir, name):
+    """What the reference's GPU driver actually multiplies: B := A^T.  Works for the rectangular inputs too."""
+    import scipy.sparse as sp
+    A = _load(oracle, mtx_dir, name)
+    rows, cols, rp, ci, v = A
+    dA = eng.upload(*A)
+    dT = eng.transpose(dA)
+    t_rows, t_cols, t_rp, t_ci, t_v = dT.download()
+    T = sp.csr_matrix((v, ci, rp), shape=(rows, cols)).T.tocsr()
+    T.sort_indices()
+    assert (t_rows, t_cols) == (cols, rows)
+    assert np.array_equal(t_rp, T.indptr) and np.array_equal(t_ci, T.indices) and np.array_equal(t_v, T.data)
+    assert eng.is_canonical(dT)
+    got, st = eng.CSR_MUL_CSR_DEV(dA, dT)
+    B = (cols, rows, t_rp, t_ci, t_v)
+    want = oracle.csr_mul_csr(rows, rows, rp, ci, v, t_rp, t_ci, t_v)
+    assert_csr = __import__("util").assert_csr_parity
+    assert_csr(got, want, mag=abs_product(oracle, A, B))
+    assert st["products"] == oracle.getflop(rp, ci, t_rp)
+    dT.close(); dA.close()
+
+
+def test_dia_times_dia_transpose_screenshot_values(eng, oracle, golden, mtx_dir):
+    """GPU/2.jpg: dia.mtx * dia.mtx^T has 13 products, 10 stored entries, memory_size 152."""
+    g = golden["dia_times_diaT"]
+    A = _load(oracle, mtx_dir, "dia")
+    dA = eng.upload(*A)
+    dT = eng.transpose(dA)
+    assert dT.download()[2].tolist() == g["b_row_ptr"] and dT.download()[3].tolist() == g["b_col_ind"]
+    (rp, ci, v), st = eng.CSR_MUL_CSR_DEV(dA, dT)
+    assert st["nnz"] == g["nnz"] == 10 and st["products"] == g["flop"] == 13
+    assert eng.lib.ias_sizeof_csr(4, st["nnz"]) == g["sizeof_csr"] == 152.0
+    dT.close(); dA.close()
+
+
+def test_transpose_large_random_and_roundtrip(eng):
+    import scipy.sparse as sp
+    A = W.rmat(12, 8, seed=9)
+    dA = eng.upload(*A)
+    dT = eng.transpose(dA)
+    dTT = eng.transpose(dT)
+    r = dTT.download()
+    assert np.array_equal(r[2], A[2]) and np.array_equal(r[3], A[3]) and np.array_equal(r[4], A[4])
+    T = sp.csr_matrix((A[4], A[3], A[2]), shape=(A[0], A[1])).T.tocsr(); T.sort_indices()
+    t = dT.download()
+    assert np.array_equal(t[2], T.indptr) and np.array_equal(t[3], T.indices) and np.array_equal(t[4], T.data)
+    for d in (dTT, dT, dA):
+        d.close()
+
+
+def test_matrix_market_writer_roundtrip(eng, oracle, tmp_path):
+    A = W.random_sparse(40, 40, 0.1, seed=2)
+    dA = eng.upload(*A)
+    c64, st = eng.CSR_MUL_CSR_DEV(dA, dA, keep=True)
+    path = str(tmp_path / "c.mtx")
+    eng.mtx_write(path, c64)
+    want = eng._take_csr64(c64)
+    rows, cols, rp, ci, v = eng.mtx_load(path)
+    assert (rows, cols) == (40, 40)
+    assert np.array_equal(rp, want[0]) and np.array_equal(ci, want[1]) and np.array_equal(v, want[2])   # %.17g round-trips fp64
+    dA.close()
