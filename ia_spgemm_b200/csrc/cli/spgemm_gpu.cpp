@@ -5,7 +5,9 @@
 //   spgemm-gpu A.mtx B.mtx [mode]    C = A*B; mode != 0 dumps the operands like testing_mode (CPU/main.cpp:489-497)
 //   options: --all (run every format as the reference does), --json, --gate X (default 20, GPU release),
 //            --repeat N (best of N timed runs after one warm-up; the reference times one cold run),
-//            --transpose-b (B := A^T, what GPU/main.cu:261-269 computes), --write-c FILE (CSR result as .mtx)
+//            --transpose-b (B := A^T, what GPU/main.cu:261-269 computes), --write-c FILE (CSR result as .mtx),
+//            --matnet FILE.h5 (select with the reference's MatNet weights, e.g. NetWeights/Intel_weights.h5 or
+//            P100_weights.h5; without it a rule on the feature vector picks the format)
 //
 // Same stages as the reference main: Matrix-Market load -> density images ./imgs/img{1,2}.txt ->
 // 26 features -> format selection -> multiply -> report block (Appendix A of SURVEY.md: run_time,
@@ -65,7 +67,7 @@ int main(int argc, char **argv)
 {
     std::vector<std::string> pos;
     bool all = false, json = false, transpose_b = false;
-    std::string write_c;
+    std::string write_c, matnet_path;
     double gate = 20.0;
     int repeat = 1;
     for (int i = 1; i < argc; ++i) {
@@ -74,6 +76,7 @@ int main(int argc, char **argv)
         else if (a == "--json") json = true;
         else if (a == "--transpose-b") transpose_b = true;
         else if (a == "--write-c" && i + 1 < argc) write_c = argv[++i];
+        else if (a == "--matnet" && i + 1 < argc) matnet_path = argv[++i];
         else if (a == "--gate" && i + 1 < argc) gate = atof(argv[++i]);
         else if (a == "--repeat" && i + 1 < argc) repeat = atoi(argv[++i]);
         else pos.push_back(a);
@@ -109,12 +112,12 @@ int main(int argc, char **argv)
     else if (ias_upload_csr(&B, &dB)) return die("upload B");
 
     // density representation -> ./imgs/img1.txt, ./imgs/img2.txt (CPU/main.cpp:516-643)
-    std::vector<long long> img(128 * 128);
+    std::vector<long long> img(128 * 128), img_b(128 * 128);
     mkdir("imgs", 0755);
     if (ias_density_image(&dA, img.data())) return die("density A");
     if (write_image("./imgs/img1.txt", img.data())) fprintf(stderr, "spgemm-gpu: cannot write ./imgs/img1.txt\n");
-    if (ias_density_image(&dB, img.data())) return die("density B");
-    if (write_image("./imgs/img2.txt", img.data())) fprintf(stderr, "spgemm-gpu: cannot write ./imgs/img2.txt\n");
+    if (ias_density_image(&dB, img_b.data())) return die("density B");
+    if (write_image("./imgs/img2.txt", img_b.data())) fprintf(stderr, "spgemm-gpu: cannot write ./imgs/img2.txt\n");
     printf("------------------------------------------\n");
 
     double feat[26];
@@ -141,6 +144,25 @@ int main(int argc, char **argv)
     bool dia_ok = a_dia.choice && b_dia.choice, ell_ok = a_ell.choice && b_ell.choice;
 
     int c = select_format(feat, dia_ok, ell_ok);
+    if (!matnet_path.empty()) {
+        // MatNet.Pred (CPU/MatNet.py:24-96) on the two density images and the feature vector
+        void *net = nullptr;
+        if (ias_matnet_load(matnet_path.c_str(), &net)) return die("MatNet weights");
+        int nf = 0, nc = 0, cls = 0;
+        double probs[8] = {0};
+        ias_matnet_shape(net, &nf, &nc, nullptr);
+        if (ias_matnet_predict(net, img.data(), img_b.data(), feat, &cls, probs)) return die("MatNet.Pred");
+        ias_matnet_free(net);
+        if (nc == 5) {                         // CPU nets: 0 MKL 1 CSR 2 DIA 3 ELL 4 COO (the engine runs its CSR path for the MKL slot)
+            c = cls == 0 ? 1 : cls;
+            if ((c == 2 && !dia_ok) || (c == 3 && !ell_ok)) c = 1;      // the size gate refused the format MatNet asked for
+        } else {                               // GPU net: CUSP / cuSPARSE / NSPARSE are all CSR SpGEMMs -> the engine's CSR pipeline
+            static const char *names[3] = {"CUSP", "cuSPARSE", "NSPARSE"};
+            printf("MatNet predicts Algorithm %s is optimal\n", names[cls < 3 ? cls : 0]);
+            c = 1;
+        }
+        printf("MatNet class %d of %d (p = %.4f)\n", cls, nc, probs[cls]);
+    }
     printf("The Chosen One = Algorithm %d\n", c + 1);
 
     auto want = [&](int k) { return all || k == c || (k == 1 && !write_c.empty()); };

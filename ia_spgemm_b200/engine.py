@@ -94,7 +94,72 @@ ABI_SYMBOLS = [
     "ias_sizeof_csr", "ias_sizeof_dia", "ias_sizeof_ell", "ias_sizeof_coo",
     "ias_mtx_load", "ias_free_host_csr", "ias_mtx_write_csr64", "ias_csr_transpose",
     "ias_gen_poisson2d", "ias_gen_uniform", "ias_gen_rmat",
+    "ias_matnet_load", "ias_matnet_create", "ias_matnet_set_tensor", "ias_matnet_get_tensor", "ias_matnet_shape",
+    "ias_matnet_predict", "ias_matnet_free",
 ]
+
+
+class MatNet:
+    """Native MatNet selector (MatNet.Pred, CPU/MatNet.py:24-96).  Host only: usable without a GPU."""
+    TENSORS = ["conv2d_%d/%s" % (i, k) for i in range(1, 7) for k in ("kernel", "bias")] + \
+              ["dense_%d/%s" % (i, k) for i in range(1, 5) for k in ("kernel", "bias")]
+
+    def __init__(self, lib, handle):
+        self.lib, self.h = lib, handle
+
+    @classmethod
+    def load(cls, path, lib=None):
+        lib = lib or load_library()
+        h = C.c_void_p()
+        rc = lib.ias_matnet_load(path.encode(), C.byref(h))
+        if rc != 0:
+            raise EngineError(rc, (lib.ias_last_error() or b"").decode(errors="replace"))
+        return cls(lib, h)
+
+    @classmethod
+    def from_arrays(cls, tensors, lib=None):
+        lib = lib or load_library()
+        h = C.c_void_p()
+        lib.ias_matnet_create(C.byref(h))
+        for name, a in tensors.items():
+            a = np.ascontiguousarray(a, dtype=np.float32)
+            dims = (C.c_longlong * a.ndim)(*a.shape)
+            rc = lib.ias_matnet_set_tensor(h, name.encode(), a.ctypes.data_as(C.POINTER(C.c_float)), dims, a.ndim)
+            if rc != 0:
+                raise EngineError(rc, (lib.ias_last_error() or b"").decode(errors="replace"))
+        return cls(lib, h)
+
+    def shape(self):
+        f, c, p = C.c_int(), C.c_int(), C.c_longlong()
+        self.lib.ias_matnet_shape(self.h, C.byref(f), C.byref(c), C.byref(p))
+        return f.value, c.value, p.value
+
+    def tensor(self, name):
+        dims, rank = (C.c_longlong * 4)(), C.c_int()
+        if self.lib.ias_matnet_get_tensor(self.h, name.encode(), None, dims, C.byref(rank)) != 0:
+            raise KeyError(name)
+        shape = tuple(dims[i] for i in range(rank.value))
+        out = np.empty(shape, dtype=np.float32)
+        self.lib.ias_matnet_get_tensor(self.h, name.encode(), out.ctypes.data_as(C.POINTER(C.c_float)), None, None)
+        return out
+
+    def predict(self, img1, img2, features):
+        img1 = np.ascontiguousarray(img1, dtype=np.int64).reshape(-1)
+        img2 = np.ascontiguousarray(img2, dtype=np.int64).reshape(-1)
+        f = np.ascontiguousarray(features, dtype=np.float64)
+        nf, nc, _ = self.shape()
+        assert img1.size == 16384 and img2.size == 16384 and f.size >= nf
+        cls_, probs = C.c_int(), np.zeros(nc)
+        rc = self.lib.ias_matnet_predict(self.h, img1.ctypes.data_as(_L), img2.ctypes.data_as(_L), f.ctypes.data_as(_D),
+                                         C.byref(cls_), probs.ctypes.data_as(_D))
+        if rc != 0:
+            raise EngineError(rc, (self.lib.ias_last_error() or b"").decode(errors="replace"))
+        return cls_.value, probs
+
+    def close(self):
+        if self.h:
+            self.lib.ias_matnet_free(self.h)
+            self.h = None
 
 
 def load_library():
@@ -116,6 +181,11 @@ def load_library():
         "ias_getinfo3": [C.c_int, C.c_longlong, C.c_int, _D],
         "ias_gen_rmat": [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p],
         "ias_csr_to_dia": [C.c_void_p, C.c_double, C.c_void_p], "ias_csr_to_ell": [C.c_void_p, C.c_double, C.c_void_p],
+        "ias_matnet_load": [C.c_char_p, C.c_void_p], "ias_matnet_create": [C.c_void_p], "ias_matnet_free": [C.c_void_p],
+        "ias_matnet_set_tensor": [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int],
+        "ias_matnet_get_tensor": [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p],
+        "ias_matnet_shape": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
+        "ias_matnet_predict": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p],
     }
     for name, args in sigs.items():
         if hasattr(lib, name):          # a missing export is reported by tests/test_abi.py, not here

@@ -235,6 +235,20 @@ void ias_free_host_csr(IasCsrMatrix *m);
  * never calls); row_base shifts the row indices of a row block */
 int ias_mtx_write_csr64(const char *path, const IasCsr64Dev *C, int row_base);
 
+/* ---------------------------------------------------------------- MatNet format selector (host) */
+/* MatNet.Pred, CPU/MatNet.py:24-96 (called through embedded CPython at CPU/main.cpp:682-704, GPU/main.cu:446-460):
+ * weights from a Keras 2.1 HDF5 file (./NetWeights/{Intel,Amd,P100}_weights.h5), two 128x128 density images and the
+ * feature vector (26 values for the CPU nets, 18 for the GPU net) -> class index (CPU: 0 MKL 1 CSR 2 DIA 3 ELL
+ * 4 COO; GPU: 0 CUSP 1 cuSPARSE 2 NSPARSE). */
+int ias_matnet_load(const char *h5_path, void **net);
+int ias_matnet_create(void **net);                /* empty net, to be filled with ias_matnet_set_tensor */
+int ias_matnet_set_tensor(void *net, const char *name, const float *data, const long long *dims, int rank);
+int ias_matnet_get_tensor(void *net, const char *name, float *out, long long *dims, int *rank);
+int ias_matnet_shape(void *net, int *n_features, int *n_classes, long long *n_params);
+int ias_matnet_predict(void *net, const long long *img1_16384, const long long *img2_16384, const double *features,
+                       int *cls, double *probs);
+void ias_matnet_free(void *net);
+
 /* ---------------------------------------------------------------- synthetic operands (device) */
 /* BASELINE.json configs, bit-identical to ia_spgemm_b200/workloads.py */
 int ias_gen_poisson2d(int nx, int ny, IasCsrMatrixDev *out);   /* nx*ny nodes, row-major node order */
