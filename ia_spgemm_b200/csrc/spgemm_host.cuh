@@ -207,10 +207,20 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
     if (bl.count[BIN_W]) {
         IAS_BIN_BEGIN(BIN_W);
         int n = (int)bl.count[BIN_W];
-        auto k = k_sym_hash<AV, BV, 32, 256, SYM_W_TSIZE>;
-        size_t sm = (size_t)8 * SYM_W_TSIZE * sizeof(int);
-        IAS_TRY(opt_in_smem(k, sm));
-        IAS_LAUNCH(k, grid_for(n, 8), 256, sm, bl.rows_of(BIN_W), n, r0, A, B, rw.nnz_row.p);
+        // key table sized from the bin's largest ub (load <= 50 %): 256 / 512 / 1024 slots per warp
+        int mub = std::max(rw.max_warp_ub, T_MAX + 1);
+        if (mub <= 128) {
+            auto k = k_sym_hash<AV, BV, 32, 256, 256>;
+            IAS_LAUNCH(k, grid_for(n, 8), 256, (size_t)8 * 256 * sizeof(int), bl.rows_of(BIN_W), n, r0, A, B, rw.nnz_row.p);
+        } else if (mub <= 256) {
+            auto k = k_sym_hash<AV, BV, 32, 256, 512>;
+            IAS_LAUNCH(k, grid_for(n, 8), 256, (size_t)8 * 512 * sizeof(int), bl.rows_of(BIN_W), n, r0, A, B, rw.nnz_row.p);
+        } else {
+            auto k = k_sym_hash<AV, BV, 32, 256, SYM_W_TSIZE>;
+            size_t sm = (size_t)8 * SYM_W_TSIZE * sizeof(int);
+            IAS_TRY(opt_in_smem(k, sm));
+            IAS_LAUNCH(k, grid_for(n, 8), 256, sm, bl.rows_of(BIN_W), n, r0, A, B, rw.nnz_row.p);
+        }
         IAS_BIN_END(BIN_W);
         rw.sym_timed[BIN_W] = true;
     }
@@ -347,7 +357,8 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
         {
             auto k = k_num_global<AV, BV, 1024>;
-            int win = 24576;                                   // 192 KB tile of fp64 partial sums
+            int win = 20480;                                   // 160 KB tile of fp64 partial sums (192 KB would leave 28 KB of L1 for the
+                                                               // B-row stream: ncu/clock64 showed the mark pass 1.6x slower)
             size_t sm = (size_t)win * sizeof(double);
             IAS_TRY(opt_in_smem(k, sm));
             IAS_LAUNCH(k, rw.gslots, 1024, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p, GLayout::make(ncols_b),
