@@ -40,7 +40,7 @@ def main():
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
         ki, ri, wi = hdr.index("Kernel Name"), hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
         for r in rows[2:]:
-            name = r[ki].split("<")[0].split("(")[0].replace("void ", "").strip()
+            name = r[ki].replace("void ", "").replace("<unnamed>::", "").replace("ias::", "").split("<")[0].split("(")[0].strip()
             b = float(r[ri]) * scale.get(units[ri], 1.0) + float(r[wi]) * scale.get(units[wi], 1.0)
             traffic.setdefault(workload, {})[name] = b
         json.dump(traffic, open(tj, "w"), indent=1, sort_keys=True)
