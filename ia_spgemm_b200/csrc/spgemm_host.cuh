@@ -69,7 +69,6 @@ struct RangeWork {
     long long products = 0;
     long long sym_hist[8] = {0};
     long long num_hist[8] = {0};
-    int max_tiny_nnz = 0, max_nnz = 0;
     int b_canonical = 0;           // every B row strictly increasing in column (enables the merge kernels)
     int max_warp_ub = 0;           // largest upper bound among warp-bin rows (sizes the register sort)
     int max_tiny_na = 0;           // longest A row / largest upper bound among tiny rows

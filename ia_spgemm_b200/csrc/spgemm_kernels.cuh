@@ -6,17 +6,20 @@
 // Gustavson loops of ELL_MUL_ELL / COO_MUL_COO (ell:80-189, coo:72-161).
 //
 // Pipeline (one row range [r0, r1) of C at a time):
-//   analyze   k_row_ub_*      ub[i] = sum of B row lengths over A(i,:) (= the row's share of GetFlop),
-//                             symbolic bin of the row, histogram of bins, total products
-//   symbolic  k_sym_tiny      ub <= 32       one thread per row, private list in shared memory
-//             k_sym_hash      ub <= 24576    warp / CTA per row, shared-memory hash of column keys
-//             k_sym_global    larger         persistent CTA per row, column bitmap in global memory (L2)
+//   analyze   k_row_ub_thread  ub[i] = sum of B row lengths over A(i,:) (= the row's share of GetFlop), symbolic
+//             k_row_ub_long    bin, bin histogram, total products, canonical check of A's rows; tiny rows are
+//                              counted on the spot with the k-way merge (kept if B turns out canonical)
+//   symbolic  k_sym_tiny       ub <= 32       thread per row: cursor merge (canonical B) or private list
+//             k_sym_hash       ub <= 24576    warp / CTA per row, shared-memory hash of column keys
+//             k_sym_global     larger         persistent CTA per row, {bitmap, rank} cells in global memory (L2)
 //   scan      cub ExclusiveSum over nnz(C_i) -> 64-bit row pointers
-//   numeric   k_num_tiny      ub <= 32       one thread per row, sorted private list, coalesced copy-out
-//             k_num_hash      nnz <= 12288   warp / CTA per row, shared-memory hash SPA (key,value),
-//                                            in-place compaction + bitonic sort -> column-sorted row
-//             k_num_global    larger         bitmap + rank: mark columns, prefix-popcount, emit sorted
-//                                            columns, accumulate values with RED.F64 at the ranked slot
+//   numeric   k_num_tiny       ub <= 32       thread per row k-way merge, rows staged in smem, coalesced copy-out
+//             k_esc_warp       ub <= 512      warp per row: expand - bitonic sort in registers - compress
+//             k_num_hash_cta   nnz <= 12288   CTA per row: shared-memory hash SPA, block radix sort of
+//                                             (column, slot), striped coalesced write
+//             k_num_global     larger         bitmap + rank: mark columns, prefix-popcount, emit sorted columns,
+//                                             accumulate windows of ranks in a dense shared-memory tile
+//   products are enumerated by warp_products (one warp) / cta_products (balanced over a CTA, 4 per lane and trip)
 // No intermediate product is ever materialised in global memory (the reference's ESC chain writes
 // 24 B per product, csr_dev:170,190-194).
 #pragma once
