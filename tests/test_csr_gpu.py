@@ -246,3 +246,18 @@ def test_touched_b_bytes(eng):
         T = np.unique(ci[rp[r0]:rp[r1]])
         assert eng.touched_b_bytes(dA, dA, rows=(r0, r1)) == int(4 * len(T) + 12 * lens[T].sum())
     dA.close()
+
+
+def test_wide_column_space_uses_64bit_sort_keys(eng, oracle):
+    """More than 2^23 columns: the register sort of the warp bin packs (column, index) into 64-bit keys."""
+    rng = np.random.default_rng(5)
+    ncols = (1 << 24) + 5
+    A = W.random_sparse(200, 300, 0.03, seed=21)
+    per = 40
+    cols = np.sort(np.stack([rng.choice(ncols, size=per, replace=False) for _ in range(300)]), axis=1)
+    cols[0, -1] = ncols - 1                                  # the very last column is used
+    B = (300, ncols, (np.arange(301) * per).astype(np.int32), cols.reshape(-1).astype(np.int32),
+         rng.uniform(0.5, 1.5, size=300 * per))
+    got, st = _check(eng, oracle, A, B, mag=False)
+    assert st["num_bin_rows"][2] > 0                         # warp bin populated
+    assert int(got[1].max()) == ncols - 1

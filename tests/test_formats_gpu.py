@@ -336,3 +336,29 @@ def test_matrix_market_writer_roundtrip(eng, oracle, tmp_path):
     assert (rows, cols) == (40, 40)
     assert np.array_equal(rp, want[0]) and np.array_equal(ci, want[1]) and np.array_equal(v, want[2])   # %.17g round-trips fp64
     dA.close()
+
+
+def test_ell_and_coo_views_through_every_bin(eng, oracle):
+    """The CTA / global kernels are templated on the operand view: run them on ELL (fixed width) and COO
+    (64-bit row offsets) operands of a skewed matrix that populates every bin."""
+    A = W.rmat(11, 16, seed=5)
+    dA = eng.upload(*A)
+    want = sort_rows(*oracle.csr_mul_csr(A[0], A[1], A[2], A[3], A[4], A[2], A[3], A[4]))
+    _, st = eng.CSR_MUL_CSR_DEV(dA, dA, download=False)
+    assert st["num_bin_rows"][3] > 0 and st["num_bin_rows"][4] > 0 and st["num_bin_rows"][5] > 0
+    k = eng.CSRtoCOO(dA)
+    c, _ = eng.COO_MUL_COO_DEV(k, k)
+    got = eng.download_coo(c)
+    assert np.array_equal(got["row_offset"], want[0]) and np.array_equal(got["col_ind"], want[1])
+    assert np.allclose(got["values"], want[2], rtol=1e-12, atol=0)
+    eng.free_coo(c); eng.free_coo(k)
+    e = eng.CSRtoELL(dA, gate=1e9)                       # the 20x gate would refuse a power-law operand
+    assert e.choice
+    c, _ = eng.ELL_MUL_ELL_DEV(e, e)
+    got = eng.download_ell(c)
+    assert np.array_equal(got["nnz_row"], np.diff(want[0]))
+    for i in range(0, A[0], 37):
+        n = int(got["nnz_row"][i]); s = int(want[0][i])
+        assert np.array_equal(got["col_ind"][i, :n], want[1][s:s + n])
+        assert np.allclose(got["values"][i, :n], want[2][s:s + n], rtol=1e-12, atol=0)
+    eng.free_ell(c); eng.free_ell(e); dA.close()
