@@ -340,25 +340,37 @@ def test_matrix_market_writer_roundtrip(eng, oracle, tmp_path):
 
 def test_ell_and_coo_views_through_every_bin(eng, oracle):
     """The CTA / global kernels are templated on the operand view: run them on ELL (fixed width) and COO
-    (64-bit row offsets) operands of a skewed matrix that populates every bin."""
-    A = W.rmat(11, 16, seed=5)
-    dA = eng.upload(*A)
-    want = sort_rows(*oracle.csr_mul_csr(A[0], A[1], A[2], A[3], A[4], A[2], A[3], A[4]))
-    _, st = eng.CSR_MUL_CSR_DEV(dA, dA, download=False)
-    assert st["num_bin_rows"][3] > 0 and st["num_bin_rows"][4] > 0 and st["num_bin_rows"][5] > 0
-    k = eng.CSRtoCOO(dA)
-    c, _ = eng.COO_MUL_COO_DEV(k, k)
-    got = eng.download_coo(c)
-    assert np.array_equal(got["row_offset"], want[0]) and np.array_equal(got["col_ind"], want[1])
-    assert np.allclose(got["values"], want[2], rtol=1e-12, atol=0)
-    eng.free_coo(c); eng.free_coo(k)
-    e = eng.CSRtoELL(dA, gate=1e9)                       # the 20x gate would refuse a power-law operand
-    assert e.choice
-    c, _ = eng.ELL_MUL_ELL_DEV(e, e)
-    got = eng.download_ell(c)
-    assert np.array_equal(got["nnz_row"], np.diff(want[0]))
-    for i in range(0, A[0], 37):
-        n = int(got["nnz_row"][i]); s = int(want[0][i])
-        assert np.array_equal(got["col_ind"][i, :n], want[1][s:s + n])
-        assert np.allclose(got["values"][i, :n], want[2][s:s + n], rtol=1e-12, atol=0)
-    eng.free_ell(c); eng.free_ell(e); dA.close()
+    (64-bit row offsets) operands that populate the CTA bins (R-MAT scale 13) and the global bin (a dense-ish
+    rectangular product)."""
+    cases = [(W.rmat(13, 16, seed=5), None, (3, 4)),
+             (W.random_sparse(40, 300, 0.9, seed=3), W.random_sparse(300, 40000, 0.4, seed=4), (5,))]
+    for A, B, bins in cases:
+        B = A if B is None else B
+        dA = eng.upload(*A)
+        dB = dA if B is A else eng.upload(*B)
+        want = sort_rows(*oracle.csr_mul_csr(A[0], B[1], A[2], A[3], A[4], B[2], B[3], B[4]))
+        _, st = eng.CSR_MUL_CSR_DEV(dA, dB, download=False)
+        assert all(st["num_bin_rows"][b] > 0 for b in bins), st["num_bin_rows"]
+        ka = eng.CSRtoCOO(dA)
+        kb = ka if B is A else eng.CSRtoCOO(dB)
+        c, _ = eng.COO_MUL_COO_DEV(ka, kb)
+        got = eng.download_coo(c)
+        assert np.array_equal(got["row_offset"], want[0]) and np.array_equal(got["col_ind"], want[1])
+        assert np.allclose(got["values"], want[2], rtol=1e-12, atol=0)
+        eng.free_coo(c); eng.free_coo(ka)
+        if B is not A:
+            eng.free_coo(kb)
+        ea = eng.CSRtoELL(dA, gate=1e9)                  # the 20x gate would refuse a power-law operand
+        eb = ea if B is A else eng.CSRtoELL(dB, gate=1e9)
+        assert ea.choice and eb.choice
+        c, _ = eng.ELL_MUL_ELL_DEV(ea, eb)
+        got = eng.download_ell(c)
+        assert np.array_equal(got["nnz_row"], np.diff(want[0]))
+        for i in range(0, A[0], 37):
+            n = int(got["nnz_row"][i]); s0 = int(want[0][i])
+            assert np.array_equal(got["col_ind"][i, :n], want[1][s0:s0 + n])
+            assert np.allclose(got["values"][i, :n], want[2][s0:s0 + n], rtol=1e-12, atol=0)
+        eng.free_ell(c); eng.free_ell(ea)
+        if B is not A:
+            eng.free_ell(eb); dB.close()
+        dA.close()
