@@ -106,16 +106,20 @@ int ias_upload_csr(const IasCsrMatrix *h, IasCsrMatrixDev *d)
     IAS_TRY(ensure_init());
     if (!h || !d || h->row < 0 || h->nnz < 0) return fail(IAS_E_ARG, "ias_upload_csr: bad argument");
     d->choice = true; d->row = h->row; d->col = h->col; d->nnz = h->nnz;
-    IAS_TRY(dalloc(&d->row_ind_dev, (size_t)h->row + 1));
-    IAS_TRY(dalloc(&d->col_ind_dev, (size_t)h->nnz));
-    IAS_TRY(dalloc(&d->values_dev, (size_t)h->nnz));
+    d->row_ind_dev = nullptr; d->col_ind_dev = nullptr; d->values_dev = nullptr;
+    DBuf<int> rp, ci;                                  // released automatically if a later step fails
+    DBuf<double> v;
+    IAS_TRY(rp.alloc((size_t)h->row + 1));
+    IAS_TRY(ci.alloc((size_t)h->nnz));
+    IAS_TRY(v.alloc((size_t)h->nnz));
     cudaStream_t s = ctx().stream;
-    IAS_CUDA(cudaMemcpyAsync(d->row_ind_dev, h->row_ind, sizeof(int) * ((size_t)h->row + 1), cudaMemcpyHostToDevice, s));
+    IAS_CUDA(cudaMemcpyAsync(rp.p, h->row_ind, sizeof(int) * ((size_t)h->row + 1), cudaMemcpyHostToDevice, s));
     if (h->nnz) {
-        IAS_CUDA(cudaMemcpyAsync(d->col_ind_dev, h->col_ind, sizeof(int) * (size_t)h->nnz, cudaMemcpyHostToDevice, s));
-        IAS_CUDA(cudaMemcpyAsync(d->values_dev, h->values, sizeof(double) * (size_t)h->nnz, cudaMemcpyHostToDevice, s));
+        IAS_CUDA(cudaMemcpyAsync(ci.p, h->col_ind, sizeof(int) * (size_t)h->nnz, cudaMemcpyHostToDevice, s));
+        IAS_CUDA(cudaMemcpyAsync(v.p, h->values, sizeof(double) * (size_t)h->nnz, cudaMemcpyHostToDevice, s));
     }
     IAS_CUDA(cudaStreamSynchronize(s));
+    d->row_ind_dev = rp.release(); d->col_ind_dev = ci.release(); d->values_dev = v.release();
     return IAS_OK;
 }
 

@@ -1,6 +1,8 @@
 // csr_api.cu -- C ABI of the CSR hot path (Algorithm 2 and the library calls it replaces).
 #include <stdlib.h>
 
+#include <vector>
+
 #include "spgemm_host.cuh"
 
 using namespace ias;
@@ -113,9 +115,9 @@ int ias_csr_mul_csr_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, i
     IAS_TRY(nb.alloc(1));
     IAS_LAUNCH(k_batch_bounds, 1, 1, 0, nrows, rp.p, cap, MAXB, bounds.p, nb.p);
     int h_nb = 0;
-    static int h_bounds[MAXB + 1];
+    std::vector<int> h_bounds(MAXB + 1, 0);
     IAS_CUDA(cudaMemcpyAsync(&h_nb, nb.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
-    IAS_CUDA(cudaMemcpyAsync(h_bounds, bounds.p, sizeof(int) * (MAXB + 1), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaMemcpyAsync(h_bounds.data(), bounds.p, sizeof(int) * (MAXB + 1), cudaMemcpyDeviceToHost, c.stream));
     IAS_CUDA(cudaStreamSynchronize(c.stream));
     if (h_nb < 0) return fail(IAS_E_NOMEM, "streaming budget of %zu bytes needs more than %d batches", budget_bytes, MAXB);
 
