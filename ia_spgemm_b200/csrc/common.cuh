@@ -9,7 +9,19 @@
 
 namespace ias {
 
+// knobs of the kernel selection (ias_set_option / IAS_OPT_<NAME> in the environment at ias_init)
+struct Tuning {
+    long long global_rows_smem = 1;   // 1: windowed shared-memory kernels for global rows (canonical B), 0: L2 bitmap kernels
+    long long gwin_swords = 8192;     // numeric: bitmap words per super-window (x32 columns)
+    long long gwin_win = 0;           // numeric: entries per rank window (0: whatever shared memory is left)
+    long long gwin_sym_swords = 0;    // symbolic: bitmap words per super-window (0: as many as fit)
+    long long gwin_smem_kb = 0;       // cap on the dynamic shared memory of the windowed kernels (0: device limit)
+    long long gwin_max_sw = 4;        // numeric: use the windowed kernel up to this many super-windows per row (0: always);
+                                      // beyond, the per-window scans of the cells cost more than the L2 lookups they replace
+};
+
 struct Ctx {
+    Tuning tune;
     bool ready = false;
     int device = 0;
     int sm_count = 148;

@@ -43,6 +43,19 @@ const char *ias_version(void) { return "ia-spgemm-b200 0.1 (sm_100a)"; }
 const char *ias_last_error(void) { return ctx().err; }
 long long ias_kernel_launches(void) { return ctx().launches; }
 
+static long long *option_slot(const char *name)
+{
+    Tuning &t = ctx().tune;
+    if (!name) return nullptr;
+    if (!strcmp(name, "global_rows_smem")) return &t.global_rows_smem;
+    if (!strcmp(name, "gwin_swords")) return &t.gwin_swords;
+    if (!strcmp(name, "gwin_win")) return &t.gwin_win;
+    if (!strcmp(name, "gwin_sym_swords")) return &t.gwin_sym_swords;
+    if (!strcmp(name, "gwin_smem_kb")) return &t.gwin_smem_kb;
+    if (!strcmp(name, "gwin_max_sw")) return &t.gwin_max_sw;
+    return nullptr;
+}
+
 int ias_init(int device)
 {
     Ctx &c = ctx();
@@ -70,7 +83,33 @@ int ias_init(int device)
     for (int i = 0; i < 32; ++i)
         if (!c.ev_bin[i]) IAS_CUDA(cudaEventCreate(&c.ev_bin[i]));
     if (!c.h_scalars) IAS_CUDA(cudaMallocHost((void **)&c.h_scalars, 64 * sizeof(long long)));
+    static const char *const names[] = {"global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw"};
+    for (const char *n : names) {                  // IAS_OPT_GWIN_WIN=4096 etc.
+        char env[64] = "IAS_OPT_";
+        size_t k = strlen(env);
+        for (const char *q = n; *q && k + 1 < sizeof env; ++q) env[k++] = (char)(*q >= 'a' && *q <= 'z' ? *q - 32 : *q);
+        env[k] = 0;
+        const char *v = getenv(env);
+        if (v && *v) *option_slot(n) = atoll(v);
+    }
     c.ready = true;
+    return IAS_OK;
+}
+
+int ias_set_option(const char *name, long long value)
+{
+    long long *slot = option_slot(name);
+    if (!slot) return fail(IAS_E_ARG, "unknown option '%s'", name ? name : "(null)");
+    if (value < 0) return fail(IAS_E_ARG, "option '%s' must not be negative", name);
+    *slot = value;
+    return IAS_OK;
+}
+
+int ias_get_option(const char *name, long long *value)
+{
+    long long *slot = option_slot(name);
+    if (!slot || !value) return fail(IAS_E_ARG, "unknown option '%s'", name ? name : "(null)");
+    *value = *slot;
     return IAS_OK;
 }
 

@@ -129,6 +129,65 @@ inline int ensure_gwork(RangeWork &rw, int ncols, long long nrows_g, bool one_pe
     return IAS_OK;
 }
 
+// Windowed shared-memory kernels for global rows (k_sym_gwin / k_num_gwin): one persistent 1024-thread CTA per SM
+// (more when the bitmap is small), dynamic shared memory = everything the static tile leaves.
+constexpr int GW_BLOCK = 1024;
+
+inline bool use_gwin(const RangeWork &rw) { return rw.b_canonical && ctx().tune.global_rows_smem != 0; }
+
+template <class K>
+inline int gwin_dyn_max(K kernel, size_t *out)
+{
+    cudaFuncAttributes fa;
+    IAS_CUDA(cudaFuncGetAttributes(&fa, kernel));
+    size_t lim = ctx().smem_optin;
+    if (fa.sharedSizeBytes + 4096 > lim) return fail(IAS_E_CUDA, "windowed global-row kernel: static shared memory %zu leaves no room", fa.sharedSizeBytes);
+    size_t dyn = lim - fa.sharedSizeBytes - 256;
+    if (ctx().tune.gwin_smem_kb > 0) dyn = std::min(dyn, (size_t)ctx().tune.gwin_smem_kb * 1024);
+    *out = dyn;
+    return IAS_OK;
+}
+
+template <class K>
+inline int gwin_grid(K kernel, size_t smem, long long nrows_g, int *grid)
+{
+    int occ = 1;
+    IAS_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, GW_BLOCK, smem));
+    if (occ < 1) return fail(IAS_E_CUDA, "windowed global-row kernel does not fit an SM with %zu bytes of shared memory", smem);
+    *grid = (int)std::min<long long>(nrows_g, (long long)occ * ctx().sm_count);
+    return IAS_OK;
+}
+
+#ifdef IAS_GWIN_PROFILE
+// phase clocks of the windowed kernels since the last dump (stderr), in SM clocks summed over CTAs
+inline void gwin_profile_dump(const char *what)
+{
+    unsigned long long h[32];
+    cudaStreamSynchronize(ctx().stream);
+    if (cudaMemcpyFromSymbol(h, g_gwin_prof, sizeof h) != cudaSuccess) return;
+    fprintf(stderr, "[gwin %s]", what);
+    for (int i = 0; i < 32; ++i) fprintf(stderr, " %d:%llu", i, h[i]);
+    fprintf(stderr, "\n");
+    memset(h, 0, sizeof h);
+    cudaMemcpyToSymbol(g_gwin_prof, h, sizeof h);
+}
+#define GWIN_PROFILE_DUMP(what) gwin_profile_dump(what)
+#else
+#define GWIN_PROFILE_DUMP(what) do {} while (0)
+#endif
+
+inline int words_of(int ncols) { return (int)((((long long)ncols + 31) / 32 + 31) / 32 * 32); }
+
+// numeric: every (row, super-window) pair costs a few passes over the window's cells whatever it holds, so the
+// windowed kernel wins while rows need few super-windows (R-MAT scale <= 20 at the default 8192 words) and loses
+// to the L2 bitmap kernel beyond (measured at scale 22: 16 super-windows per row, 4.6 s against 3.7 s)
+inline bool gwin_numeric_pays(int ncols)
+{
+    long long sw = ctx().tune.gwin_swords > 0 ? std::max<long long>(32, (ctx().tune.gwin_swords + 31) & ~31LL) : 8192;
+    long long nsw = (words_of(ncols) + sw - 1) / sw;
+    return ctx().tune.gwin_max_sw == 0 || nsw <= ctx().tune.gwin_max_sw;
+}
+
 // analysis + symbolic over [r0, r1): fills rw.ub, rw.nnz_row (exact nnz(C_i)), products
 template <class AV, class BV>
 int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double avg_a_row, RangeWork &rw, IasSpgemmStats *st,
@@ -243,7 +302,25 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
         IAS_BIN_END(BIN_B2);
         rw.sym_timed[BIN_B2] = true;
     }
-    if (bl.count[BIN_G]) {
+    if (bl.count[BIN_G] && use_gwin(rw)) {
+        IAS_BIN_BEGIN(BIN_G);
+        int n = (int)bl.count[BIN_G];
+        auto k = k_sym_gwin<AV, BV, GW_BLOCK>;
+        size_t dyn = 0;
+        IAS_TRY(gwin_dyn_max(k, &dyn));
+        int swords = std::min(words_of(ncols_b), (int)(dyn / 4) & ~31);
+        if (c.tune.gwin_sym_swords > 0) swords = std::min<long long>(swords, std::max<long long>(32, (c.tune.gwin_sym_swords + 31) & ~31LL));
+        size_t sm = (size_t)swords * 4;
+        IAS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   // static + dynamic may exceed 48 KB
+        int grid = 1;
+        IAS_TRY(gwin_grid(k, sm, n, &grid));
+        if (!rw.cursor.p) IAS_TRY(rw.cursor.alloc(1));
+        IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
+        IAS_LAUNCH(k, grid, GW_BLOCK, sm, bl.rows_of(BIN_G), n, r0, A, B, rw.nnz_row.p, rw.cursor.p, ncols_b, swords);
+        IAS_BIN_END(BIN_G);
+        GWIN_PROFILE_DUMP("sym");
+        rw.sym_timed[BIN_G] = true;
+    } else if (bl.count[BIN_G]) {
         IAS_BIN_BEGIN(BIN_G);
         int n = (int)bl.count[BIN_G];
         IAS_TRY(ensure_gwork(rw, ncols_b, n));
@@ -349,7 +426,31 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         IAS_BIN_END(8 + BIN_B2);
         rw.num_timed[BIN_B2] = true;
     }
-    if (bl.count[BIN_G]) {
+    if (bl.count[BIN_G] && use_gwin(rw) && gwin_numeric_pays(ncols_b)) {
+        IAS_BIN_BEGIN(8 + BIN_G);
+        int m = (int)bl.count[BIN_G];
+        auto k = k_num_gwin<AV, BV, GW_BLOCK>;
+        size_t dyn = 0;
+        IAS_TRY(gwin_dyn_max(k, &dyn));
+        // {bitmap, rank} cells of a super-window (8 B per 32 columns) + rank window (8 B sum + 4 B column per entry)
+        long long sw_cap = c.tune.gwin_swords > 0 ? std::max<long long>(32, (c.tune.gwin_swords + 31) & ~31LL) : 8192;
+        sw_cap = std::min<long long>(sw_cap, (long long)((dyn / 2) / 8) & ~31LL);
+        int swords = (int)std::min<long long>(words_of(ncols_b), sw_cap);
+        // split-point table (one int per A entry and super-window boundary) only when there are several super-windows
+        int tbl_cap = words_of(ncols_b) > swords ? 4096 : 0;
+        int win = (int)((dyn - (size_t)swords * 8 - (size_t)tbl_cap * 4) / 12) & ~31;
+        if (c.tune.gwin_win > 0) win = (int)std::min<long long>(win, std::max<long long>(32, c.tune.gwin_win & ~31LL));
+        size_t sm = (size_t)swords * 8 + (size_t)win * 12 + (size_t)tbl_cap * 4;
+        IAS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+        int grid = 1;
+        IAS_TRY(gwin_grid(k, sm, m, &grid));
+        if (!rw.cursor.p) IAS_TRY(rw.cursor.alloc(1));
+        IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
+        IAS_LAUNCH(k, grid, GW_BLOCK, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.cursor.p, ncols_b, swords, win, tbl_cap);
+        IAS_BIN_END(8 + BIN_G);
+        GWIN_PROFILE_DUMP("num");
+        rw.num_timed[BIN_G] = true;
+    } else if (bl.count[BIN_G]) {
         IAS_BIN_BEGIN(8 + BIN_G);
         int m = (int)bl.count[BIN_G];
         IAS_TRY(ensure_gwork(rw, ncols_b, m, true));

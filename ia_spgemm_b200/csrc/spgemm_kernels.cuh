@@ -578,7 +578,7 @@ struct ColumnWindow {
     __device__ __forceinline__ void operator()(typename BV::off_t &qb, int &len) const
     {
         if (len == 0) return;
-        typename BV::off_t s = lower(qb, len, c_lo);
+        typename BV::off_t s = c_lo > 0 ? lower(qb, len, c_lo) : qb;
         typename BV::off_t e = c_hi == 0x7fffffff ? qb + len : lower(qb, len, c_hi);
         qb = s; len = (int)(e - s);
     }
@@ -1119,6 +1119,501 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
         // 4. leave the slot clean for the next row
         g_clear<BLOCK>(wp, summary, wsum, L);
         __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- global rows, windowed in shared memory
+// The L2 variant above pays one L2 transaction per product and pass (ncu: 31 % issue, DRAM 3 %, L2-latency
+// bound at ~100 G products/s).  A microbenchmark on B200 (tools/ubench/smem_atomics.cu) gives 7.4 lanes/clk/SM
+// for random ATOMS.OR / LDS and 1.9 lanes/clk/SM for the fp64 atomicAdd CAS loop in shared memory, i.e.
+// 2.2 T and 0.55 T products/s for the chip, so every per-product random access of these kernels goes to
+// shared memory.  Needs canonical B (strictly increasing columns per row): the column space is cut into
+// super-windows of 32*swords columns, and only the part of each B row inside the current window is visited.
+//   symbolic: bitmap of the super-window in shared memory (up to 1.5 M columns), popcount, clear.
+//   numeric:  {bitmap word, rank of its first bit} cells of the super-window in shared memory; mark, warp-scan
+//             the populations, then rank windows of at most `win` entries: sorted columns staged in scol[],
+//             products added into acc[] (fp64, indexed by rank), both written out once, coalesced.
+// A restricted visit needs two lower bounds per A entry: rows with few A entries (the common case, ~70 at
+// R-MAT scale 22) let a whole warp search one B row with 32 probes per step (3 dependent loads instead of 11
+// for a 2 000-entry row); longer A rows search one entry per thread.
+
+// optional phase clocks (make prof): thread 0 of every CTA adds up clock64 deltas per phase
+#ifdef IAS_GWIN_PROFILE
+static __device__ unsigned long long g_gwin_prof[32];
+#define GP_START() long long gp_t = clock64()
+#define GP_ADD(slot)                                                                           \
+    do {                                                                                       \
+        if (threadIdx.x == 0) {                                                                \
+            long long gp_n = clock64();                                                        \
+            atomicAdd(&g_gwin_prof[slot], (unsigned long long)(gp_n - gp_t));                  \
+            gp_t = gp_n;                                                                       \
+        }                                                                                      \
+    } while (0)
+#define GP_CNT(slot, v)                                                                        \
+    do {                                                                                       \
+        if (threadIdx.x == 0) atomicAdd(&g_gwin_prof[slot], (unsigned long long)(v));          \
+    } while (0)
+#else
+#define GP_START() do {} while (0)
+#define GP_ADD(slot) do {} while (0)
+#define GP_CNT(slot, v) do {} while (0)
+#endif
+
+__device__ __forceinline__ bool use_tbl_probe(bool single_tile, int nsw, int n_a, int tstride, int tbl_cap)
+{
+    return single_tile && nsw > 1 && (long long)n_a * tstride <= tbl_cap;
+}
+
+// first index in ci[0, len) whose column is >= c; all 32 lanes call with the same arguments
+__device__ __forceinline__ int warp_lower_bound(const int *__restrict__ ci, int len, int c, int lane)
+{
+    int lo = 0, hi = len;
+    while (lo < hi) {
+        const int step = (hi - lo) / 33 + 1;
+        const int pos = lo + (lane + 1) * step - 1;
+        const bool less = pos < hi && __ldg(ci + pos) < c;
+        const int cnt = __popc(__ballot_sync(0xffffffffu, less));     // sorted: the first cnt probes are smaller
+        const int nlo = lo + cnt * step;
+        hi = min(hi, nlo + step - 1);
+        lo = nlo;
+    }
+    return lo;
+}
+
+constexpr int GWIN_COOP_MAX = 128;    // A-row tiles of at most this many entries use the warp-wide search
+
+// restrict every thread's B row (qb, len) of a tile with n_in entries to columns [c_lo, c_hi)
+template <int BLOCK, class BV>
+__device__ __forceinline__ void gwin_restrict(const BV &B, int n_in, typename BV::off_t &qb, int &len,
+                                              CtaTile<BV, BLOCK> &tile, int c_lo, int c_hi)
+{
+    typedef typename BV::off_t boff;
+    constexpr int NWARPS = BLOCK / 32;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    if (c_lo <= 0 && c_hi == 0x7fffffff) return;
+    if (n_in <= GWIN_COOP_MAX) {
+        tile.rel[tid] = qb;
+        tile.incl[tid] = len;
+        __syncthreads();
+        for (int e = wid; e < n_in; e += NWARPS) {
+            const boff b = tile.rel[e];
+            const int l = tile.incl[e];
+            const int s = c_lo > 0 ? warp_lower_bound(B.ci + b, l, c_lo, lane) : 0;
+            const int t = c_hi != 0x7fffffff ? s + warp_lower_bound(B.ci + b + s, l - s, c_hi, lane) : l;
+            __syncwarp();
+            if (lane == 0) { tile.rel[e] = b + s; tile.incl[e] = t - s; }
+        }
+        __syncthreads();
+        qb = tile.rel[tid];
+        len = tile.incl[tid];
+        __syncthreads();
+    } else {
+        ColumnWindow<BV>{B, c_lo, c_hi}(qb, len);
+    }
+}
+
+// scan the tile's segment lengths; leaves the tile in shared memory (ends with a barrier), returns its product count
+template <bool NEED_VALUES, int BLOCK, class BV>
+__device__ __forceinline__ int gwin_scan(CtaTile<BV, BLOCK> &tile, typename BV::off_t qb, int len, double av)
+{
+    typedef typename BV::off_t boff;
+    const int tid = threadIdx.x;
+    int incl;
+    typename CtaTile<BV, BLOCK>::Scan(tile.scan).InclusiveSum(len, incl);
+    tile.incl[tid] = incl;
+    tile.rel[tid] = qb - (boff)(incl - len);
+    if (NEED_VALUES) tile.av[tid] = av;
+    __syncthreads();
+    return tile.incl[BLOCK - 1];
+}
+
+// entry `base + tid` of the A row: B row start, length, A value
+template <bool NEED_VALUES, class AV, class BV>
+__device__ __forceinline__ void gwin_load(const AV &A, const BV &B, typename AV::off_t base, typename AV::off_t pe,
+                                          typename BV::off_t &qb, int &len, double &av)
+{
+    typename AV::off_t p = base + threadIdx.x;
+    len = 0; qb = 0; av = 0.0;
+    if (p < pe) {
+        int j = __ldg(A.ci + p);
+        qb = B.begin(j);
+        len = (int)(B.end(j) - qb);
+        if (NEED_VALUES) av = __ldg(A.v + p);
+    }
+}
+
+// one tile of BLOCK A entries starting at `base`, B rows restricted to columns [c_lo, c_hi)
+template <bool NEED_VALUES, int BLOCK, class AV, class BV>
+__device__ __forceinline__ int gwin_build(const AV &A, const BV &B, typename AV::off_t base, typename AV::off_t pe,
+                                          CtaTile<BV, BLOCK> &tile, int c_lo, int c_hi)
+{
+    typename BV::off_t qb;
+    int len;
+    double av;
+    gwin_load<NEED_VALUES>(A, B, base, pe, qb, len, av);
+    gwin_restrict<BLOCK>(B, (int)min((typename AV::off_t)BLOCK, pe - base), qb, len, tile, c_lo, c_hi);
+    return gwin_scan<NEED_VALUES, BLOCK>(tile, qb, len, av);
+}
+
+// the products of a built tile, dealt out evenly to the warps (same scheme as cta_products); no barrier.
+// A trip of 32*PB products that lies inside one B-row segment (the common case on hub-heavy rows) takes its
+// offsets from one broadcast read instead of searching the tile per product.
+template <bool NEED_VALUES, int BLOCK, class BV, class F>
+__device__ __forceinline__ void gwin_run(const CtaTile<BV, BLOCK> &tile, int total, F &&f)
+{
+    constexpr int NWARPS = BLOCK / 32;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int share = ((total + NWARPS - 1) / NWARPS + 31) & ~31;
+    const int t_begin = wid * share, t_end = min(total, t_begin + share);
+    if (t_begin >= t_end) return;
+    int lo = 0, hi = BLOCK - 1;                    // smallest entry whose inclusive count exceeds t_begin
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (tile.incl[mid] <= t_begin) lo = mid + 1; else hi = mid; }
+    int e = lo;
+    for (int t0 = t_begin; t0 < t_end; t0 += 32 * PB) {
+        typename BV::off_t q[PB];
+        double pav[PB];
+        unsigned valid = 0;
+        while (tile.incl[e] <= t0) ++e;            // warp-uniform: the entry that owns product t0
+        const int trip_end = min(t_end, t0 + 32 * PB);
+        if (tile.incl[e] >= trip_end) {
+            const typename BV::off_t r = tile.rel[e] + t0 + lane;
+            const double a = NEED_VALUES ? tile.av[e] : 0.0;
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                q[u] = r + 32 * u;
+                pav[u] = a;
+                if (t0 + 32 * u + lane < trip_end) valid |= 1u << u;
+            }
+            f(q, pav, valid);
+        } else {
+            int me = e;
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                int t = t0 + 32 * u + lane;
+                q[u] = 0; pav[u] = 0.0;
+                if (t < t_end) {
+                    while (tile.incl[me] <= t) ++me;
+                    q[u] = tile.rel[me] + t;
+                    if (NEED_VALUES) pav[u] = tile.av[me];
+                    valid |= 1u << u;
+                }
+            }
+            f(q, pav, valid);
+            e = __shfl_sync(0xffffffffu, me, 31);
+        }
+    }
+}
+
+template <class AV, class BV, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_sym_gwin(const int *__restrict__ rows, int nrows, int r0, AV A, BV B,
+                                                    int *__restrict__ nnz_row, int *__restrict__ cursor, int ncols, int swords)
+{
+    typedef typename AV::off_t aoff;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    unsigned *bits = reinterpret_cast<unsigned *>(smem_raw);      // swords words, all zero between rows
+    __shared__ int s_row, s_cnt;
+    __shared__ CtaTile<BV, BLOCK> tile;
+    const int tid = threadIdx.x, lane = tid & 31;
+    for (int w = tid; w < swords; w += BLOCK) bits[w] = 0;
+    const long long span = (long long)swords * 32;
+    while (true) {
+        if (tid == 0) { s_row = atomicAdd(cursor, 1); s_cnt = 0; }
+        __syncthreads();
+        const int idx = s_row;
+        if (idx >= nrows) break;
+        const int li = rows ? rows[idx] : idx;
+        const int i = r0 + li;
+        const aoff pa = A.begin(i), pe = A.end(i);
+        int cnt = 0;
+        GP_START();
+        GP_CNT(24, 1);
+        for (long long sw_lo = 0; sw_lo < ncols; sw_lo += span) {
+            const int c_lo = (int)sw_lo;
+            const int c_hi = sw_lo + span >= ncols ? 0x7fffffff : (int)(sw_lo + span);
+            bool any = false;
+            for (aoff base = pa; base < pe; base += BLOCK) {
+                const int total = gwin_build<false, BLOCK>(A, B, base, pe, tile, c_lo, c_hi);
+                GP_ADD(25);
+                if (total) {
+                    any = true;
+                    gwin_run<false, BLOCK>(tile, total, [&](const typename BV::off_t (&q)[PB], const double (&)[PB], unsigned valid) {
+                        int k[PB];
+                        unsigned cur[PB];
+#pragma unroll
+                        for (int u = 0; u < PB; ++u) k[u] = (valid >> u) & 1u ? __ldg(B.ci + q[u]) - c_lo : -1;
+#pragma unroll
+                        for (int u = 0; u < PB; ++u) cur[u] = k[u] >= 0 ? bits[k[u] >> 5] : 0xffffffffu;
+#pragma unroll
+                        for (int u = 0; u < PB; ++u) {
+                            const unsigned bit = 1u << (k[u] & 31);
+                            if (!(cur[u] & bit)) atomicOr(&bits[k[u] >> 5], bit);
+                        }
+                    });
+                }
+                __syncthreads();
+                GP_ADD(26);
+            }
+            if (any) {
+                const int nw = (int)min((long long)swords, ((long long)ncols - sw_lo + 31) / 32);
+                for (int w = tid; w < nw; w += BLOCK) {
+                    const unsigned b = bits[w];
+                    if (b) { cnt += __popc(b); bits[w] = 0; }
+                }
+                __syncthreads();
+                GP_ADD(27);
+            }
+        }
+        cnt = warp_sum(cnt);
+        if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+        __syncthreads();
+        if (tid == 0) nnz_row[li] = s_cnt;
+    }
+}
+
+template <class AV, class BV, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_num_gwin(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
+                                                    int *__restrict__ c_ci, double *__restrict__ c_v, int *__restrict__ cursor,
+                                                    int ncols, int swords, int win, int tbl_cap)
+{
+    typedef typename AV::off_t aoff;
+    typedef typename BV::off_t boff;
+    constexpr int NWARPS = BLOCK / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint2 *cells = reinterpret_cast<uint2 *>(smem_raw);                               // swords x {bits, rank}
+    double *acc = reinterpret_cast<double *>(smem_raw + (size_t)swords * 8);         // win partial sums, zero between windows
+    int *scol = reinterpret_cast<int *>(smem_raw + (size_t)swords * 8 + (size_t)win * 8);   // win sorted columns
+    int *tbl = scol + win;                                                            // tbl_cap split points (see below)
+    __shared__ int s_row;
+    __shared__ int s_wtot[32], s_wbase[33];
+    __shared__ CtaTile<BV, BLOCK> tile;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    for (int w = tid; w < swords; w += BLOCK) cells[w] = make_uint2(0u, 0u);
+    for (int t = tid; t < win; t += BLOCK) acc[t] = 0.0;
+    const long long span = (long long)swords * 32;
+    const int nsw = (int)((ncols + span - 1) / span);
+    const int tstride = (nsw + 1) | 1;                 // odd stride: thread e reads tbl[e * tstride + k] without bank conflicts
+    while (true) {
+        if (tid == 0) s_row = atomicAdd(cursor, 1);
+        __syncthreads();
+        const int idx = s_row;
+        if (idx >= nrows) break;
+        const int li = rows ? rows[idx] : idx;
+        const int i = r0 + li;
+        const long long gs = out.start(li);
+        const aoff pa = A.begin(i), pe = A.end(i);
+        const int n_a = (int)min((aoff)0x7fffffff, pe - pa);
+        const bool single_tile = pe - pa <= (aoff)BLOCK;
+        int emitted = 0;
+        GP_START();
+        GP_CNT(8, 1);
+        if (!single_tile) GP_CNT(20, 1);
+        if (use_tbl_probe(single_tile, nsw, n_a, tstride, tbl_cap)) GP_CNT(21, 1);
+        // A rows of at most BLOCK entries (nearly all of them): thread e owns entry e for the whole row, and the
+        // positions where its B row crosses the super-window boundaries are found once, all in parallel (one
+        // latency chain per row instead of one per window): tbl[e][k] = first index of B row e with column >= k*span.
+        boff my_qb = 0;
+        int my_len = 0;
+        double my_av = 0.0;
+        const bool use_tbl = single_tile && nsw > 1 && (long long)n_a * tstride <= tbl_cap;
+        if (single_tile) gwin_load<true>(A, B, pa, pe, my_qb, my_len, my_av);
+        if (use_tbl) {
+            tile.rel[tid] = my_qb;
+            tile.incl[tid] = my_len;
+            __syncthreads();
+            const int items = n_a * (nsw - 1);
+            for (int it = tid; it < items; it += BLOCK) {
+                const int e = it / (nsw - 1), k = it - e * (nsw - 1) + 1;
+                const boff b = tile.rel[e];
+                const int l = tile.incl[e];
+                const int c = (int)(k * span);
+                int lo = 0, hi = l;
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(B.ci + b + mid) < c) lo = mid + 1; else hi = mid; }
+                tbl[e * tstride + k] = lo;
+            }
+            if (tid < n_a) { tbl[tid * tstride] = 0; tbl[tid * tstride + nsw] = my_len; }
+            __syncthreads();
+            GP_ADD(13);
+        }
+        for (int k = 0; k < nsw; ++k) {
+            const long long sw_lo = k * span;
+            const int c_lo = (int)sw_lo;
+            const int c_hi = k + 1 == nsw ? 0x7fffffff : (int)(sw_lo + span);
+            const int nw = (int)min((long long)swords, ((long long)ncols - sw_lo + 31) / 32);
+            // this thread's B-row segment inside the super-window (single_tile only)
+            boff sw_qb = my_qb;
+            int sw_len = my_len;
+            // 1. mark the columns of this super-window (the tile of a short A row is kept for step 3)
+            bool any = false;
+            int tile_total = 0;
+            if (single_tile) {
+                if (use_tbl) {
+                    const int o0 = tid < n_a ? tbl[tid * tstride + k] : 0, o1 = tid < n_a ? tbl[tid * tstride + k + 1] : 0;
+                    sw_qb = my_qb + o0;
+                    sw_len = o1 - o0;
+                } else {
+                    gwin_restrict<BLOCK>(B, n_a, sw_qb, sw_len, tile, c_lo, c_hi);
+                }
+                tile_total = gwin_scan<true, BLOCK>(tile, sw_qb, sw_len, my_av);
+            }
+            auto mark = [&](const boff (&q)[PB], const double (&)[PB], unsigned valid) {
+                int kk[PB];
+                unsigned cur[PB];
+#pragma unroll
+                for (int u = 0; u < PB; ++u) kk[u] = (valid >> u) & 1u ? __ldg(B.ci + q[u]) - c_lo : -1;
+#pragma unroll
+                for (int u = 0; u < PB; ++u) cur[u] = kk[u] >= 0 ? cells[kk[u] >> 5].x : 0xffffffffu;
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    const unsigned bit = 1u << (kk[u] & 31);
+                    if (!(cur[u] & bit)) atomicOr(&cells[kk[u] >> 5].x, bit);
+                }
+            };
+            if (single_tile) {
+                GP_ADD(0);
+                if (tile_total) { any = true; gwin_run<false, BLOCK>(tile, tile_total, mark); }
+                __syncthreads();
+                GP_ADD(1);
+            } else {
+                for (aoff base = pa; base < pe; base += BLOCK) {
+                    const int total = gwin_build<false, BLOCK>(A, B, base, pe, tile, c_lo, c_hi);
+                    GP_ADD(17);
+                    GP_CNT(18, 1);
+                    if (total) { any = true; gwin_run<false, BLOCK>(tile, total, mark); }
+                    __syncthreads();
+                    GP_ADD(19);
+                }
+            }
+            if (!any) { GP_CNT(12, 1); continue; }
+            GP_CNT(9, 1);
+            // 2. rank of every word's first bit: each warp scans a contiguous chunk, then the chunk bases are added
+            const int chunk = ((nw + NWARPS - 1) / NWARPS + 31) & ~31;
+            const int w_begin = min(nw, wid * chunk), w_end = min(nw, w_begin + chunk);
+            {
+                int carry = 0;
+                for (int w0 = w_begin; w0 < w_end; w0 += 32) {
+                    const int w = w0 + lane;
+                    const int c = w < w_end ? __popc(cells[w].x) : 0;
+                    int incl = c;
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+                    if (w < w_end) cells[w].y = (unsigned)(carry + incl - c);
+                    carry += __shfl_sync(0xffffffffu, incl, 31);
+                }
+                if (lane == 0) s_wtot[wid] = carry;
+            }
+            __syncthreads();
+            if (wid == 0) {
+                const int v = lane < NWARPS ? s_wtot[lane] : 0;
+                int incl = v;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+                s_wbase[lane] = incl - v;
+                if (lane == 31) s_wbase[32] = incl;
+            }
+            __syncthreads();
+            {
+                const unsigned wb = (unsigned)s_wbase[wid];
+                if (wb)
+                    for (int w = w_begin + lane; w < w_end; w += 32) cells[w].y += wb;
+            }
+            const int sw_total = s_wbase[32];
+            __syncthreads();
+            GP_ADD(2);
+            // 3. rank windows: words [ws, we) hold at most `win` entries
+            int ws = 0;
+            while (ws < nw) {
+                const int base_rank = (int)cells[ws].y;
+                if (sw_total - base_rank == 0) break;
+                int we = nw;
+                if (sw_total - base_rank > win) {
+                    int lo = ws + 1, hi = nw - 1;          // a word holds at most 32 <= win entries: ws + 1 is always valid
+                    while (lo < hi) {
+                        const int mid = (lo + hi + 1) >> 1;
+                        if ((int)cells[mid].y - base_rank <= win) lo = mid; else hi = mid - 1;
+                    }
+                    we = lo;
+                }
+                const int wn = (we == nw ? sw_total : (int)cells[we].y) - base_rank;
+                // sorted columns of the window; every lane starts at another bit position so that dense words
+                // (rank stride 32) do not pile onto one bank
+                for (int w = ws + tid; w < we; w += BLOCK) {
+                    const uint2 c = cells[w];
+                    const int r = (int)c.y - base_rank;
+                    const int col0 = c_lo + w * 32;
+                    const unsigned himask = 0xffffffffu << lane;
+                    unsigned cur = c.x & himask;
+                    unsigned rest = c.x & ~himask;
+                    while (cur | rest) {
+                        if (!cur) { cur = rest; rest = 0; }
+                        const int q = __ffs(cur) - 1;
+                        cur &= cur - 1;
+                        scol[r + __popc(c.x & ((1u << q) - 1u))] = col0 + q;
+                    }
+                }
+                GP_ADD(3);
+                GP_CNT(10, 1);
+                // products of the window
+                const bool whole = ws == 0 && we == nw;
+                const int a_lo = ws == 0 ? c_lo : c_lo + ws * 32;
+                const int a_hi = we == nw ? c_hi : c_lo + we * 32;
+                auto add = [&](const boff (&q)[PB], const double (&av)[PB], unsigned valid) {
+                    int kk[PB];
+                    double x[PB];
+                    uint2 cell[PB];
+#pragma unroll
+                    for (int u = 0; u < PB; ++u) {
+                        kk[u] = -1; x[u] = 0.0;
+                        if ((valid >> u) & 1u) { kk[u] = __ldg(B.ci + q[u]) - c_lo; x[u] = av[u] * __ldg(B.v + q[u]); }
+                    }
+#pragma unroll
+                    for (int u = 0; u < PB; ++u) cell[u] = kk[u] >= 0 ? cells[kk[u] >> 5] : make_uint2(0u, 0u);
+#pragma unroll
+                    for (int u = 0; u < PB; ++u) {
+                        if (kk[u] < 0) continue;
+                        const int slot = (int)cell[u].y - base_rank + __popc(cell[u].x & ((1u << (kk[u] & 31)) - 1u));
+                        if ((unsigned)slot < (unsigned)wn) atomicAdd(&acc[slot], x[u]);
+                    }
+                };
+                if (single_tile) {
+                    if (whole) {
+                        GP_CNT(11, 1);
+                        gwin_run<true, BLOCK>(tile, tile_total, add);          // the tile of the mark pass is still in place
+                    } else {
+                        // narrow this thread's super-window segment to the rank window (short searches)
+                        boff qb = sw_qb;
+                        int len = sw_len;
+                        gwin_restrict<BLOCK>(B, n_a, qb, len, tile, ws == 0 ? 0 : a_lo, we == nw ? 0x7fffffff : a_hi);   // the segment already ends with the super-window
+                        const int total = gwin_scan<true, BLOCK>(tile, qb, len, my_av);
+                        GP_ADD(4);
+                        if (total) gwin_run<true, BLOCK>(tile, total, add);
+                    }
+                } else {
+                    for (aoff base = pa; base < pe; base += BLOCK) {
+                        const int total = gwin_build<true, BLOCK>(A, B, base, pe, tile, a_lo, a_hi);
+                        GP_ADD(14);
+                        GP_CNT(15, 1);
+                        if (total) gwin_run<true, BLOCK>(tile, total, add);
+                        __syncthreads();
+                        GP_ADD(16);
+                    }
+                }
+                __syncthreads();
+                GP_ADD(5);
+                for (int t = tid; t < wn; t += BLOCK) {
+                    c_ci[gs + emitted + t] = scol[t];
+                    c_v[gs + emitted + t] = acc[t];
+                    acc[t] = 0.0;
+                }
+                emitted += wn;
+                ws = we;
+                __syncthreads();
+                GP_ADD(6);
+            }
+            // 4. leave the cells clean for the next super-window / row
+            for (int w = tid; w < nw; w += BLOCK) cells[w] = make_uint2(0u, 0u);
+            __syncthreads();
+            GP_ADD(7);
+        }
     }
 }
 

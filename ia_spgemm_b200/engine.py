@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libiaspgemm.so")
+LIB_PATH = os.environ.get("IAS_LIB") or os.path.join(HERE, "libiaspgemm.so")     # IAS_LIB: an instrumented build (make prof)
 
 _I = C.POINTER(C.c_int)
 _L = C.POINTER(C.c_longlong)
@@ -80,7 +80,7 @@ BIN_NAMES = ["empty", "tiny", "warp", "cta_s", "cta_l", "global"]
 # every symbol include/iaspgemm.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
     "ias_init", "ias_set_stream", "ias_sync", "ias_last_error", "ias_version", "ias_device_info",
-    "ias_kernel_launches",
+    "ias_kernel_launches", "ias_set_option", "ias_get_option",
     "ias_upload_csr", "ias_free_csr_dev", "ias_free_csr64_dev", "ias_download_csr64", "ias_download_csr",
     "ias_csr_is_canonical", "ias_copy", "ias_forget_operand",
     "ias_csr_mul_csr_dev64", "ias_csr_mul_csr_dev", "ias_csr_mul_csr_rows_dev64", "ias_csr_mul_csr_stream",
@@ -176,6 +176,7 @@ def load_library():
         "ias_sizeof_csr": [C.c_int, C.c_longlong], "ias_sizeof_coo": [C.c_int, C.c_longlong],
         "ias_sizeof_dia": [C.c_int, C.c_int, C.c_int], "ias_sizeof_ell": [C.c_int, C.c_int],
         "ias_copy": [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int],
+        "ias_set_option": [C.c_char_p, C.c_longlong], "ias_get_option": [C.c_char_p, C.c_void_p],
         "ias_set_stream": [C.c_void_p], "ias_checksum": [C.c_void_p, C.c_longlong, _D],
         "ias_csr_mul_csr_stream": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p],
         "ias_getinfo3": [C.c_int, C.c_longlong, C.c_int, _D],
@@ -253,6 +254,15 @@ class Engine:
 
     def kernel_launches(self):
         return int(self.lib.ias_kernel_launches())
+
+    def set_option(self, name, value):
+        """Kernel-selection knob (include/iaspgemm.h: ias_set_option); results never depend on it."""
+        self._ck(self.lib.ias_set_option(name.encode(), int(value)))
+
+    def get_option(self, name):
+        v = C.c_longlong()
+        self._ck(self.lib.ias_get_option(name.encode(), C.byref(v)))
+        return int(v.value)
 
     def device_info(self):
         sm, smem, fr, tot = C.c_int(), C.c_size_t(), C.c_size_t(), C.c_size_t()

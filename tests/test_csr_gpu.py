@@ -261,3 +261,64 @@ def test_wide_column_space_uses_64bit_sort_keys(eng, oracle):
     got, st = _check(eng, oracle, A, B, mag=False)
     assert st["num_bin_rows"][2] > 0                         # warp bin populated
     assert int(got[1].max()) == ncols - 1
+
+
+# ---------------------------------------------------------------- global rows: windowed shared-memory kernels
+_GWIN_OPTS = ("global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw")
+
+
+@pytest.fixture
+def options(eng):
+    saved = {k: eng.get_option(k) for k in _GWIN_OPTS}
+    yield eng.set_option
+    for k, v in saved.items():
+        eng.set_option(k, v)
+
+
+def _global_operands(kind):
+    if kind == "few_a_entries":        # <= 128 A entries per row: warp-wide lower bounds, tile reused by the accumulate pass
+        return W.random_sparse(12, 100, 0.8, seed=11), W.random_sparse(100, 70001, 0.02, seed=12)
+    if kind == "mid_a_entries":        # 129..1024 A entries: one lower bound per thread, single tile
+        return W.random_sparse(10, 400, 0.7, seed=13), W.random_sparse(400, 50000, 0.005, seed=14)
+    if kind == "long_a_rows":          # more than 1024 A entries: several A tiles per window
+        return W.random_sparse(6, 3000, 0.9, seed=15), W.random_sparse(3000, 30011, 0.0007, seed=16)
+    raise ValueError(kind)
+
+
+@pytest.mark.parametrize("kind", ["few_a_entries", "mid_a_entries", "long_a_rows"])
+@pytest.mark.parametrize("swords,win,sym_swords", [(0, 0, 0), (32, 32, 32), (64, 96, 64), (8192, 64, 0), (32, 0, 0), (512, 4096, 1024)])
+def test_global_rows_windowed_kernels(eng, oracle, options, kind, swords, win, sym_swords):
+    """k_sym_gwin / k_num_gwin with every window geometry: one or many super-windows (32*swords columns),
+    one or many rank windows (win entries), last super-window partial (column counts are not multiples of 32)."""
+    A, B = _global_operands(kind)
+    options("global_rows_smem", 1)
+    options("gwin_max_sw", 0)
+    options("gwin_swords", swords)
+    options("gwin_win", win)
+    options("gwin_sym_swords", sym_swords)
+    got, st = _check(eng, oracle, A, B, mag=False)
+    assert st["num_bin_rows"][5] > 0 and st["sym_bin_rows"][5] > 0
+
+
+def test_global_rows_both_kernel_families_agree(eng, oracle, options):
+    """The L2 bitmap kernels (kept for non-canonical B) and the windowed kernels give the same C."""
+    A, B = _global_operands("mid_a_entries")
+    dA, dB = eng.upload(*A), eng.upload(*B)
+    options("global_rows_smem", 0)
+    (rp0, ci0, v0), st0 = eng.CSR_MUL_CSR_DEV(dA, dB)
+    options("global_rows_smem", 1)
+    options("gwin_max_sw", 0)
+    options("gwin_swords", 64)
+    options("gwin_win", 1024)
+    (rp1, ci1, v1), st1 = eng.CSR_MUL_CSR_DEV(dA, dB)
+    dA.close()
+    dB.close()
+    assert st0["num_bin_rows"][5] > 0 and st1["num_bin_rows"][5] > 0
+    assert np.array_equal(rp0, rp1) and np.array_equal(ci0, ci1)
+    assert np.all(np.abs(v0 - v1) <= RTOL * np.maximum(np.abs(v0), np.abs(v1)))
+
+
+def test_unknown_option_is_an_error(eng):
+    from ia_spgemm_b200.engine import EngineError
+    with pytest.raises(EngineError):
+        eng.set_option("no_such_knob", 1)
