@@ -16,7 +16,8 @@ struct Tuning {
     long long gwin_win = 0;           // numeric: entries per rank window (0: whatever shared memory is left)
     long long gwin_sym_swords = 0;    // symbolic: bitmap words per super-window (0: as many as fit)
     long long gwin_smem_kb = 0;       // cap on the dynamic shared memory of the windowed kernels (0: device limit)
-    long long gwin_max_sw = 4;        // numeric: use the windowed kernel up to this many super-windows per row (0: always);
+    long long g_win = 20480;          // L2 bitmap kernel: entries per accumulate window (multiple of 16; 160 KB tile by default)
+    long long gwin_max_sw = 1;        // numeric: use the windowed kernel up to this many super-windows per row (0: always);
                                       // beyond, the per-window scans of the cells cost more than the L2 lookups they replace
 };
 

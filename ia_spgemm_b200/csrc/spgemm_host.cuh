@@ -457,12 +457,13 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
         {
             auto k = k_num_global<AV, BV, 1024>;
-            int win = 20480;                                   // 160 KB tile of fp64 partial sums (192 KB would leave 28 KB of L1 for the
+            int win = (int)std::min<long long>(20480, std::max<long long>(16, c.tune.g_win & ~15LL));   // 160 KB tile of fp64 partial sums (192 KB would leave 28 KB of L1 for the
                                                                // B-row stream: ncu/clock64 showed the mark pass 1.6x slower)
             size_t sm = (size_t)win * sizeof(double);
             IAS_TRY(opt_in_smem(k, sm));
+            const int smem_mark = rw.b_canonical && c.tune.global_rows_smem != 0 && (win % 16) == 0;
             IAS_LAUNCH(k, rw.gslots, 1024, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p, GLayout::make(ncols_b),
-                       rw.cursor.p, win, rw.b_canonical);
+                       rw.cursor.p, win, rw.b_canonical, smem_mark, ncols_b);
         }
         IAS_BIN_END(8 + BIN_G);
         rw.num_timed[BIN_G] = true;

@@ -896,232 +896,6 @@ __global__ void __launch_bounds__(BLOCK) k_esc_warp(const int *__restrict__ rows
     }
 }
 
-// ---------------------------------------------------------------- global rows: bitmap + rank in L2
-// Workspace of one slot (all 32-bit words, zero between rows except prefix/blkpref):
-//   wp[words]       {bitmap word, output rank of its first bit}   words = ceil(ncols/32) rounded up to 32
-//   summary[sumw]   one bit per block of 32 bitmap words (= 1024 columns)
-//   blkpref[blocks] output rank of each block           blocks = words/32, sumw = ceil(blocks/32)
-//   wsum[blocks]    which of a block's 32 words are non-zero: the per-row scans read 4 bytes per block and
-//                   only the populated cells instead of the whole 8*cols/32-byte cell array
-struct GLayout {
-    int words, blocks, sumw;
-    size_t slot_words;          // words + words + sumw + blocks
-    __host__ __device__ static GLayout make(int ncols)
-    {
-        GLayout g;
-        long long w = ((long long)ncols + 31) / 32;
-        w = (w + 31) / 32 * 32;
-        g.words = (int)w; g.blocks = g.words / 32; g.sumw = (g.blocks + 31) / 32;
-        g.slot_words = ((size_t)g.words * 2 + g.sumw + 2 * (size_t)g.blocks + 31) / 32 * 32;   // keeps every slot 128-byte aligned
-        return g;
-    }
-};
-
-// bitmap word and rank prefix of the same 32 columns share one 8-byte cell {bits, rank}: the accumulate
-// pass needs both and gets them with a single L2 access (the global path is bound by L2 transactions)
-// a word that turns non-zero registers itself in its block's word mask, a block that turns non-zero in the summary
-__device__ __forceinline__ void g_first_touch(unsigned *summary, unsigned *wsum, int w)
-{
-    unsigned oldm = atomicOr(wsum + (w >> 5), 1u << (w & 31));
-    if (oldm == 0) atomicOr(summary + (w >> 10), 1u << ((w >> 5) & 31));
-}
-
-// PB products at once: all column loads, then all cell loads, then the (rare) atomics
-template <class BV>
-__device__ __forceinline__ void g_mark_batch(const BV &B, uint2 *wp, unsigned *summary, unsigned *wsum,
-                                             const typename BV::off_t (&q)[PB], unsigned valid, int &cnt)
-{
-    int k[PB];
-    unsigned cur[PB];
-#pragma unroll
-    for (int u = 0; u < PB; ++u) k[u] = (valid >> u) & 1u ? __ldg(B.ci + q[u]) : -1;
-#pragma unroll
-    for (int u = 0; u < PB; ++u) cur[u] = k[u] >= 0 ? __ldcg(&wp[k[u] >> 5].x) : 0xffffffffu;
-#pragma unroll
-    for (int u = 0; u < PB; ++u) {
-        if (k[u] < 0) continue;
-        int w = k[u] >> 5;
-        unsigned bit = 1u << (k[u] & 31);
-        if (!(cur[u] & bit)) {
-            unsigned old = atomicOr(&wp[w].x, bit);
-            if (!(old & bit)) {
-                ++cnt;
-                if (old == 0) g_first_touch(summary, wsum, w);
-            }
-        }
-    }
-}
-
-// zero exactly the cells that were touched (found through wsum), one thread per 1024-column block: the
-// per-row passes over the workspace are latency bound, so every thread issues its block's accesses at once
-template <int BLOCK>
-__device__ __forceinline__ void g_clear(uint2 *wp, unsigned *summary, unsigned *wsum, const GLayout &L)
-{
-    for (int b = threadIdx.x; b < L.blocks; b += BLOCK) {
-        unsigned m = __ldcg(wsum + b);
-        if (!m) continue;
-        wsum[b] = 0;
-        uint2 *cell = wp + (size_t)b * 32;
-#pragma unroll
-        for (int x = 0; x < 32; ++x)
-            if ((m >> x) & 1u) cell[x] = make_uint2(0, 0);
-    }
-    for (int sw = threadIdx.x; sw < L.sumw; sw += BLOCK) summary[sw] = 0;
-}
-
-template <class AV, class BV, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_sym_global(const int *__restrict__ rows, int nrows, int r0, AV A, BV B,
-                                                      int *__restrict__ nnz_row, unsigned *__restrict__ work, GLayout L,
-                                                      int *__restrict__ cursor)
-{
-    __shared__ int s_row, s_cnt;
-    __shared__ CtaTile<BV, BLOCK> tile;
-    uint2 *wp = reinterpret_cast<uint2 *>(work + (size_t)blockIdx.x * L.slot_words);
-    unsigned *summary = reinterpret_cast<unsigned *>(wp + L.words);
-    unsigned *wsum = summary + L.sumw + L.blocks;
-    int lane = threadIdx.x & 31;
-    while (true) {
-        if (threadIdx.x == 0) { s_row = atomicAdd(cursor, 1); s_cnt = 0; }
-        __syncthreads();
-        int idx = s_row;
-        if (idx >= nrows) break;
-        int li = rows ? rows[idx] : idx;
-        int i = r0 + li;
-        int cnt = 0;
-        cta_products<false, BLOCK>(A, B, A.begin(i), A.end(i), tile,
-                                   [&](const typename BV::off_t (&q)[PB], const double (&)[PB], unsigned valid) {
-                                       g_mark_batch(B, wp, summary, wsum, q, valid, cnt);
-                                   });
-        cnt = warp_sum(cnt);
-        if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
-        __syncthreads();
-        if (threadIdx.x == 0) nnz_row[li] = s_cnt;
-        g_clear<BLOCK>(wp, summary, wsum, L);
-        __syncthreads();
-    }
-}
-
-// Numeric pass of a global row.  The values are NOT accumulated in global memory: with hundreds of
-// rows in flight the value segments (up to 16 MB each at R-MAT scale 22) thrash the L2 and every RED
-// becomes an HBM round trip.  Instead the row is cut into windows of WIN consecutive ranks; a window's
-// values live in a dense shared-memory tile indexed by rank, products are added with shared-memory
-// atomics, and the tile is written out once, coalesced.  With canonical B only the part of each B row
-// inside the window's column range is visited (two binary searches per A entry and window); most
-// global rows need one or two windows.
-template <class AV, class BV, int BLOCK>
-__global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
-                                                      int *__restrict__ c_ci, double *__restrict__ c_v,
-                                                      unsigned *__restrict__ work, GLayout L, int *__restrict__ cursor,
-                                                      int win, int b_canonical)
-{
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    double *acc = reinterpret_cast<double *>(smem_raw);           // win entries
-    typedef cub::BlockScan<unsigned, BLOCK> Scan;
-    __shared__ typename Scan::TempStorage scan_tmp;
-    __shared__ int s_row, s_lo, s_hi;
-    __shared__ unsigned s_carry;
-    __shared__ CtaTile<BV, BLOCK> tile;
-    uint2 *wp = reinterpret_cast<uint2 *>(work + (size_t)blockIdx.x * L.slot_words);
-    unsigned *summary = reinterpret_cast<unsigned *>(wp + L.words);
-    unsigned *wsum = summary + L.sumw + L.blocks;
-    while (true) {
-        if (threadIdx.x == 0) { s_row = atomicAdd(cursor, 1); s_carry = 0; }
-        __syncthreads();
-        int idx = s_row;
-        if (idx >= nrows) break;
-        int li = rows ? rows[idx] : idx;
-        int i = r0 + li;
-        long long gs = out.start(li);
-        const int n = out.count(li);
-        typename AV::off_t pa = A.begin(i), pe = A.end(i);
-        // 1. mark the columns of the row
-        int dummy = 0;
-        cta_products<false, BLOCK>(A, B, pa, pe, tile,
-                                   [&](const typename BV::off_t (&q)[PB], const double (&)[PB], unsigned valid) {
-                                       g_mark_batch(B, wp, summary, wsum, q, valid, dummy);
-                                   });
-        __syncthreads();
-        // 2. ranks.  One thread per 1024-column block: fetch the block's populated words in one burst (32
-        //    independent predicated loads), block-scan the populations, then write each word's rank and emit
-        //    the sorted column list.
-        for (int bb = 0; bb < L.blocks; bb += BLOCK) {
-            const int b = bb + threadIdx.x;
-            unsigned m = b < L.blocks ? __ldcg(wsum + b) : 0u;
-            const uint2 *cell = wp + (size_t)b * 32;
-            unsigned word[32];
-            unsigned c = 0;
-#pragma unroll
-            for (int x = 0; x < 32; ++x) {
-                word[x] = (m >> x) & 1u ? __ldcg(&cell[x].x) : 0u;
-                c += __popc(word[x]);
-            }
-            unsigned excl, tile_total;
-            Scan(scan_tmp).ExclusiveSum(c, excl, tile_total);
-            __syncthreads();                               // scan_tmp is reused by the next trip
-            unsigned rank = s_carry + excl;                 // s_carry: entries of the blocks of earlier trips
-            if (m) {
-#pragma unroll
-                for (int x = 0; x < 32; ++x) {
-                    unsigned wd = word[x];
-                    if (!wd) continue;
-                    wp[(size_t)b * 32 + x].y = rank;
-                    while (wd) {
-                        int bit = __ffs(wd) - 1;
-                        wd &= wd - 1;
-                        c_ci[gs + rank] = (b * 32 + x) * 32 + bit;
-                        ++rank;
-                    }
-                }
-            }
-            __syncthreads();
-            if (threadIdx.x == 0) s_carry += tile_total;
-            __syncthreads();
-        }
-        __threadfence();          // window bounds below are read back from c_ci by another thread
-        __syncthreads();
-        // 3. one window of `win` ranks at a time: accumulate in the shared-memory tile, then write it out
-        for (int wbase = 0; wbase < n; wbase += win) {
-            const int wn = min(win, n - wbase);
-            if (threadIdx.x == 0) {
-                s_lo = wbase == 0 ? 0 : __ldcg(c_ci + gs + wbase);
-                s_hi = wbase + win < n ? __ldcg(c_ci + gs + wbase + win) : 0x7fffffff;
-            }
-            for (int t = threadIdx.x; t < wn; t += BLOCK) acc[t] = 0.0;
-            __syncthreads();
-            const int c_lo = s_lo, c_hi = s_hi;
-            auto add = [&](const typename BV::off_t (&q)[PB], const double (&av)[PB], unsigned valid) {
-                int k[PB];
-                double x[PB];
-                uint2 cell[PB];
-#pragma unroll
-                for (int u = 0; u < PB; ++u) {
-                    k[u] = -1; x[u] = 0.0;
-                    if ((valid >> u) & 1u) { k[u] = __ldg(B.ci + q[u]); x[u] = av[u] * __ldg(B.v + q[u]); }
-                }
-#pragma unroll
-                for (int u = 0; u < PB; ++u) {
-                    if (k[u] < c_lo || k[u] >= c_hi) k[u] = -1;
-                    cell[u] = k[u] >= 0 ? __ldcg(wp + (k[u] >> 5)) : make_uint2(0, 0);
-                }
-#pragma unroll
-                for (int u = 0; u < PB; ++u) {
-                    if (k[u] < 0) continue;
-                    unsigned below = cell[u].x & ((1u << (k[u] & 31)) - 1u);
-                    atomicAdd(&acc[(int)(cell[u].y + __popc(below)) - wbase], x[u]);
-                }
-            };
-            if (b_canonical && n > win) cta_products<true, BLOCK>(A, B, pa, pe, tile, add, ColumnWindow<BV>{B, c_lo, c_hi});
-            else cta_products<true, BLOCK>(A, B, pa, pe, tile, add);
-            __syncthreads();
-            for (int t = threadIdx.x; t < wn; t += BLOCK) c_v[gs + wbase + t] = acc[t];
-            __syncthreads();
-        }
-        // 4. leave the slot clean for the next row
-        g_clear<BLOCK>(wp, summary, wsum, L);
-        __syncthreads();
-    }
-}
-
 // ---------------------------------------------------------------- global rows, windowed in shared memory
 // The L2 variant above pays one L2 transaction per product and pass (ncu: 31 % issue, DRAM 3 %, L2-latency
 // bound at ~100 G products/s).  A microbenchmark on B200 (tools/ubench/smem_atomics.cu) gives 7.4 lanes/clk/SM
@@ -1304,6 +1078,281 @@ __device__ __forceinline__ void gwin_run(const CtaTile<BV, BLOCK> &tile, int tot
     }
 }
 
+// ---------------------------------------------------------------- global rows: bitmap + rank in L2
+// Workspace of one slot (all 32-bit words, zero between rows except prefix/blkpref):
+//   wp[words]       {bitmap word, output rank of its first bit}   words = ceil(ncols/32) rounded up to 32
+//   summary[sumw]   one bit per block of 32 bitmap words (= 1024 columns)
+//   blkpref[blocks] output rank of each block           blocks = words/32, sumw = ceil(blocks/32)
+//   wsum[blocks]    which of a block's 32 words are non-zero: the per-row scans read 4 bytes per block and
+//                   only the populated cells instead of the whole 8*cols/32-byte cell array
+struct GLayout {
+    int words, blocks, sumw;
+    size_t slot_words;          // words + words + sumw + blocks
+    __host__ __device__ static GLayout make(int ncols)
+    {
+        GLayout g;
+        long long w = ((long long)ncols + 31) / 32;
+        w = (w + 31) / 32 * 32;
+        g.words = (int)w; g.blocks = g.words / 32; g.sumw = (g.blocks + 31) / 32;
+        g.slot_words = ((size_t)g.words * 2 + g.sumw + 2 * (size_t)g.blocks + 31) / 32 * 32;   // keeps every slot 128-byte aligned
+        return g;
+    }
+};
+
+// bitmap word and rank prefix of the same 32 columns share one 8-byte cell {bits, rank}: the accumulate
+// pass needs both and gets them with a single L2 access (the global path is bound by L2 transactions)
+// a word that turns non-zero registers itself in its block's word mask, a block that turns non-zero in the summary
+__device__ __forceinline__ void g_first_touch(unsigned *summary, unsigned *wsum, int w)
+{
+    unsigned oldm = atomicOr(wsum + (w >> 5), 1u << (w & 31));
+    if (oldm == 0) atomicOr(summary + (w >> 10), 1u << ((w >> 5) & 31));
+}
+
+// PB products at once: all column loads, then all cell loads, then the (rare) atomics
+template <class BV>
+__device__ __forceinline__ void g_mark_batch(const BV &B, uint2 *wp, unsigned *summary, unsigned *wsum,
+                                             const typename BV::off_t (&q)[PB], unsigned valid, int &cnt)
+{
+    int k[PB];
+    unsigned cur[PB];
+#pragma unroll
+    for (int u = 0; u < PB; ++u) k[u] = (valid >> u) & 1u ? __ldg(B.ci + q[u]) : -1;
+#pragma unroll
+    for (int u = 0; u < PB; ++u) cur[u] = k[u] >= 0 ? __ldcg(&wp[k[u] >> 5].x) : 0xffffffffu;
+#pragma unroll
+    for (int u = 0; u < PB; ++u) {
+        if (k[u] < 0) continue;
+        int w = k[u] >> 5;
+        unsigned bit = 1u << (k[u] & 31);
+        if (!(cur[u] & bit)) {
+            unsigned old = atomicOr(&wp[w].x, bit);
+            if (!(old & bit)) {
+                ++cnt;
+                if (old == 0) g_first_touch(summary, wsum, w);
+            }
+        }
+    }
+}
+
+// zero exactly the cells that were touched (found through wsum), one thread per 1024-column block: the
+// per-row passes over the workspace are latency bound, so every thread issues its block's accesses at once
+template <int BLOCK>
+__device__ __forceinline__ void g_clear(uint2 *wp, unsigned *summary, unsigned *wsum, const GLayout &L)
+{
+    for (int b = threadIdx.x; b < L.blocks; b += BLOCK) {
+        unsigned m = __ldcg(wsum + b);
+        if (!m) continue;
+        wsum[b] = 0;
+        uint2 *cell = wp + (size_t)b * 32;
+#pragma unroll
+        for (int x = 0; x < 32; ++x)
+            if ((m >> x) & 1u) cell[x] = make_uint2(0, 0);
+    }
+    for (int sw = threadIdx.x; sw < L.sumw; sw += BLOCK) summary[sw] = 0;
+}
+
+template <class AV, class BV, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_sym_global(const int *__restrict__ rows, int nrows, int r0, AV A, BV B,
+                                                      int *__restrict__ nnz_row, unsigned *__restrict__ work, GLayout L,
+                                                      int *__restrict__ cursor)
+{
+    __shared__ int s_row, s_cnt;
+    __shared__ CtaTile<BV, BLOCK> tile;
+    uint2 *wp = reinterpret_cast<uint2 *>(work + (size_t)blockIdx.x * L.slot_words);
+    unsigned *summary = reinterpret_cast<unsigned *>(wp + L.words);
+    unsigned *wsum = summary + L.sumw + L.blocks;
+    int lane = threadIdx.x & 31;
+    while (true) {
+        if (threadIdx.x == 0) { s_row = atomicAdd(cursor, 1); s_cnt = 0; }
+        __syncthreads();
+        int idx = s_row;
+        if (idx >= nrows) break;
+        int li = rows ? rows[idx] : idx;
+        int i = r0 + li;
+        int cnt = 0;
+        cta_products<false, BLOCK>(A, B, A.begin(i), A.end(i), tile,
+                                   [&](const typename BV::off_t (&q)[PB], const double (&)[PB], unsigned valid) {
+                                       g_mark_batch(B, wp, summary, wsum, q, valid, cnt);
+                                   });
+        cnt = warp_sum(cnt);
+        if (lane == 0 && cnt) atomicAdd(&s_cnt, cnt);
+        __syncthreads();
+        if (threadIdx.x == 0) nnz_row[li] = s_cnt;
+        g_clear<BLOCK>(wp, summary, wsum, L);
+        __syncthreads();
+    }
+}
+
+// Numeric pass of a global row.  The values are NOT accumulated in global memory: with hundreds of
+// rows in flight the value segments (up to 16 MB each at R-MAT scale 22) thrash the L2 and every RED
+// becomes an HBM round trip.  Instead the row is cut into windows of WIN consecutive ranks; a window's
+// values live in a dense shared-memory tile indexed by rank, products are added with shared-memory
+// atomics, and the tile is written out once, coalesced.  With canonical B only the part of each B row
+// inside the window's column range is visited (two binary searches per A entry and window); most
+// global rows need one or two windows.
+template <class AV, class BV, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
+                                                      int *__restrict__ c_ci, double *__restrict__ c_v,
+                                                      unsigned *__restrict__ work, GLayout L, int *__restrict__ cursor,
+                                                      int win, int b_canonical, int smem_mark, int ncols)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *acc = reinterpret_cast<double *>(smem_raw);           // win entries
+    typedef cub::BlockScan<unsigned, BLOCK> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    __shared__ int s_row, s_lo, s_hi;
+    __shared__ unsigned s_carry;
+    __shared__ CtaTile<BV, BLOCK> tile;
+    uint2 *wp = reinterpret_cast<uint2 *>(work + (size_t)blockIdx.x * L.slot_words);
+    unsigned *summary = reinterpret_cast<unsigned *>(wp + L.words);
+    unsigned *wsum = summary + L.sumw + L.blocks;
+    while (true) {
+        if (threadIdx.x == 0) { s_row = atomicAdd(cursor, 1); s_carry = 0; }
+        __syncthreads();
+        int idx = s_row;
+        if (idx >= nrows) break;
+        int li = rows ? rows[idx] : idx;
+        int i = r0 + li;
+        long long gs = out.start(li);
+        const int n = out.count(li);
+        typename AV::off_t pa = A.begin(i), pe = A.end(i);
+        // 1. mark the columns of the row.  Canonical B: in shared memory, one super-window of 2*win*32 columns at a
+        //    time (the bitmap borrows the accumulate tile), each flushed to the row's cells with coalesced stores --
+        //    no L2 atomic per product (that pass was 38 % of this kernel at R-MAT scale 22).
+        if (smem_mark) {
+            unsigned *bits = reinterpret_cast<unsigned *>(smem_raw);
+            const int swords = win * 2;                                  // 32-bit words in the tile's bytes
+            const long long span = (long long)swords * 32;
+            for (int w = threadIdx.x; w < swords; w += BLOCK) bits[w] = 0;
+            __syncthreads();
+            for (long long sw_lo = 0; sw_lo < ncols; sw_lo += span) {
+                const int c_lo = (int)sw_lo;
+                const int c_hi = sw_lo + span >= ncols ? 0x7fffffff : (int)(sw_lo + span);
+                bool any = false;
+                for (typename AV::off_t base = pa; base < pe; base += BLOCK) {
+                    const int total = gwin_build<false, BLOCK>(A, B, base, pe, tile, c_lo, c_hi);
+                    if (total) {
+                        any = true;
+                        gwin_run<false, BLOCK>(tile, total, [&](const typename BV::off_t (&q)[PB], const double (&)[PB], unsigned valid) {
+                            int k[PB];
+                            unsigned cur[PB];
+#pragma unroll
+                            for (int u = 0; u < PB; ++u) k[u] = (valid >> u) & 1u ? __ldg(B.ci + q[u]) - c_lo : -1;
+#pragma unroll
+                            for (int u = 0; u < PB; ++u) cur[u] = k[u] >= 0 ? bits[k[u] >> 5] : 0xffffffffu;
+#pragma unroll
+                            for (int u = 0; u < PB; ++u) {
+                                const unsigned bit = 1u << (k[u] & 31);
+                                if (!(cur[u] & bit)) atomicOr(&bits[k[u] >> 5], bit);
+                            }
+                        });
+                    }
+                    __syncthreads();
+                }
+                if (!any) continue;
+                // flush: a warp per block of 32 words; the block's word mask comes from one ballot
+                const int w0g = c_lo >> 5;                                // first global word of the super-window
+                const int nwords = min(swords, L.words - w0g);
+                for (int wb = (threadIdx.x >> 5) * 32; wb < nwords; wb += BLOCK) {
+                    const int w = wb + (threadIdx.x & 31);
+                    const unsigned word = bits[w];                        // nwords is a multiple of 32 (L.words and swords are)
+                    const unsigned m = __ballot_sync(0xffffffffu, word != 0u);
+                    if (word) { wp[w0g + w].x = word; bits[w] = 0; }
+                    if (m && (threadIdx.x & 31) == 0) wsum[(w0g + wb) >> 5] = m;
+                }
+                __syncthreads();
+            }
+        } else {
+            int dummy = 0;
+            cta_products<false, BLOCK>(A, B, pa, pe, tile,
+                                       [&](const typename BV::off_t (&q)[PB], const double (&)[PB], unsigned valid) {
+                                           g_mark_batch(B, wp, summary, wsum, q, valid, dummy);
+                                       });
+        }
+        __syncthreads();
+        // 2. ranks.  One thread per 1024-column block: fetch the block's populated words in one burst (32
+        //    independent predicated loads), block-scan the populations, then write each word's rank and emit
+        //    the sorted column list.  (A warp-per-block, entry-parallel emission with coalesced stores was tried:
+        //    its per-block L2 round trips are serial per warp and it lost 20 % at R-MAT scale 20/22.)
+        for (int bb = 0; bb < L.blocks; bb += BLOCK) {
+            const int b = bb + threadIdx.x;
+            unsigned m = b < L.blocks ? __ldcg(wsum + b) : 0u;
+            const uint2 *cell = wp + (size_t)b * 32;
+            unsigned word[32];
+            unsigned c = 0;
+#pragma unroll
+            for (int x = 0; x < 32; ++x) {
+                word[x] = (m >> x) & 1u ? __ldcg(&cell[x].x) : 0u;
+                c += __popc(word[x]);
+            }
+            unsigned excl, tile_total;
+            Scan(scan_tmp).ExclusiveSum(c, excl, tile_total);
+            __syncthreads();                               // scan_tmp is reused by the next trip
+            unsigned rank = s_carry + excl;                 // s_carry: entries of the blocks of earlier trips
+            if (m) {
+#pragma unroll
+                for (int x = 0; x < 32; ++x) {
+                    unsigned wd = word[x];
+                    if (!wd) continue;
+                    wp[(size_t)b * 32 + x].y = rank;
+                    while (wd) {
+                        int bit = __ffs(wd) - 1;
+                        wd &= wd - 1;
+                        c_ci[gs + rank] = (b * 32 + x) * 32 + bit;
+                        ++rank;
+                    }
+                }
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) s_carry += tile_total;
+            __syncthreads();
+        }
+        __threadfence();          // window bounds below are read back from c_ci by another thread
+        __syncthreads();
+        // 3. one window of `win` ranks at a time: accumulate in the shared-memory tile, then write it out
+        for (int wbase = 0; wbase < n; wbase += win) {
+            const int wn = min(win, n - wbase);
+            if (threadIdx.x == 0) {
+                s_lo = wbase == 0 ? 0 : __ldcg(c_ci + gs + wbase);
+                s_hi = wbase + win < n ? __ldcg(c_ci + gs + wbase + win) : 0x7fffffff;
+            }
+            for (int t = threadIdx.x; t < wn; t += BLOCK) acc[t] = 0.0;
+            __syncthreads();
+            const int c_lo = s_lo, c_hi = s_hi;
+            auto add = [&](const typename BV::off_t (&q)[PB], const double (&av)[PB], unsigned valid) {
+                int k[PB];
+                double x[PB];
+                uint2 cell[PB];
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    k[u] = -1; x[u] = 0.0;
+                    if ((valid >> u) & 1u) { k[u] = __ldg(B.ci + q[u]); x[u] = av[u] * __ldg(B.v + q[u]); }
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    if (k[u] < c_lo || k[u] >= c_hi) k[u] = -1;
+                    cell[u] = k[u] >= 0 ? __ldcg(wp + (k[u] >> 5)) : make_uint2(0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    if (k[u] < 0) continue;
+                    unsigned below = cell[u].x & ((1u << (k[u] & 31)) - 1u);
+                    atomicAdd(&acc[(int)(cell[u].y + __popc(below)) - wbase], x[u]);
+                }
+            };
+            if (b_canonical && n > win) cta_products<true, BLOCK>(A, B, pa, pe, tile, add, ColumnWindow<BV>{B, c_lo, c_hi});
+            else cta_products<true, BLOCK>(A, B, pa, pe, tile, add);
+            __syncthreads();
+            for (int t = threadIdx.x; t < wn; t += BLOCK) c_v[gs + wbase + t] = acc[t];
+            __syncthreads();
+        }
+        // 4. leave the slot clean for the next row
+        g_clear<BLOCK>(wp, summary, wsum, L);
+        __syncthreads();
+    }
+}
+
+// ---------------------------------------------------------------- windowed kernels (helpers are defined ahead of the L2 kernels, which share them)
 template <class AV, class BV, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_sym_gwin(const int *__restrict__ rows, int nrows, int r0, AV A, BV B,
                                                     int *__restrict__ nnz_row, int *__restrict__ cursor, int ncols, int swords)
@@ -1413,9 +1462,10 @@ __global__ void __launch_bounds__(BLOCK) k_num_gwin(const int *__restrict__ rows
         // latency chain per row instead of one per window): tbl[e][k] = first index of B row e with column >= k*span.
         boff my_qb = 0;
         int my_len = 0;
-        double my_av = 0.0;
         const bool use_tbl = single_tile && nsw > 1 && (long long)n_a * tstride <= tbl_cap;
-        if (single_tile) gwin_load<true>(A, B, pa, pe, my_qb, my_len, my_av);
+        if (single_tile) { double unused; gwin_load<false>(A, B, pa, pe, my_qb, my_len, unused); }
+        // (the A value is re-read where a tile is built: one L1/L2 hit instead of two registers held across the row)
+        auto my_av = [&]() { return tid < n_a ? __ldg(A.v + pa + tid) : 0.0; };
         if (use_tbl) {
             tile.rel[tid] = my_qb;
             tile.incl[tid] = my_len;
@@ -1440,20 +1490,23 @@ __global__ void __launch_bounds__(BLOCK) k_num_gwin(const int *__restrict__ rows
             const int c_hi = k + 1 == nsw ? 0x7fffffff : (int)(sw_lo + span);
             const int nw = (int)min((long long)swords, ((long long)ncols - sw_lo + 31) / 32);
             // this thread's B-row segment inside the super-window (single_tile only)
-            boff sw_qb = my_qb;
-            int sw_len = my_len;
+            auto segment = [&](boff &qb, int &len) {
+                qb = my_qb; len = my_len;
+                if (use_tbl) {
+                    const int o0 = tid < n_a ? tbl[tid * tstride + k] : 0, o1 = tid < n_a ? tbl[tid * tstride + k + 1] : 0;
+                    qb = my_qb + o0;
+                    len = o1 - o0;
+                }
+            };
             // 1. mark the columns of this super-window (the tile of a short A row is kept for step 3)
             bool any = false;
             int tile_total = 0;
             if (single_tile) {
-                if (use_tbl) {
-                    const int o0 = tid < n_a ? tbl[tid * tstride + k] : 0, o1 = tid < n_a ? tbl[tid * tstride + k + 1] : 0;
-                    sw_qb = my_qb + o0;
-                    sw_len = o1 - o0;
-                } else {
-                    gwin_restrict<BLOCK>(B, n_a, sw_qb, sw_len, tile, c_lo, c_hi);
-                }
-                tile_total = gwin_scan<true, BLOCK>(tile, sw_qb, sw_len, my_av);
+                boff qb;
+                int len;
+                segment(qb, len);
+                if (!use_tbl) gwin_restrict<BLOCK>(B, n_a, qb, len, tile, c_lo, c_hi);
+                tile_total = gwin_scan<true, BLOCK>(tile, qb, len, my_av());
             }
             auto mark = [&](const boff (&q)[PB], const double (&)[PB], unsigned valid) {
                 int kk[PB];
@@ -1485,18 +1538,29 @@ __global__ void __launch_bounds__(BLOCK) k_num_gwin(const int *__restrict__ rows
             }
             if (!any) { GP_CNT(12, 1); continue; }
             GP_CNT(9, 1);
-            // 2. rank of every word's first bit: each warp scans a contiguous chunk, then the chunk bases are added
-            const int chunk = ((nw + NWARPS - 1) / NWARPS + 31) & ~31;
-            const int w_begin = min(nw, wid * chunk), w_end = min(nw, w_begin + chunk);
+            // 2. rank of every word's first bit: each warp scans a contiguous chunk (four cells per lane and trip,
+            //    128-bit shared-memory accesses), then the chunk bases are added.  Cells between nw and the next
+            //    multiple of 4 are empty and may be rewritten.
+            const int chunk = ((nw + NWARPS - 1) / NWARPS + 127) & ~127;
+            const int nw4 = (nw + 3) & ~3;
+            const int w_begin = min(nw4, wid * chunk), w_end = min(nw4, w_begin + chunk);
             {
                 int carry = 0;
-                for (int w0 = w_begin; w0 < w_end; w0 += 32) {
-                    const int w = w0 + lane;
-                    const int c = w < w_end ? __popc(cells[w].x) : 0;
+                for (int w0 = w_begin; w0 < w_end; w0 += 128) {
+                    const int w = w0 + lane * 4;
+                    uint4 a = make_uint4(0u, 0u, 0u, 0u), b = a;
+                    if (w < w_end) { a = *reinterpret_cast<const uint4 *>(cells + w); b = *reinterpret_cast<const uint4 *>(cells + w + 2); }
+                    const int c0 = __popc(a.x), c1 = __popc(a.z), c2 = __popc(b.x), c3 = __popc(b.z);
+                    const int c = c0 + c1 + c2 + c3;
                     int incl = c;
 #pragma unroll
                     for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-                    if (w < w_end) cells[w].y = (unsigned)(carry + incl - c);
+                    if (w < w_end) {
+                        const unsigned y0 = (unsigned)(carry + incl - c);
+                        a.y = y0; a.w = y0 + c0; b.y = y0 + c0 + c1; b.w = y0 + c0 + c1 + c2;
+                        *reinterpret_cast<uint4 *>(cells + w) = a;
+                        *reinterpret_cast<uint4 *>(cells + w + 2) = b;
+                    }
                     carry += __shfl_sync(0xffffffffu, incl, 31);
                 }
                 if (lane == 0) s_wtot[wid] = carry;
@@ -1514,7 +1578,11 @@ __global__ void __launch_bounds__(BLOCK) k_num_gwin(const int *__restrict__ rows
             {
                 const unsigned wb = (unsigned)s_wbase[wid];
                 if (wb)
-                    for (int w = w_begin + lane; w < w_end; w += 32) cells[w].y += wb;
+                    for (int w = w_begin + lane * 2; w < w_end; w += 64) {
+                        uint4 a = *reinterpret_cast<const uint4 *>(cells + w);
+                        a.y += wb; a.w += wb;
+                        *reinterpret_cast<uint4 *>(cells + w) = a;
+                    }
             }
             const int sw_total = s_wbase[32];
             __syncthreads();
@@ -1534,20 +1602,30 @@ __global__ void __launch_bounds__(BLOCK) k_num_gwin(const int *__restrict__ rows
                     we = lo;
                 }
                 const int wn = (we == nw ? sw_total : (int)cells[we].y) - base_rank;
-                // sorted columns of the window; every lane starts at another bit position so that dense words
-                // (rank stride 32) do not pile onto one bank
-                for (int w = ws + tid; w < we; w += BLOCK) {
-                    const uint2 c = cells[w];
-                    const int r = (int)c.y - base_rank;
-                    const int col0 = c_lo + w * 32;
-                    const unsigned himask = 0xffffffffu << lane;
-                    unsigned cur = c.x & himask;
-                    unsigned rest = c.x & ~himask;
-                    while (cur | rest) {
-                        if (!cur) { cur = rest; rest = 0; }
-                        const int q = __ffs(cur) - 1;
-                        cur &= cur - 1;
-                        scol[r + __popc(c.x & ((1u << q) - 1u))] = col0 + q;
+                // sorted columns of the window, rank-parallel: thread t produces entries [t*G, (t+1)*G) -- it finds the
+                // word that holds its first rank by binary search over the ranks, then walks the bits.  (One thread per
+                // word leaves the warp that draws the hub columns, 32 bits in every word, far behind the others.)
+                {
+                    const int G = (wn + BLOCK - 1) / BLOCK;
+                    int r = tid * G;
+                    const int r_end = min(wn, r + G);
+                    if (r < r_end) {
+                        const unsigned target = (unsigned)(base_rank + r);
+                        int lo = ws, hi = we - 1;              // last word whose first rank is <= target
+                        while (lo < hi) {
+                            const int mid = (lo + hi + 1) >> 1;
+                            if (cells[mid].y <= target) lo = mid; else hi = mid - 1;
+                        }
+                        int w = lo;
+                        const uint2 c = cells[w];
+                        unsigned bits = c.x;
+                        for (unsigned skip = target - c.y; skip > 0; --skip) bits &= bits - 1;
+                        while (r < r_end) {
+                            if (!bits) { ++w; bits = cells[w].x; continue; }
+                            const int q = __ffs(bits) - 1;
+                            bits &= bits - 1;
+                            scol[r++] = c_lo + w * 32 + q;
+                        }
                     }
                 }
                 GP_ADD(3);
@@ -1579,11 +1657,14 @@ __global__ void __launch_bounds__(BLOCK) k_num_gwin(const int *__restrict__ rows
                         GP_CNT(11, 1);
                         gwin_run<true, BLOCK>(tile, tile_total, add);          // the tile of the mark pass is still in place
                     } else {
-                        // narrow this thread's super-window segment to the rank window (short searches)
-                        boff qb = sw_qb;
-                        int len = sw_len;
-                        gwin_restrict<BLOCK>(B, n_a, qb, len, tile, ws == 0 ? 0 : a_lo, we == nw ? 0x7fffffff : a_hi);   // the segment already ends with the super-window
-                        const int total = gwin_scan<true, BLOCK>(tile, qb, len, my_av);
+                        // narrow this thread's segment to the rank window (short searches when the split table gave
+                        // the super-window's part of the B row, which then also bounds the window on the outside)
+                        boff qb;
+                        int len;
+                        segment(qb, len);
+                        if (use_tbl) gwin_restrict<BLOCK>(B, n_a, qb, len, tile, ws == 0 ? 0 : a_lo, we == nw ? 0x7fffffff : a_hi);
+                        else gwin_restrict<BLOCK>(B, n_a, qb, len, tile, a_lo, a_hi);
+                        const int total = gwin_scan<true, BLOCK>(tile, qb, len, my_av());
                         GP_ADD(4);
                         if (total) gwin_run<true, BLOCK>(tile, total, add);
                     }
@@ -1610,7 +1691,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_gwin(const int *__restrict__ rows
                 GP_ADD(6);
             }
             // 4. leave the cells clean for the next super-window / row
-            for (int w = tid; w < nw; w += BLOCK) cells[w] = make_uint2(0u, 0u);
+            for (int w = tid * 2; w < nw; w += BLOCK * 2) *reinterpret_cast<uint4 *>(cells + w) = make_uint4(0u, 0u, 0u, 0u);
             __syncthreads();
             GP_ADD(7);
         }

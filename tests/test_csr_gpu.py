@@ -264,7 +264,7 @@ def test_wide_column_space_uses_64bit_sort_keys(eng, oracle):
 
 
 # ---------------------------------------------------------------- global rows: windowed shared-memory kernels
-_GWIN_OPTS = ("global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw")
+_GWIN_OPTS = ("global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win")
 
 
 @pytest.fixture
@@ -298,6 +298,20 @@ def test_global_rows_windowed_kernels(eng, oracle, options, kind, swords, win, s
     options("gwin_sym_swords", sym_swords)
     got, st = _check(eng, oracle, A, B, mag=False)
     assert st["num_bin_rows"][5] > 0 and st["sym_bin_rows"][5] > 0
+
+
+@pytest.mark.parametrize("kind", ["few_a_entries", "mid_a_entries", "long_a_rows"])
+@pytest.mark.parametrize("g_win", [20480, 4096, 64])
+def test_global_rows_l2_kernel_with_shared_memory_mark(eng, oracle, options, kind, g_win):
+    """Wide column spaces keep the L2 bitmap/rank kernel for the numeric pass, with its mark pass done in shared
+    memory one super-window (64 * g_win columns) at a time and flushed to the row's cells."""
+    A, B = _global_operands(kind)
+    options("global_rows_smem", 1)
+    options("gwin_swords", 32)
+    options("gwin_max_sw", 1)              # 32 * 32 columns per super-window: the windowed numeric kernel is refused
+    options("g_win", g_win)
+    got, st = _check(eng, oracle, A, B, mag=False)
+    assert st["num_bin_rows"][5] > 0
 
 
 def test_global_rows_both_kernel_families_agree(eng, oracle, options):
