@@ -17,6 +17,8 @@ struct Tuning {
     long long gwin_sym_swords = 0;    // symbolic: bitmap words per super-window (0: as many as fit)
     long long gwin_smem_kb = 0;       // cap on the dynamic shared memory of the windowed kernels (0: device limit)
     long long g_win = 20480;          // L2 bitmap kernel: entries per accumulate window (multiple of 16; 160 KB tile by default)
+    long long g_coop = 1;             // L2 bitmap kernel: accumulate pass enumerates products with gwin_build / gwin_run
+    long long gwin_takes_b2 = 1;      // rows of the large CTA hash bin go to the windowed kernel when it is selected
     long long gwin_max_sw = 1;        // numeric: use the windowed kernel up to this many super-windows per row (0: always);
                                       // beyond, the per-window scans of the cells cost more than the L2 lookups they replace
 };

@@ -54,6 +54,8 @@ static long long *option_slot(const char *name)
     if (!strcmp(name, "gwin_smem_kb")) return &t.gwin_smem_kb;
     if (!strcmp(name, "gwin_max_sw")) return &t.gwin_max_sw;
     if (!strcmp(name, "g_win")) return &t.g_win;
+    if (!strcmp(name, "g_coop")) return &t.g_coop;
+    if (!strcmp(name, "gwin_takes_b2")) return &t.gwin_takes_b2;
     return nullptr;
 }
 
@@ -84,7 +86,7 @@ int ias_init(int device)
     for (int i = 0; i < 32; ++i)
         if (!c.ev_bin[i]) IAS_CUDA(cudaEventCreate(&c.ev_bin[i]));
     if (!c.h_scalars) IAS_CUDA(cudaMallocHost((void **)&c.h_scalars, 64 * sizeof(long long)));
-    static const char *const names[] = {"global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win"};
+    static const char *const names[] = {"global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win", "g_coop", "gwin_takes_b2"};
     for (const char *n : names) {                  // IAS_OPT_GWIN_WIN=4096 etc.
         char env[64] = "IAS_OPT_";
         size_t k = strlen(env);

@@ -359,7 +359,10 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         if (!rw.tiny_identity) { bl.list.p = rw.tiny_list.release(); bl.offset[BIN_T] = 0; }
     } else {
         IAS_CUDA(cudaMemsetAsync(rw.hist.p, 0, 16 * sizeof(unsigned long long), c.stream));
-        IAS_LAUNCH(k_classify_num, grid_for(n, 256), 256, 0, n, rw.ub.p + b0, rw.nnz_row.p + b0, rw.bin.p + b0, rw.hist.p);
+        // rows the windowed kernel handles in one rank window go there instead of the large CTA hash (hash insert +
+        // block radix sort cost more per product than mark + rank when the whole column space is one super-window)
+        const int b2_max = use_gwin(rw) && gwin_numeric_pays(ncols_b) && c.tune.gwin_takes_b2 ? NUM_B1_NNZ : NUM_B2_NNZ;
+        IAS_LAUNCH(k_classify_num, grid_for(n, 256), 256, 0, n, rw.ub.p + b0, rw.nnz_row.p + b0, rw.bin.p + b0, rw.hist.p, b2_max);
         IAS_TRY(read_hist(rw, NBINS + 2, h));
         for (int b = 0; b < NBINS; ++b) rw.num_hist[b] += h[b];
         IAS_TRY(build_bin_lists(n, rw.bin.p + b0, h, bl));
@@ -461,7 +464,8 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
                                                                // B-row stream: ncu/clock64 showed the mark pass 1.6x slower)
             size_t sm = (size_t)win * sizeof(double);
             IAS_TRY(opt_in_smem(k, sm));
-            const int smem_mark = rw.b_canonical && c.tune.global_rows_smem != 0 && (win % 16) == 0;
+            int smem_mark = rw.b_canonical && c.tune.global_rows_smem != 0 && (win % 16) == 0 ? 1 : 0;      // bit 0: mark pass in smem
+            if (rw.b_canonical && c.tune.g_coop) smem_mark |= 2;                                            // bit 1: accumulate via gwin_build / gwin_run
             IAS_LAUNCH(k, rw.gslots, 1024, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p, GLayout::make(ncols_b),
                        rw.cursor.p, win, rw.b_canonical, smem_mark, ncols_b);
         }

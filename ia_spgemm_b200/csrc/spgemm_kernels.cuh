@@ -50,13 +50,14 @@ __host__ __device__ __forceinline__ int sym_bin_of(long long ub)
     if (ub <= SYM_B2_UB) return BIN_B2;
     return BIN_G;
 }
-__host__ __device__ __forceinline__ int num_bin_of(int ub, int nnz)
+// b2_max: largest nnz(C_i) the large CTA hash takes (NUM_B2_NNZ, or NUM_B1_NNZ when the windowed kernel is cheaper)
+__host__ __device__ __forceinline__ int num_bin_of(int ub, int nnz, int b2_max = NUM_B2_NNZ)
 {
     if (nnz == 0) return BIN_EMPTY;
     if (ub <= T_MAX) return BIN_T;
     if (ub <= NUM_W_UB) return BIN_W;                 // expand-sort-compress in registers holds every product
     if (nnz <= NUM_B1_NNZ) return BIN_B1;
-    if (nnz <= NUM_B2_NNZ) return BIN_B2;
+    if (nnz <= b2_max) return BIN_B2;
     return BIN_G;
 }
 
@@ -280,7 +281,8 @@ __global__ void __launch_bounds__(256) k_row_ub_long(const int *__restrict__ lon
 // numeric bins from exact counts; also the largest nnz(C_i) among tiny rows (sizes k_num_tiny's smem)
 static __global__ void __launch_bounds__(256) k_classify_num(int nrows, const int *__restrict__ ub, const int *__restrict__ nnz_row,
                                                       unsigned char *__restrict__ bin_out,
-                                                      unsigned long long *__restrict__ g_hist /*NBINS+2: [NBINS]=max tiny nnz, [NBINS+1]=max nnz*/)
+                                                      unsigned long long *__restrict__ g_hist /*NBINS+2: [NBINS]=max tiny nnz, [NBINS+1]=max nnz*/,
+                                                      int b2_max)
 {
     __shared__ unsigned s_cnt[NBINS];
     __shared__ int s_max[2];
@@ -292,7 +294,7 @@ static __global__ void __launch_bounds__(256) k_classify_num(int nrows, const in
     int bin = -1, n = 0;
     if (li < nrows) {
         n = nnz_row[li];
-        bin = num_bin_of(ub[li], n);
+        bin = num_bin_of(ub[li], n, b2_max);
         bin_out[li] = (unsigned char)bin;
     }
 #pragma unroll
@@ -1219,7 +1221,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
         // 1. mark the columns of the row.  Canonical B: in shared memory, one super-window of 2*win*32 columns at a
         //    time (the bitmap borrows the accumulate tile), each flushed to the row's cells with coalesced stores --
         //    no L2 atomic per product (that pass was 38 % of this kernel at R-MAT scale 22).
-        if (smem_mark) {
+        if (smem_mark & 1) {
             unsigned *bits = reinterpret_cast<unsigned *>(smem_raw);
             const int swords = win * 2;                                  // 32-bit words in the tile's bytes
             const long long span = (long long)swords * 32;
@@ -1340,7 +1342,15 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
                     atomicAdd(&acc[(int)(cell[u].y + __popc(below)) - wbase], x[u]);
                 }
             };
-            if (b_canonical && n > win) cta_products<true, BLOCK>(A, B, pa, pe, tile, add, ColumnWindow<BV>{B, c_lo, c_hi});
+            if (smem_mark & 2) {
+                // canonical B: warp-wide lower bounds for short A rows, whole-trip fast path (see gwin_build / gwin_run)
+                const bool cut = n > win;
+                for (typename AV::off_t base = pa; base < pe; base += BLOCK) {
+                    const int total = gwin_build<true, BLOCK>(A, B, base, pe, tile, cut ? c_lo : 0, cut ? c_hi : 0x7fffffff);
+                    if (total) gwin_run<true, BLOCK>(tile, total, add);
+                    __syncthreads();
+                }
+            } else if (b_canonical && n > win) cta_products<true, BLOCK>(A, B, pa, pe, tile, add, ColumnWindow<BV>{B, c_lo, c_hi});
             else cta_products<true, BLOCK>(A, B, pa, pe, tile, add);
             __syncthreads();
             for (int t = threadIdx.x; t < wn; t += BLOCK) c_v[gs + wbase + t] = acc[t];

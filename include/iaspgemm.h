@@ -122,7 +122,7 @@ long long ias_kernel_launches(void);            /* engine kernels launched since
 /* Kernel-selection knobs (the reference has none: it hard-codes its library calls, GPU/main.cu:470-521).
  * Names: "global_rows_smem" (1 = windowed shared-memory kernels for rows beyond the CTA hash, 0 = L2 bitmap kernels),
  * "gwin_swords", "gwin_win", "gwin_sym_swords" (window sizes, 0 = automatic), "gwin_smem_kb", "gwin_max_sw" (numeric windowed
- * kernel only up to this many column super-windows per row, 0 = no limit), "g_win" (accumulate window of the L2 kernel).  Also read from
+ * kernel only up to this many column super-windows per row, 0 = no limit), "g_win" (accumulate window of the L2 kernel), "g_coop", "gwin_takes_b2" (0/1 switches kept for A/B runs).  Also read from
  * IAS_OPT_<NAME> in the environment by ias_init.  Results do not depend on any of them. */
 int ias_set_option(const char *name, long long value);
 int ias_get_option(const char *name, long long *value);

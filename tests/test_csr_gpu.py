@@ -138,12 +138,21 @@ def test_uniform_warp_bin(eng, oracle):
     assert st["sym_bin_rows"][2] == 30000
 
 
-@pytest.mark.parametrize("scale", [10, 13])
-def test_rmat_all_bins(eng, oracle, scale):
+@pytest.mark.parametrize("scale,takes_b2", [(10, 1), (13, 1), (13, 0)])
+def test_rmat_all_bins(eng, oracle, scale, takes_b2):
     A = W.rmat(scale, 16, seed=1)
-    got, st = _check(eng, oracle, A, mag=False)
+    saved = eng.get_option("gwin_takes_b2")
+    eng.set_option("gwin_takes_b2", takes_b2)
+    try:
+        got, st = _check(eng, oracle, A, mag=False)
+    finally:
+        eng.set_option("gwin_takes_b2", saved)
     if scale == 13:
-        assert st["sym_bin_rows"][5] > 0 and st["num_bin_rows"][4] > 0      # global + large CTA bins exercised
+        assert st["sym_bin_rows"][5] > 0
+        if takes_b2:      # one super-window: rows beyond the small CTA hash go to the windowed kernel
+            assert st["num_bin_rows"][4] == 0 and st["num_bin_rows"][5] > 0
+        else:             # global + large CTA bins exercised
+            assert st["num_bin_rows"][4] > 0
 
 
 def test_rmat_forced_global_bin(eng, oracle):
@@ -264,7 +273,7 @@ def test_wide_column_space_uses_64bit_sort_keys(eng, oracle):
 
 
 # ---------------------------------------------------------------- global rows: windowed shared-memory kernels
-_GWIN_OPTS = ("global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win")
+_GWIN_OPTS = ("global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win", "g_coop", "gwin_takes_b2")
 
 
 @pytest.fixture
@@ -301,8 +310,8 @@ def test_global_rows_windowed_kernels(eng, oracle, options, kind, swords, win, s
 
 
 @pytest.mark.parametrize("kind", ["few_a_entries", "mid_a_entries", "long_a_rows"])
-@pytest.mark.parametrize("g_win", [20480, 4096, 64])
-def test_global_rows_l2_kernel_with_shared_memory_mark(eng, oracle, options, kind, g_win):
+@pytest.mark.parametrize("g_win,g_coop", [(20480, 1), (4096, 1), (64, 1), (4096, 0)])
+def test_global_rows_l2_kernel_with_shared_memory_mark(eng, oracle, options, kind, g_win, g_coop):
     """Wide column spaces keep the L2 bitmap/rank kernel for the numeric pass, with its mark pass done in shared
     memory one super-window (64 * g_win columns) at a time and flushed to the row's cells."""
     A, B = _global_operands(kind)
@@ -310,6 +319,7 @@ def test_global_rows_l2_kernel_with_shared_memory_mark(eng, oracle, options, kin
     options("gwin_swords", 32)
     options("gwin_max_sw", 1)              # 32 * 32 columns per super-window: the windowed numeric kernel is refused
     options("g_win", g_win)
+    options("g_coop", g_coop)
     got, st = _check(eng, oracle, A, B, mag=False)
     assert st["num_bin_rows"][5] > 0
 

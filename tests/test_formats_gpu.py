@@ -342,9 +342,12 @@ def test_ell_and_coo_views_through_every_bin(eng, oracle):
     """The CTA / global kernels are templated on the operand view: run them on ELL (fixed width) and COO
     (64-bit row offsets) operands that populate the CTA bins (R-MAT scale 13) and the global bin (a dense-ish
     rectangular product)."""
-    cases = [(W.rmat(13, 16, seed=5), None, (3, 4)),
-             (W.random_sparse(40, 300, 0.9, seed=3), W.random_sparse(300, 40000, 0.4, seed=4), (5,))]
-    for A, B, bins in cases:
+    R13 = W.rmat(13, 16, seed=5)
+    cases = [(R13, None, (3, 4), 0),        # large CTA hash kept for its rows
+             (R13, None, (3, 5), 1),        # default: those rows go to the windowed shared-memory kernel
+             (W.random_sparse(40, 300, 0.9, seed=3), W.random_sparse(300, 40000, 0.4, seed=4), (5,), 1)]
+    for A, B, bins, takes_b2 in cases:
+        eng.set_option("gwin_takes_b2", takes_b2)
         B = A if B is None else B
         dA = eng.upload(*A)
         dB = dA if B is A else eng.upload(*B)
@@ -374,3 +377,4 @@ def test_ell_and_coo_views_through_every_bin(eng, oracle):
         if B is not A:
             eng.free_ell(eb); dB.close()
         dA.close()
+    eng.set_option("gwin_takes_b2", 1)
