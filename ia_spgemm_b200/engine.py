@@ -259,6 +259,17 @@ class Engine:
         """Kernel-selection knob (include/iaspgemm.h: ias_set_option); results never depend on it."""
         self._ck(self.lib.ias_set_option(name.encode(), int(value)))
 
+    def global_numeric_kernel(self, cols, b_canonical=True):
+        """Name of the kernel that takes the rows beyond the CTA hash (mirrors gwin_numeric_pays in spgemm_host.cuh)."""
+        if not b_canonical or not self.get_option("global_rows_smem"):
+            return "k_num_global"
+        words = ((cols + 31) // 32 + 31) // 32 * 32
+        sw = self.get_option("gwin_swords") or 8192
+        sw = max(32, (sw + 31) // 32 * 32)
+        nsw = (words + sw - 1) // sw
+        mx = self.get_option("gwin_max_sw")
+        return "k_num_gwin" if (mx == 0 or nsw <= mx) else "k_num_global"
+
     def get_option(self, name):
         v = C.c_longlong()
         self._ck(self.lib.ias_get_option(name.encode(), C.byref(v)))
