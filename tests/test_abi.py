@@ -135,3 +135,23 @@ def test_loader_agrees_with_oracle_on_random_files(lib, oracle, tmp_path):
         assert got[:2] == want[:2]
         for a, b in zip(got[2:], want[2:]):
             assert np.array_equal(a, b)
+
+
+def test_options_round_trip_without_a_device(lib):
+    """ias_set_option / ias_get_option are host-only bookkeeping: every documented knob exists, unknown names and
+    negative values are refused (status 2 = IAS_E_ARG), and nothing needs a GPU."""
+    names = ["global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win",
+             "g_coop", "gwin_takes_b2"]
+    header = open(os.path.join(ROOT, "include", "iaspgemm.h")).read()
+    for n in names:
+        assert '"%s"' % n in header, n            # documented where the entry point is declared
+        old = C.c_longlong(-1)
+        assert lib.ias_get_option(n.encode(), C.byref(old)) == 0 and old.value >= 0
+        assert lib.ias_set_option(n.encode(), 7) == 0
+        v = C.c_longlong(-1)
+        assert lib.ias_get_option(n.encode(), C.byref(v)) == 0 and v.value == 7
+        assert lib.ias_set_option(n.encode(), old.value) == 0
+    assert lib.ias_set_option(b"no_such_knob", 1) == 2
+    assert b"no_such_knob" in lib.ias_last_error()
+    assert lib.ias_set_option(b"gwin_win", -5) == 2
+    assert b"negative" in lib.ias_last_error()
