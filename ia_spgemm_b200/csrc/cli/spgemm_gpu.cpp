@@ -5,6 +5,7 @@
 //   spgemm-gpu A.mtx B.mtx [mode]    C = A*B; mode != 0 dumps the operands like testing_mode (CPU/main.cpp:489-497)
 //   options: --all (run every format as the reference does), --json, --gate X (default 20, GPU release),
 //            --repeat N (best of N timed runs after one warm-up; the reference times one cold run),
+//            --opt NAME=VALUE (kernel-selection knob, ias_set_option), --help,
 //            --transpose-b (B := A^T, what GPU/main.cu:261-269 computes), --write-c FILE (CSR result as .mtx),
 //            --matnet FILE.h5 (select with the reference's MatNet weights, e.g. NetWeights/Intel_weights.h5 or
 //            P100_weights.h5; without it a rule on the feature vector picks the format)
@@ -70,9 +71,23 @@ int main(int argc, char **argv)
     std::string write_c, matnet_path;
     double gate = 20.0;
     int repeat = 1;
+    std::vector<std::pair<std::string, long long> > opts;       // --opt name=value -> ias_set_option
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
-        if (a == "--all") all = true;
+        if (a == "--help" || a == "-h") {
+            printf("usage: spgemm-gpu A.mtx [B.mtx [testing_mode]] [--all] [--json] [--gate X] [--repeat N] [--transpose-b]\n"
+                   "                  [--write-c FILE.mtx] [--matnet WEIGHTS.h5] [--opt NAME=VALUE ...]\n"
+                   "  --opt NAME=VALUE   kernel-selection knob of the engine (ias_set_option, include/iaspgemm.h), e.g.\n"
+                   "                     global_rows_smem=0, gwin_max_sw=0; the result does not depend on it\n");
+            return 0;
+        }
+        if (a == "--opt" && i + 1 < argc) {
+            std::string kv = argv[++i];
+            size_t eq = kv.find('=');
+            if (eq == std::string::npos || eq == 0 || eq + 1 >= kv.size()) { printf("--opt expects NAME=VALUE, got '%s'\n", kv.c_str()); return -6; }
+            opts.push_back(std::make_pair(kv.substr(0, eq), atoll(kv.c_str() + eq + 1)));
+        }
+        else if (a == "--all") all = true;
         else if (a == "--json") json = true;
         else if (a == "--transpose-b") transpose_b = true;
         else if (a == "--write-c" && i + 1 < argc) write_c = argv[++i];
@@ -81,6 +96,8 @@ int main(int argc, char **argv)
         else if (a == "--repeat" && i + 1 < argc) repeat = atoi(argv[++i]);
         else pos.push_back(a);
     }
+    for (size_t o = 0; o < opts.size(); ++o)
+        if (ias_set_option(opts[o].first.c_str(), opts[o].second)) { printf("%s\n", ias_last_error()); return -6; }
     if (pos.empty()) {
         printf("please use command like this : ./spgemm-gpu ./sample.mtx\n");
         return -1;
