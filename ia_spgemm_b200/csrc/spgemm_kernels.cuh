@@ -11,15 +11,21 @@
 //                              counted on the spot with the k-way merge (kept if B turns out canonical)
 //   symbolic  k_sym_tiny       ub <= 32       thread per row: cursor merge (canonical B) or private list
 //             k_sym_hash       ub <= 24576    warp / CTA per row, shared-memory hash of column keys
-//             k_sym_global     larger         persistent CTA per row, {bitmap, rank} cells in global memory (L2)
+//             k_sym_gwin       larger         canonical B: persistent CTA per row, bitmap of a column super-window in
+//                                             shared memory, only the part of each sorted B row inside it is visited
+//             k_sym_global     larger         otherwise: {bitmap, rank} cells in global memory (L2)
 //   scan      cub ExclusiveSum over nnz(C_i) -> 64-bit row pointers
 //   numeric   k_num_tiny       ub <= 32       thread per row k-way merge, rows staged in smem, coalesced copy-out
 //             k_esc_warp       ub <= 512      warp per row: expand - bitonic sort in registers - compress
 //             k_num_hash_cta   nnz <= 12288   CTA per row: shared-memory hash SPA, block radix sort of
 //                                             (column, slot), striped coalesced write
-//             k_num_global     larger         bitmap + rank: mark columns, prefix-popcount, emit sorted columns,
-//                                             accumulate windows of ranks in a dense shared-memory tile
-//   products are enumerated by warp_products (one warp) / cta_products (balanced over a CTA, 4 per lane and trip)
+//             k_num_gwin       nnz > 4096     canonical B and a column space of one super-window (<= 262 144 columns):
+//                                             {bitmap, rank} cells + rank window in shared memory, no global workspace
+//             k_num_global     larger         bitmap + rank cells in an L2-resident slot: mark columns (in shared memory
+//                                             when B is canonical), prefix-popcount, emit sorted columns, accumulate
+//                                             windows of ranks in a dense shared-memory tile
+//   products are enumerated by warp_products (one warp) / cta_products (balanced over a CTA, 4 per lane and trip) /
+//   gwin_build + gwin_run (the same balance over B-row segments restricted to a column window)
 // No intermediate product is ever materialised in global memory (the reference's ESC chain writes
 // 24 B per product, csr_dev:170,190-194).
 #pragma once
