@@ -309,6 +309,7 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
         size_t dyn = 0;
         IAS_TRY(gwin_dyn_max(k, &dyn));
         int swords = std::min(words_of(ncols_b), (int)(dyn / 4) & ~31);
+        if (swords < 32) return fail(IAS_E_ARG, "gwin_smem_kb leaves %zu bytes of shared memory: too little for a bitmap window", dyn);
         if (c.tune.gwin_sym_swords > 0) swords = std::min<long long>(swords, std::max<long long>(32, (c.tune.gwin_sym_swords + 31) & ~31LL));
         size_t sm = (size_t)swords * 4;
         IAS_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));   // static + dynamic may exceed 48 KB
@@ -441,6 +442,9 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         int swords = (int)std::min<long long>(words_of(ncols_b), sw_cap);
         // split-point table (one int per A entry and super-window boundary) only when there are several super-windows
         int tbl_cap = words_of(ncols_b) > swords ? 4096 : 0;
+        if (swords < 32) return fail(IAS_E_ARG, "gwin_smem_kb leaves %zu bytes of shared memory: too little for a cell window", dyn);
+        if (dyn < (size_t)swords * 8 + (size_t)tbl_cap * 4 + 64 * 12) tbl_cap = 0;          // a tight budget drops the split table first
+        if (dyn < (size_t)swords * 8 + 32 * 12) return fail(IAS_E_ARG, "gwin_smem_kb leaves %zu bytes of shared memory: too little for a rank window", dyn);
         int win = (int)((dyn - (size_t)swords * 8 - (size_t)tbl_cap * 4) / 12) & ~31;
         if (c.tune.gwin_win > 0) win = (int)std::min<long long>(win, std::max<long long>(32, c.tune.gwin_win & ~31LL));
         size_t sm = (size_t)swords * 8 + (size_t)win * 12 + (size_t)tbl_cap * 4;
