@@ -7,15 +7,17 @@
 //            --repeat N (best of N timed runs after one warm-up; the reference times one cold run),
 //            --opt NAME=VALUE (kernel-selection knob, ias_set_option), --help,
 //            --transpose-b (B := A^T, what GPU/main.cu:261-269 computes), --write-c FILE (CSR result as .mtx),
-//            --matnet FILE.h5 (select with the reference's MatNet weights, e.g. NetWeights/Intel_weights.h5 or
-//            P100_weights.h5; without it a rule on the feature vector picks the format)
+//            --matnet FILE.h5 (MatNet weights; default: ./NetWeights/Intel_weights.h5 and ./NetWeights/P100_weights.h5
+//            when present, the paths CPU/MatNet.py:81 and GPU/MatNet.py load), --no-matnet (rule on the features),
+//            --stream [GB] (CSR result produced in HBM-budgeted row batches; taken automatically when C does not fit)
 //
 // Same stages as the reference main: Matrix-Market load -> density images ./imgs/img{1,2}.txt ->
-// 26 features -> format selection -> multiply -> report block (Appendix A of SURVEY.md: run_time,
+// 26 features -> MatNet format selection -> multiply -> report block (Appendix A of SURVEY.md: run_time,
 // trans_time, memory_size, verified_sum, Gflops, Speedup).  Differences, all deliberate (SURVEY
 // appendix D): file values are kept (GPU/main.cu:236-243 overwrites them with rand()%10), B := A
-// rather than A^T, and the selector is a rule on the feature vector until MatNet inference lands
-// (the reference only prints MatNet's pick and then runs everything anyway).
+// rather than A^T, the selected algorithm is the one that runs (the reference only prints MatNet's pick and
+// then runs everything anyway; --all does that), and MatNet.Pred is the engine's native forward pass
+// (ias_matnet_*) instead of embedded CPython + Keras.  Without weight files a rule on the feature vector selects.
 // Host code only: everything numeric goes through the C ABI of libiaspgemm.so.
 #include <stdio.h>
 #include <stdlib.h>
@@ -64,10 +66,49 @@ static int select_format(const double *f, bool dia_ok, bool ell_ok)
     return 1;
 }
 
+static bool file_exists(const char *p)
+{
+    struct stat st;
+    return stat(p, &st) == 0 && S_ISREG(st.st_mode);
+}
+
+// consumer of a streamed CSR result: appends the batch to an open .mtx file (entries only; the size line was
+// written from nnz_total before the first batch)
+struct MtxAppend {
+    FILE *f;
+    bool header_done;
+    int rows, cols;
+    std::vector<long long> rp;
+    std::vector<int> ci;
+    std::vector<double> v;
+};
+
+static int append_batch(const IasStreamBatch *b, void *user)
+{
+    MtxAppend *w = (MtxAppend *)user;
+    if (!w->f) return 0;
+    if (!w->header_done) {
+        fprintf(w->f, "%%%%MatrixMarket matrix coordinate real general\n%d %d %lld\n", w->rows, w->cols, b->nnz_total);
+        w->header_done = true;
+    }
+    int n = b->row_end - b->row_begin;
+    w->rp.resize((size_t)n + 1); w->ci.resize((size_t)b->batch_nnz); w->v.resize((size_t)b->batch_nnz);
+    if (ias_copy(w->rp.data(), b->row_ptr_dev, sizeof(long long) * ((size_t)n + 1), 1)) return IAS_E_CUDA;
+    if (b->batch_nnz) {
+        if (ias_copy(w->ci.data(), b->col_ind_dev, sizeof(int) * (size_t)b->batch_nnz, 1)) return IAS_E_CUDA;
+        if (ias_copy(w->v.data(), b->values_dev, sizeof(double) * (size_t)b->batch_nnz, 1)) return IAS_E_CUDA;
+    }
+    for (int i = 0; i < n; ++i)
+        for (long long p = w->rp[i] - b->entry_base; p < w->rp[i + 1] - b->entry_base; ++p)
+            fprintf(w->f, "%d %d %.17g\n", b->row_begin + i + 1, w->ci[p] + 1, w->v[p]);
+    return ferror(w->f) ? IAS_E_IO : 0;
+}
+
 int main(int argc, char **argv)
 {
     std::vector<std::string> pos;
-    bool all = false, json = false, transpose_b = false;
+    bool all = false, json = false, transpose_b = false, no_matnet = false, force_stream = false;
+    double stream_gb = 0.0;
     std::string write_c, matnet_path;
     double gate = 20.0;
     int repeat = 1;
@@ -76,7 +117,9 @@ int main(int argc, char **argv)
         std::string a = argv[i];
         if (a == "--help" || a == "-h") {
             printf("usage: spgemm-gpu A.mtx [B.mtx [testing_mode]] [--all] [--json] [--gate X] [--repeat N] [--transpose-b]\n"
-                   "                  [--write-c FILE.mtx] [--matnet WEIGHTS.h5] [--opt NAME=VALUE ...]\n"
+                   "                  [--write-c FILE.mtx] [--matnet WEIGHTS.h5 | --no-matnet] [--stream [GB]] [--opt NAME=VALUE ...]\n"
+                   "  --matnet FILE      MatNet weights (default: ./NetWeights/Intel_weights.h5, ./NetWeights/P100_weights.h5 when present)\n"
+                   "  --stream [GB]      CSR result in HBM-budgeted row batches (automatic when C does not fit the device)\n"
                    "  --opt NAME=VALUE   kernel-selection knob of the engine (ias_set_option, include/iaspgemm.h), e.g.\n"
                    "                     global_rows_smem=0, gwin_max_sw=0; the result does not depend on it\n");
             return 0;
@@ -92,6 +135,11 @@ int main(int argc, char **argv)
         else if (a == "--transpose-b") transpose_b = true;
         else if (a == "--write-c" && i + 1 < argc) write_c = argv[++i];
         else if (a == "--matnet" && i + 1 < argc) matnet_path = argv[++i];
+        else if (a == "--no-matnet") no_matnet = true;
+        else if (a == "--stream") {
+            force_stream = true;
+            if (i + 1 < argc && (argv[i + 1][0] == '.' || (argv[i + 1][0] >= '0' && argv[i + 1][0] <= '9')) && !strstr(argv[i + 1], ".mtx")) stream_gb = atof(argv[++i]);
+        }
         else if (a == "--gate" && i + 1 < argc) gate = atof(argv[++i]);
         else if (a == "--repeat" && i + 1 < argc) repeat = atoi(argv[++i]);
         else pos.push_back(a);
@@ -161,24 +209,37 @@ int main(int argc, char **argv)
     bool dia_ok = a_dia.choice && b_dia.choice, ell_ok = a_ell.choice && b_ell.choice;
 
     int c = select_format(feat, dia_ok, ell_ok);
-    if (!matnet_path.empty()) {
-        // MatNet.Pred (CPU/MatNet.py:24-96) on the two density images and the feature vector
+    // MatNet.Pred (CPU/MatNet.py:24-96, GPU/MatNet.py) on the two density images and the feature vector.  The reference
+    // always loads ./NetWeights/<machine>_weights.h5 from the working directory; so does this front end when the files
+    // are there.  A 5-class (CPU) net drives the format dispatch; the 3-class (GPU) net names a library SpGEMM, all of
+    // which are the engine's CSR pipeline, and its line is printed as GPU/main.cu:543-544 does.
+    std::vector<std::string> nets;
+    if (!matnet_path.empty()) nets.push_back(matnet_path);
+    else if (!no_matnet) {
+        if (file_exists("./NetWeights/Intel_weights.h5")) nets.push_back("./NetWeights/Intel_weights.h5");
+        if (file_exists("./NetWeights/P100_weights.h5")) nets.push_back("./NetWeights/P100_weights.h5");
+    }
+    bool dispatched = false;
+    for (size_t ni = 0; ni < nets.size(); ++ni) {
         void *net = nullptr;
-        if (ias_matnet_load(matnet_path.c_str(), &net)) return die("MatNet weights");
+        if (ias_matnet_load(nets[ni].c_str(), &net)) return die("MatNet weights");
         int nf = 0, nc = 0, cls = 0;
         double probs[8] = {0};
         ias_matnet_shape(net, &nf, &nc, nullptr);
         if (ias_matnet_predict(net, img.data(), img_b.data(), feat, &cls, probs)) return die("MatNet.Pred");
         ias_matnet_free(net);
         if (nc == 5) {                         // CPU nets: 0 MKL 1 CSR 2 DIA 3 ELL 4 COO (the engine runs its CSR path for the MKL slot)
-            c = cls == 0 ? 1 : cls;
-            if ((c == 2 && !dia_ok) || (c == 3 && !ell_ok)) c = 1;      // the size gate refused the format MatNet asked for
+            if (!dispatched) {
+                c = cls == 0 ? 1 : cls;
+                if ((c == 2 && !dia_ok) || (c == 3 && !ell_ok)) c = 1;      // the size gate refused the format MatNet asked for
+                dispatched = true;
+            }
         } else {                               // GPU net: CUSP / cuSPARSE / NSPARSE are all CSR SpGEMMs -> the engine's CSR pipeline
             static const char *names[3] = {"CUSP", "cuSPARSE", "NSPARSE"};
             printf("MatNet predicts Algorithm %s is optimal\n", names[cls < 3 ? cls : 0]);
-            c = 1;
+            if (!dispatched && nets.size() == 1) c = 1;
         }
-        printf("MatNet class %d of %d (p = %.4f)\n", cls, nc, probs[cls]);
+        printf("MatNet class %d of %d (p = %.4f) [%s]\n", cls, nc, probs[cls], nets[ni].c_str());
     }
     printf("The Chosen One = Algorithm %d\n", c + 1);
 
@@ -186,12 +247,30 @@ int main(int argc, char **argv)
     // repeat == 1: one cold run, as the reference times it; repeat > 1: one warm-up, then the best of `repeat`
     const int runs = repeat > 1 ? repeat + 1 : 1;
     auto keep = [&](int r, double t, double &best) { if (r == (runs > 1 ? 1 : 0) || (r > 0 && t < best)) best = t; };
-    // Algorithm 2: CSR
+    // Algorithm 2: CSR.  A result that does not fit the device (IAS_E_NOMEM) is produced in HBM-budgeted row batches
+    // instead: checksum, nnz and the optional .mtx output come from the batch consumer.
+    bool streamed = false;
+    int stream_batches = 0;
     if (want(1)) {
         for (int r = 0; r < runs; ++r) {
             IasCsr64Dev C;
             IasSpgemmStats st;
-            if (ias_csr_mul_csr_dev64(&dA, &dB, &C, &st)) return die("CSR_MUL_CSR_DEV");
+            int mrc = force_stream ? IAS_E_NOMEM : ias_csr_mul_csr_dev64(&dA, &dB, &C, &st);
+            if (mrc == IAS_E_NOMEM) {
+                MtxAppend w;
+                w.f = nullptr; w.header_done = false; w.rows = dA.row; w.cols = dB.col;
+                if (r == runs - 1 && !write_c.empty() && !(w.f = fopen(write_c.c_str(), "w"))) { printf("cannot open %s\n", write_c.c_str()); return -7; }
+                if (ias_csr_mul_csr_stream_cb(&dA, &dB, 0, dA.row, (size_t)(stream_gb * 1e9), nullptr, append_batch, &w, &st)) return die("CSR_MUL_CSR_DEV (streamed)");
+                if (w.f) {
+                    if (!w.header_done) fprintf(w.f, "%%%%MatrixMarket matrix coordinate real general\n%d %d 0\n", w.rows, w.cols);
+                    if (fclose(w.f) != 0) { printf("write to %s failed\n", write_c.c_str()); return -7; }
+                }
+                streamed = true; stream_batches = st.batches;
+                keep(r, st.ms_total, run[1]);
+                if (r == runs - 1) { sum[1] = st.checksum; size[1] = ias_sizeof_csr(dA.row, st.nnz); }
+                continue;
+            }
+            if (mrc) return die("CSR_MUL_CSR_DEV");
             keep(r, st.ms_total, run[1]);
             if (r == runs - 1) {
                 ias_checksum(C.values_dev, C.nnz, &sum[1]); size[1] = ias_sizeof_csr(C.row, C.nnz);
@@ -199,7 +278,7 @@ int main(int argc, char **argv)
             }
             ias_free_csr64_dev(&C);
         }
-        printf("DONE CSR\n");
+        printf(streamed ? "DONE CSR (streamed in %d row batches)\n" : "DONE CSR\n", stream_batches);
     }
     // Algorithm 3: DIA
     if (want(2) && dia_ok) {

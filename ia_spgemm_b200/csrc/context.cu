@@ -56,6 +56,7 @@ static long long *option_slot(const char *name)
     if (!strcmp(name, "g_win")) return &t.g_win;
     if (!strcmp(name, "g_coop")) return &t.g_coop;
     if (!strcmp(name, "gwin_takes_b2")) return &t.gwin_takes_b2;
+    if (!strcmp(name, "trust_operand_cache")) return &t.trust_operand_cache;
     return nullptr;
 }
 
@@ -71,6 +72,16 @@ int ias_init(int device)
     }
     if (device < 0 || device >= n) return fail(IAS_E_ARG, "device %d out of range (have %d)", device, n);
     IAS_CUDA(cudaSetDevice(device));
+    if (c.ready && c.device != device) {
+        // re-bound to another device: streams and events belong to the device they were created on
+        if (c.own_stream) cudaStreamDestroy(c.own_stream);
+        c.own_stream = nullptr;
+        for (int i = 0; i < 8; ++i) { if (c.ev[i]) cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
+        for (int i = 0; i < 32; ++i) { if (c.ev_bin[i]) cudaEventDestroy(c.ev_bin[i]); c.ev_bin[i] = nullptr; }
+        c.canon_ci = c.canon_rp = nullptr; c.canon_rows = c.canon_nnz = -1;
+        c.ready = false;
+        cudaGetLastError();
+    }
     c.device = device;
     cudaDeviceProp p;
     IAS_CUDA(cudaGetDeviceProperties(&p, device));
@@ -86,7 +97,8 @@ int ias_init(int device)
     for (int i = 0; i < 32; ++i)
         if (!c.ev_bin[i]) IAS_CUDA(cudaEventCreate(&c.ev_bin[i]));
     if (!c.h_scalars) IAS_CUDA(cudaMallocHost((void **)&c.h_scalars, 64 * sizeof(long long)));
-    static const char *const names[] = {"global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win", "g_coop", "gwin_takes_b2"};
+    static const char *const names[] = {"global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win", "g_coop", "gwin_takes_b2",
+                                        "trust_operand_cache"};
     for (const char *n : names) {                  // IAS_OPT_GWIN_WIN=4096 etc.
         char env[64] = "IAS_OPT_";
         size_t k = strlen(env);
@@ -119,7 +131,14 @@ int ias_get_option(const char *name, long long *value)
 int ias_set_stream(void *s)
 {
     IAS_TRY(ensure_init());
-    ctx().stream = s ? (cudaStream_t)s : ctx().own_stream;
+    ctx().stream = (cudaStream_t)s;          // NULL is the legacy default stream (what torch's default stream handle is)
+    return IAS_OK;
+}
+
+int ias_use_own_stream(void)
+{
+    IAS_TRY(ensure_init());
+    ctx().stream = ctx().own_stream;
     return IAS_OK;
 }
 
@@ -168,7 +187,7 @@ int ias_upload_csr(const IasCsrMatrix *h, IasCsrMatrixDev *d)
 int ias_forget_operand(const IasCsrMatrixDev *m)
 {
     Ctx &c = ctx();
-    if (!m || c.canon_ci == (const void *)m->col_ind_dev) { c.canon_ci = nullptr; c.canon_rows = c.canon_nnz = -1; }
+    if (!m || c.canon_ci == (const void *)m->col_ind_dev) { c.canon_ci = c.canon_rp = nullptr; c.canon_rows = c.canon_nnz = -1; }
     return IAS_OK;
 }
 

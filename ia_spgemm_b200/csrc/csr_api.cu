@@ -76,6 +76,12 @@ int ias_csr_mul_csr_dev(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, IasC
 int ias_csr_mul_csr_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, size_t budget_bytes,
                            int *row_nnz_dev, IasSpgemmStats *st)
 {
+    return ias_csr_mul_csr_stream_cb(A, B, r0, r1, budget_bytes, row_nnz_dev, nullptr, nullptr, st);
+}
+
+int ias_csr_mul_csr_stream_cb(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, size_t budget_bytes,
+                              int *row_nnz_dev, ias_stream_consumer consumer, void *user, IasSpgemmStats *st)
+{
     IAS_TRY(ensure_init());
     IAS_TRY(check_operands(A, B, r0, r1));
     Ctx &c = ctx();
@@ -145,6 +151,17 @@ int ias_csr_mul_csr_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, i
         IAS_TRY(numeric_rows(av, bv, rw, b0, b1, B->col, out, ci.p, cv.p, &local));
         long long threads = (e1 - e0 + 15) / 16;
         IAS_LAUNCH(k_consume, grid_for(threads, 256), 256, 0, b1 - b0, r0 + b0, rp.p + b0, e0, ci.p, cv.p, d_hash.p, d_sum.p);
+        if (consumer) {
+            IasStreamBatch sb;
+            sb.row_begin = r0 + b0; sb.row_end = r0 + b1; sb.batch_index = b; sb.batch_count = h_nb;
+            sb.nnz_total = nnz; sb.entry_base = e0; sb.batch_nnz = e1 - e0;
+            sb.row_ptr_dev = rp.p + b0; sb.col_ind_dev = ci.p; sb.values_dev = cv.p; sb.cuda_stream = (void *)c.stream;
+            int crc = consumer(&sb, user);
+            if (crc != 0) {
+                cudaStreamSynchronize(c.stream);
+                return fail(crc, "stream consumer returned %d at batch %d of %d (rows [%d,%d))", crc, b, h_nb, sb.row_begin, sb.row_end);
+            }
+        }
     }
     IAS_CUDA(cudaEventRecord(c.ev[4], c.stream));
     IAS_CUDA(cudaMemcpyAsync(c.h_scalars + 42, d_hash.p, sizeof(long long), cudaMemcpyDeviceToHost, c.stream));

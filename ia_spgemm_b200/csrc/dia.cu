@@ -122,6 +122,16 @@ __global__ void __launch_bounds__(256) k_dia_to_row_major(int rows, int nd, cons
     out[t] = in[s * rows + i];
 }
 
+// the reference's row-major [i*nd + slot] -> diagonal-major
+__global__ void __launch_bounds__(256) k_dia_to_diag_major(int rows, int nd, const double *__restrict__ in, double *__restrict__ out)
+{
+    size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    size_t n = (size_t)rows * nd;
+    if (t >= n) return;
+    size_t s = t / rows, i = t % rows;
+    out[t] = in[i * nd + s];
+}
+
 int diag_census(const IasCsrMatrixDev *A, DBuf<int> &flags, DBuf<int> &slot_of, int *nd)
 {
     Ctx &c = ctx();
@@ -266,6 +276,33 @@ int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, do
     IAS_CUDA(cudaStreamSynchronize(s));
     if (elapsed_ms) { float ms = 0; cudaEventElapsedTime(&ms, c.ev[0], c.ev[1]); *elapsed_ms = ms; }
     C->diagonal_ind_dev = di.release(); C->diagonal_offsets_dev = off.release(); C->values_dev = val.release();
+    return IAS_OK;
+}
+
+int ias_dia_relayout(const IasDiaDev *in, int to_row_major, IasDiaDev *out)
+{
+    IAS_TRY(ensure_init());
+    if (!in || !out) return fail(IAS_E_ARG, "NULL");
+    if (!in->choice) return fail(IAS_E_GATE, "DIA matrix was rejected by the size gate");
+    Ctx &c = ctx();
+    IasDiaDev r = *in;
+    r.diagonal_ind_dev = nullptr; r.diagonal_offsets_dev = nullptr; r.values_dev = nullptr;
+    int span = std::max(in->row + in->col - 1, 1);
+    size_t n = (size_t)in->row * in->num_diagonals;
+    DBuf<int> di, off;
+    DBuf<double> val;
+    IAS_TRY(di.alloc((size_t)span));
+    IAS_TRY(off.alloc((size_t)std::max(in->num_diagonals, 1)));
+    IAS_TRY(val.alloc(n));
+    if (in->row + in->col - 1 > 0) IAS_CUDA(cudaMemcpyAsync(di.p, in->diagonal_ind_dev, sizeof(int) * (size_t)(in->row + in->col - 1), cudaMemcpyDeviceToDevice, c.stream));
+    if (in->num_diagonals) IAS_CUDA(cudaMemcpyAsync(off.p, in->diagonal_offsets_dev, sizeof(int) * (size_t)in->num_diagonals, cudaMemcpyDeviceToDevice, c.stream));
+    if (n) {
+        if (to_row_major) IAS_LAUNCH(k_dia_to_row_major, grid_for((long long)n, 256), 256, 0, in->row, in->num_diagonals, in->values_dev, val.p);
+        else IAS_LAUNCH(k_dia_to_diag_major, grid_for((long long)n, 256), 256, 0, in->row, in->num_diagonals, in->values_dev, val.p);
+    }
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    r.diagonal_ind_dev = di.release(); r.diagonal_offsets_dev = off.release(); r.values_dev = val.release();
+    *out = r;
     return IAS_OK;
 }
 

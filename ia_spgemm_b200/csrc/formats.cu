@@ -45,6 +45,12 @@ __global__ void __launch_bounds__(256) k_widen(int n, const int *__restrict__ in
     if (i < n) out[i] = in[i];
 }
 
+__global__ void __launch_bounds__(256) k_narrow(int n, const long long *__restrict__ in, int *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = (int)in[i];
+}
+
 // row index of every entry: each thread owns 16 consecutive entries (one binary search per thread)
 __global__ void __launch_bounds__(256) k_expand_rows(int nrows, const long long *__restrict__ rp, int *__restrict__ row_ind)
 {
@@ -130,7 +136,7 @@ int ias_free_ell_dev(IasEllDev *m)
     return IAS_OK;
 }
 
-int ias_ell_mul_ell_dev(const IasEllDev *A, const IasEllDev *B, IasEllDev *C, double *elapsed_ms)
+static int ell_mul(const IasEllDev *A, const IasEllDev *B, IasEll64Dev *C, double *elapsed_ms)
 {
     IAS_TRY(ensure_init());
     if (!A || !B || !C) return fail(IAS_E_ARG, "NULL");
@@ -176,6 +182,33 @@ int ias_ell_mul_ell_dev(const IasEllDev *A, const IasEllDev *B, IasEllDev *C, do
     return IAS_OK;
 }
 
+int ias_ell_mul_ell_dev64(const IasEllDev *A, const IasEllDev *B, IasEll64Dev *C, double *elapsed_ms)
+{
+    return ell_mul(A, B, C, elapsed_ms);
+}
+
+int ias_free_ell64_dev(IasEll64Dev *m)
+{
+    if (!m) return IAS_OK;
+    dfree(m->nnz_row_dev); dfree(m->col_ind_dev); dfree(m->values_dev);
+    m->nnz_row_dev = nullptr; m->col_ind_dev = nullptr; m->values_dev = nullptr;
+    return IAS_OK;
+}
+
+int ias_ell_mul_ell_dev(const IasEllDev *A, const IasEllDev *B, IasEllDev *C, double *elapsed_ms)
+{
+    if (!C) return fail(IAS_E_ARG, "NULL");
+    IasEll64Dev c64;
+    IAS_TRY(ell_mul(A, B, &c64, elapsed_ms));
+    if (c64.nnz > 0x7fffffffLL) {
+        ias_free_ell64_dev(&c64);
+        return fail(IAS_E_OVERFLOW, "nnz(C) = %lld does not fit the int32 EllMatrixDev layout; use ias_ell_mul_ell_dev64", c64.nnz);
+    }
+    C->choice = true; C->row = c64.row; C->col = c64.col; C->nnz = (int)c64.nnz; C->max_nnz_per_row = c64.max_nnz_per_row;
+    C->nnz_row_dev = c64.nnz_row_dev; C->col_ind_dev = c64.col_ind_dev; C->values_dev = c64.values_dev;
+    return IAS_OK;
+}
+
 int ias_download_ell(const IasEllDev *d, int *nnz_row, int *col_ind, double *values)
 {
     IAS_TRY(ensure_init());
@@ -198,16 +231,18 @@ int ias_csr_to_coo(const IasCsrMatrixDev *A, IasCooDev *out)
     Ctx &c = ctx();
     memset(out, 0, sizeof *out);
     out->choice = true; out->row = A->row; out->col = A->col; out->nnz = A->nnz;
-    DBuf<long long> ro;
-    DBuf<int> ri, ci;
+    DBuf<long long> ro64;
+    DBuf<int> ro, ri, ci;
     DBuf<double> v;
     IAS_TRY(ro.alloc((size_t)A->row + 1));
+    IAS_TRY(ro64.alloc((size_t)A->row + 1));
     IAS_TRY(ri.alloc((size_t)A->nnz));
     IAS_TRY(ci.alloc((size_t)A->nnz));
     IAS_TRY(v.alloc((size_t)A->nnz));
-    IAS_LAUNCH(k_widen, grid_for(A->row + 1, 256), 256, 0, A->row + 1, A->row_ind_dev, ro.p);
+    IAS_CUDA(cudaMemcpyAsync(ro.p, A->row_ind_dev, sizeof(int) * ((size_t)A->row + 1), cudaMemcpyDeviceToDevice, c.stream));
     if (A->nnz) {
-        IAS_LAUNCH(k_expand_rows, grid_for(((long long)A->nnz + 15) / 16, 256), 256, 0, A->row, ro.p, ri.p);
+        IAS_LAUNCH(k_widen, grid_for(A->row + 1, 256), 256, 0, A->row + 1, A->row_ind_dev, ro64.p);
+        IAS_LAUNCH(k_expand_rows, grid_for(((long long)A->nnz + 15) / 16, 256), 256, 0, A->row, ro64.p, ri.p);
         IAS_CUDA(cudaMemcpyAsync(ci.p, A->col_ind_dev, sizeof(int) * (size_t)A->nnz, cudaMemcpyDeviceToDevice, c.stream));
         IAS_CUDA(cudaMemcpyAsync(v.p, A->values_dev, sizeof(double) * (size_t)A->nnz, cudaMemcpyDeviceToDevice, c.stream));
     }
@@ -224,15 +259,24 @@ int ias_free_coo_dev(IasCooDev *m)
     return IAS_OK;
 }
 
-int ias_coo_mul_coo_dev(const IasCooDev *A, const IasCooDev *B, IasCooDev *C, double *elapsed_ms)
+int ias_free_coo64_dev(IasCoo64Dev *m)
+{
+    if (!m) return IAS_OK;
+    dfree(m->row_offset_dev); dfree(m->row_ind_dev); dfree(m->col_ind_dev); dfree(m->values_dev);
+    m->row_offset_dev = nullptr; m->row_ind_dev = nullptr; m->col_ind_dev = nullptr; m->values_dev = nullptr;
+    return IAS_OK;
+}
+
+int ias_coo_mul_coo_dev64(const IasCooDev *A, const IasCooDev *B, IasCoo64Dev *C, double *elapsed_ms)
 {
     IAS_TRY(ensure_init());
     if (!A || !B || !C) return fail(IAS_E_ARG, "NULL");
     if (A->col > B->row) return fail(IAS_E_ARG, "shape mismatch: A is %dx%d, B is %dx%d", A->row, A->col, B->row, B->col);
     Ctx &c = ctx();
     memset(C, 0, sizeof *C);
-    Csr64View av{A->row_offset_dev, A->col_ind_dev, A->values_dev};
-    Csr64View bv{B->row_offset_dev, B->col_ind_dev, B->values_dev};
+    // the reference COO carries a CSR-like row_offset (coo:29-66): the multiply is the CSR pipeline on it
+    CsrView av{A->row_offset_dev, A->col_ind_dev, A->values_dev};
+    CsrView bv{B->row_offset_dev, B->col_ind_dev, B->values_dev};
     IasCsr64Dev c64;
     IasSpgemmStats st;
     double avg = A->row ? (double)A->nnz / A->row : 0.0;
@@ -250,7 +294,41 @@ int ias_coo_mul_coo_dev(const IasCooDev *A, const IasCooDev *B, IasCooDev *C, do
     return IAS_OK;
 }
 
-int ias_download_coo(const IasCooDev *d, long long *row_offset, int *row_ind, int *col_ind, double *values)
+int ias_coo_mul_coo_dev(const IasCooDev *A, const IasCooDev *B, IasCooDev *C, double *elapsed_ms)
+{
+    if (!C) return fail(IAS_E_ARG, "NULL");
+    IasCoo64Dev c64;
+    IAS_TRY(ias_coo_mul_coo_dev64(A, B, &c64, elapsed_ms));
+    if (c64.nnz > 0x7fffffffLL) {
+        ias_free_coo64_dev(&c64);
+        return fail(IAS_E_OVERFLOW, "nnz(C) = %lld does not fit the int32 CooMatrixDev layout; use ias_coo_mul_coo_dev64", c64.nnz);
+    }
+    memset(C, 0, sizeof *C);
+    DBuf<int> ro;
+    IAS_TRY(ro.alloc((size_t)c64.row + 1));
+    IAS_LAUNCH(k_narrow, grid_for(c64.row + 1, 256), 256, 0, c64.row + 1, c64.row_offset_dev, ro.p);
+    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
+    dfree(c64.row_offset_dev);
+    C->choice = true; C->row = c64.row; C->col = c64.col; C->nnz = (int)c64.nnz;
+    C->row_offset_dev = ro.release(); C->row_ind_dev = c64.row_ind_dev; C->col_ind_dev = c64.col_ind_dev; C->values_dev = c64.values_dev;
+    return IAS_OK;
+}
+
+int ias_download_coo(const IasCooDev *d, int *row_offset, int *row_ind, int *col_ind, double *values)
+{
+    IAS_TRY(ensure_init());
+    if (!d) return fail(IAS_E_ARG, "NULL");
+    cudaStream_t s = ctx().stream;
+    size_t n = (size_t)d->nnz;
+    if (row_offset) IAS_CUDA(cudaMemcpyAsync(row_offset, d->row_offset_dev, sizeof(int) * ((size_t)d->row + 1), cudaMemcpyDeviceToHost, s));
+    if (row_ind && n) IAS_CUDA(cudaMemcpyAsync(row_ind, d->row_ind_dev, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    if (col_ind && n) IAS_CUDA(cudaMemcpyAsync(col_ind, d->col_ind_dev, sizeof(int) * n, cudaMemcpyDeviceToHost, s));
+    if (values && n) IAS_CUDA(cudaMemcpyAsync(values, d->values_dev, sizeof(double) * n, cudaMemcpyDeviceToHost, s));
+    IAS_CUDA(cudaStreamSynchronize(s));
+    return IAS_OK;
+}
+
+int ias_download_coo64(const IasCoo64Dev *d, long long *row_offset, int *row_ind, int *col_ind, double *values)
 {
     IAS_TRY(ensure_init());
     if (!d) return fail(IAS_E_ARG, "NULL");

@@ -40,7 +40,8 @@ struct MatNet {
 struct H5 {
     std::vector<unsigned char> b;
     unsigned long long base = 0;
-    bool ok(size_t off, size_t n) const { return off + n <= b.size(); }
+    bool ok(size_t off, size_t n) const { return off <= b.size() && n <= b.size() - off; }     // no wrap-around
+    unsigned char at(size_t off) const { return off < b.size() ? b[off] : 0; }
     template <class T>
     T rd(size_t off) const
     {
@@ -111,23 +112,28 @@ struct H5 {
         size_t data = 0, size = 0;
         for (const Msg &x : m) {
             if (x.type == 0x01) {
-                int ver = b[x.body], rank = b[x.body + 1];
+                if (x.size < 2) return false;
+                int ver = at(x.body), rank = at(x.body + 1);
+                if (rank > 8) return false;
                 size_t off = x.body + (ver == 1 ? 8 : 4);
                 t.dims.clear();
                 for (int r = 0; r < rank; ++r) t.dims.push_back((long long)rd<unsigned long long>(off + 8 * r));
                 have_dims = true;
             } else if (x.type == 0x03) {
-                f32 = (b[x.body] & 0x0F) == 1 && rd<unsigned>(x.body + 4) == 4 && (b[x.body + 1] & 1) == 0;
+                f32 = x.size >= 8 && (at(x.body) & 0x0F) == 1 && rd<unsigned>(x.body + 4) == 4 && (at(x.body + 1) & 1) == 0;
             } else if (x.type == 0x08) {
-                if (b[x.body] != 3 || b[x.body + 1] != 1) return false;     // layout v3, contiguous
+                if (x.size < 18 || at(x.body) != 3 || at(x.body + 1) != 1) return false;     // layout v3, contiguous
                 data = (size_t)rd<unsigned long long>(x.body + 2);
                 size = (size_t)rd<unsigned long long>(x.body + 10);
             }
         }
         if (!f32 || !have_dims || !size) return false;
         size_t n = 1;
-        for (long long d : t.dims) n *= (size_t)d;
-        if (size != 4 * n || !ok(base + data, size)) return false;
+        for (long long d : t.dims) {
+            if (d < 0 || (d > 0 && n > b.size() / (size_t)d)) return false;      // more elements than the file has bytes
+            n *= (size_t)d;
+        }
+        if (size != 4 * n || data > b.size() || !ok(base + data, size)) return false;
         t.data.resize(n);
         memcpy(t.data.data(), b.data() + base + data, size);
         return true;

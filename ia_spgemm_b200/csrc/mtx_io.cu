@@ -5,12 +5,17 @@
 //   coordinate files; `complex` rejected; real via %lg, integer via %d, pattern -> 1.0;
 //   1-based -> 0-based; symmetric / hermitian entries mirrored for i != j (skew-symmetric is not);
 //   rows filled in file order (stable counting sort by row): columns are NOT sorted and duplicate
-//   (i,j) are NOT merged.  Return codes follow main(): -1 open, -2 banner, -3 complex, -4 size line.
+//   (i,j) are NOT merged.  Return codes follow main(): -1 open, -2 banner, -3 complex, -4 size line;
+//   -5 (ours) when the matrix does not fit the int32 layout or host memory.  Entries whose row or
+//   column lies outside the declared shape are skipped (the reference writes out of bounds there).
 #include <ctype.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
+#include <limits.h>
+
+#include <new>
 #include <string>
 #include <vector>
 
@@ -29,9 +34,23 @@ struct Entry { int i, j; double v; };
 
 }  // namespace
 
+static int mtx_load_impl(const char *path, IasCsrMatrix *out);
+
 extern "C" {
 
 int ias_mtx_load(const char *path, IasCsrMatrix *out)
+{
+    try {
+        return mtx_load_impl(path, out);
+    } catch (const std::bad_alloc &) {        // nothing may unwind through the C boundary
+        if (out) memset(out, 0, sizeof *out);
+        return -5;
+    }
+}
+
+}  // extern "C"
+
+static int mtx_load_impl(const char *path, IasCsrMatrix *out)
 {
     if (!path || !out) return -1;
     memset(out, 0, sizeof *out);
@@ -57,7 +76,7 @@ int ias_mtx_load(const char *path, IasCsrMatrix *out)
     if (!have_size || m < 0 || n < 0 || nz < 0) { fclose(f); return -4; }
 
     std::vector<Entry> e;
-    e.reserve((size_t)nz);
+    e.reserve((size_t)(nz < (1 << 24) ? nz : (1 << 24)));      // the size line is input: do not trust it with memory
     for (int t = 0; t < nz; ++t) {
         Entry x{0, 0, 1.0};
         int iv = 0;
@@ -67,7 +86,7 @@ int ias_mtx_load(const char *path, IasCsrMatrix *out)
         if (got != (field == "pattern" ? 2 : 3)) break;
         if (field == "integer") x.v = iv;
         --x.i; --x.j;
-        if (x.i < 0 || x.i >= m) continue;                 // the reference would write out of bounds here
+        if (x.i < 0 || x.i >= m || x.j < 0 || x.j >= n) continue;   // the reference would write / index out of bounds here
         e.push_back(x);
     }
     fclose(f);
@@ -75,19 +94,24 @@ int ias_mtx_load(const char *path, IasCsrMatrix *out)
     std::vector<long long> fill((size_t)m + 1, 0);
     for (const Entry &x : e) {
         fill[x.i]++;
-        if (mirror && x.i != x.j && x.j >= 0 && x.j < m) fill[x.j]++;
+        if (mirror && x.i != x.j && x.j < m && x.i < n) fill[x.j]++;
     }
+    long long all = 0;
+    for (int i = 0; i < m; ++i) all += fill[i];
+    if (all > (long long)INT_MAX) return -5;
     int *rp = (int *)malloc(sizeof(int) * ((size_t)m + 1));
+    if (!rp) return -5;
     long long run = 0;
     for (int i = 0; i < m; ++i) { rp[i] = (int)run; run += fill[i]; fill[i] = 0; }
     rp[m] = (int)run;
     size_t total = (size_t)run;
     int *ci = (int *)malloc(sizeof(int) * (total ? total : 1));
     double *v = (double *)malloc(sizeof(double) * (total ? total : 1));
+    if (!ci || !v) { free(rp); free(ci); free(v); return -5; }
     for (const Entry &x : e) {
         size_t p = (size_t)rp[x.i] + (size_t)fill[x.i]++;
         ci[p] = x.j; v[p] = x.v;
-        if (mirror && x.i != x.j && x.j >= 0 && x.j < m) {
+        if (mirror && x.i != x.j && x.j < m && x.i < n) {
             p = (size_t)rp[x.j] + (size_t)fill[x.j]++;
             ci[p] = x.i; v[p] = x.v;
         }
@@ -96,6 +120,8 @@ int ias_mtx_load(const char *path, IasCsrMatrix *out)
     out->row_ind = rp; out->col_ind = ci; out->values = v;
     return 0;
 }
+
+extern "C" {
 
 void ias_free_host_csr(IasCsrMatrix *m)
 {

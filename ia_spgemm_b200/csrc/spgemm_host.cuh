@@ -209,15 +209,20 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
         IAS_TRY(long_count.alloc(1));
         IAS_CUDA(cudaMemsetAsync(long_count.p, 0, sizeof(int), c.stream));
         IAS_LAUNCH((k_row_ub_thread<AV, BV>), grid_for(nrows, 256), 256, 0, nrows, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p, long_list.p, long_count.p, rw.nnz_row.p);
-        if (avg_a_row * nrows > LONG_A)        // some row can be long only if the operand has that many entries at all
-            IAS_LAUNCH((k_row_ub_long<AV, BV>), c.sm_count * 8, 256, 0, long_list.p, long_count.p, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p);
+        // always launched: the kernel reads *long_count on the device and leaves at once when no row was deferred
+        // (a host-side guess from the operand's average row length missed long rows inside small row blocks)
+        (void)avg_a_row;
+        IAS_LAUNCH((k_row_ub_long<AV, BV>), c.sm_count * 8, 256, 0, long_list.p, long_count.p, r0, A, B, rw.ub.p, rw.bin.p, rw.hist.p);
     }
     // canonical B: the analyze kernel has just checked the rows of A it walked; that covers B only when B is A
     // and the range is the whole matrix, otherwise B gets its own pass (4 B per entry of B)
     bool covered = b_is_a && r0 == 0 && r1 == b_rows;
-    // B's canonical flag is remembered per operand (pointers + shape), so repeated row-block multiplies
-    // against the same B (multi-GPU, streaming callers) pay the 4 B/entry pass once
-    bool cached = !covered && b_nnz >= 0 && c.canon_ci == (const void *)B.ci && c.canon_rows == b_rows && c.canon_nnz == b_nnz;
+    // Opt-in ("trust_operand_cache"): B's canonical flag is remembered per operand (pointers + shape), so repeated
+    // row-block multiplies against the same B (multi-GPU ranks, callers that stream blocks themselves) pay the
+    // 4 B/entry pass once.  Off by default: caller-owned memory can be freed and re-allocated at the same address
+    // with the same shape (caching allocators do exactly that), and a stale flag would go unnoticed.
+    bool cached = c.tune.trust_operand_cache != 0 && !covered && b_nnz >= 0 && c.canon_ci == (const void *)B.ci &&
+                  c.canon_rp == (const void *)B.rp_base() && c.canon_rows == b_rows && c.canon_nnz == b_nnz;
     if (!covered && !cached && b_rows > 0) {
         IAS_CUDA(cudaMemsetAsync(rw.hist.p + NBINS + 1, 0, sizeof(unsigned long long), c.stream));
         IAS_LAUNCH((k_rows_canonical<BV>), grid_for(b_rows, 256), 256, 0, b_rows, B, rw.hist.p + NBINS + 1);
@@ -227,7 +232,10 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
     rw.products = h[NBINS];
     rw.b_canonical = (b_rows > 0 && h[NBINS + 1] == 0) ? 1 : 0;
     if (cached) rw.b_canonical = c.canon_flag;
-    else if (b_nnz >= 0 && b_rows > 0) { c.canon_ci = (const void *)B.ci; c.canon_rows = b_rows; c.canon_nnz = b_nnz; c.canon_flag = rw.b_canonical; }
+    else if (c.tune.trust_operand_cache != 0 && b_nnz >= 0 && b_rows > 0) {
+        c.canon_ci = (const void *)B.ci; c.canon_rp = (const void *)B.rp_base(); c.canon_rows = b_rows; c.canon_nnz = b_nnz;
+        c.canon_flag = rw.b_canonical;
+    }
     rw.max_tiny_na = (int)h[NBINS + 2];
     rw.max_tiny_ub = (int)h[NBINS + 3];
     rw.max_warp_ub = (int)h[NBINS + 4];

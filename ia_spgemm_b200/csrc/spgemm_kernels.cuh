@@ -74,6 +74,7 @@ struct CsrView {                       // CsrMatrixDev, GPU/detail/format.h:59-6
     __device__ __forceinline__ off_t begin(int i) const { return __ldg(rp + i); }
     __device__ __forceinline__ off_t end(int i) const { return __ldg(rp + i + 1); }
     __device__ __forceinline__ int len(int i) const { return __ldg(rp + i + 1) - __ldg(rp + i); }
+    const void *rp_base() const { return rp; }
 };
 struct Csr64View {                     // CSR with 64-bit row offsets (IasCooDev::row_offset_dev)
     const long long *rp; const int *ci; const double *v;
@@ -81,6 +82,7 @@ struct Csr64View {                     // CSR with 64-bit row offsets (IasCooDev
     __device__ __forceinline__ off_t begin(int i) const { return __ldg(rp + i); }
     __device__ __forceinline__ off_t end(int i) const { return __ldg(rp + i + 1); }
     __device__ __forceinline__ int len(int i) const { return (int)(__ldg(rp + i + 1) - __ldg(rp + i)); }
+    const void *rp_base() const { return rp; }
 };
 struct EllView {                       // EllMatrixDev, GPU/detail/format.h:108-119 (row-major, fixed width)
     const int *nr; const int *ci; const double *v; int w;
@@ -88,6 +90,7 @@ struct EllView {                       // EllMatrixDev, GPU/detail/format.h:108-
     __device__ __forceinline__ off_t begin(int i) const { return (long long)i * w; }
     __device__ __forceinline__ off_t end(int i) const { return (long long)i * w + __ldg(nr + i); }
     __device__ __forceinline__ int len(int i) const { return __ldg(nr + i); }
+    const void *rp_base() const { return nr; }
 };
 
 // where row li of the current range goes in the output arrays
@@ -366,7 +369,9 @@ __global__ void __launch_bounds__(BLOCK) k_sym_tiny(const int *__restrict__ rows
 {
     __shared__ int list[T_MAX * BLOCK];          // [slot][thread]: conflict free (list path only)
     int idx = blockIdx.x * BLOCK + threadIdx.x;
-    if (idx >= nrows) return;                    // (partial last warp: the mask below is the active mask)
+    // lanes of this warp that own a row: taken before any divergence, so the reduction below names exactly them
+    const unsigned mask = __ballot_sync(0xffffffffu, idx < nrows);
+    if (idx >= nrows) return;
     int li = rows ? rows[idx] : idx;
     int i = r0 + li;
     typename AV::off_t pa = A.begin(i), pe = A.end(i);
@@ -398,7 +403,8 @@ __global__ void __launch_bounds__(BLOCK) k_sym_tiny(const int *__restrict__ rows
         }
     }
     nnz_row[li] = cnt;
-    int wmax = __reduce_max_sync(__activemask(), cnt);
+    __syncwarp(mask);
+    int wmax = __reduce_max_sync(mask, cnt);
     if ((threadIdx.x & 31) == 0 && (unsigned long long)wmax > *max_out) atomicMax(max_out, (unsigned long long)wmax);
 }
 

@@ -33,7 +33,13 @@ class Csr64Dev(C.Structure):
                 ("row_ptr_dev", C.c_void_p), ("col_ind_dev", C.c_void_p), ("values_dev", C.c_void_p)]
 
 
-class CooDev(C.Structure):
+class CooDev(C.Structure):             # IasCooDev == CooMatrixDev (format.h:29-40)
+    _fields_ = [("choice", C.c_bool), ("row", C.c_int), ("col", C.c_int), ("nnz", C.c_int),
+                ("row_offset_dev", C.c_void_p), ("row_ind_dev", C.c_void_p), ("col_ind_dev", C.c_void_p),
+                ("values_dev", C.c_void_p)]
+
+
+class Coo64Dev(C.Structure):           # results beyond int32
     _fields_ = [("choice", C.c_bool), ("row", C.c_int), ("col", C.c_int), ("nnz", C.c_longlong),
                 ("row_offset_dev", C.c_void_p), ("row_ind_dev", C.c_void_p), ("col_ind_dev", C.c_void_p),
                 ("values_dev", C.c_void_p)]
@@ -44,10 +50,26 @@ class DiaDev(C.Structure):
                 ("diagonal_ind_dev", C.c_void_p), ("diagonal_offsets_dev", C.c_void_p), ("values_dev", C.c_void_p)]
 
 
-class EllDev(C.Structure):
+class EllDev(C.Structure):             # IasEllDev == EllMatrixDev (format.h:108-119)
+    _fields_ = [("choice", C.c_bool), ("row", C.c_int), ("col", C.c_int), ("nnz", C.c_int),
+                ("max_nnz_per_row", C.c_int),
+                ("nnz_row_dev", C.c_void_p), ("col_ind_dev", C.c_void_p), ("values_dev", C.c_void_p)]
+
+
+class Ell64Dev(C.Structure):           # results beyond int32
     _fields_ = [("choice", C.c_bool), ("row", C.c_int), ("col", C.c_int), ("nnz", C.c_longlong),
                 ("max_nnz_per_row", C.c_int),
                 ("nnz_row_dev", C.c_void_p), ("col_ind_dev", C.c_void_p), ("values_dev", C.c_void_p)]
+
+
+class StreamBatch(C.Structure):        # IasStreamBatch
+    _fields_ = [("row_begin", C.c_int), ("row_end", C.c_int), ("batch_index", C.c_int), ("batch_count", C.c_int),
+                ("nnz_total", C.c_longlong), ("entry_base", C.c_longlong), ("batch_nnz", C.c_longlong),
+                ("row_ptr_dev", C.c_void_p), ("col_ind_dev", C.c_void_p), ("values_dev", C.c_void_p),
+                ("cuda_stream", C.c_void_p)]
+
+
+STREAM_CONSUMER = C.CFUNCTYPE(C.c_int, C.POINTER(StreamBatch), C.c_void_p)
 
 
 class SpgemmStats(C.Structure):
@@ -79,16 +101,18 @@ BIN_NAMES = ["empty", "tiny", "warp", "cta_s", "cta_l", "global"]
 
 # every symbol include/iaspgemm.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
-    "ias_init", "ias_set_stream", "ias_sync", "ias_last_error", "ias_version", "ias_device_info",
+    "ias_init", "ias_set_stream", "ias_use_own_stream", "ias_sync", "ias_last_error", "ias_version", "ias_device_info",
     "ias_kernel_launches", "ias_set_option", "ias_get_option",
     "ias_upload_csr", "ias_free_csr_dev", "ias_free_csr64_dev", "ias_download_csr64", "ias_download_csr",
     "ias_csr_is_canonical", "ias_copy", "ias_forget_operand",
     "ias_csr_mul_csr_dev64", "ias_csr_mul_csr_dev", "ias_csr_mul_csr_rows_dev64", "ias_csr_mul_csr_stream",
+    "ias_csr_mul_csr_stream_cb",
     "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_touched_b_bytes", "ias_partition_rows", "ias_checksum",
     "ias_structure_hash",
-    "ias_csr_to_dia", "ias_dia_mul_dia_dev", "ias_download_dia", "ias_free_dia_dev",
-    "ias_csr_to_ell", "ias_ell_mul_ell_dev", "ias_download_ell", "ias_free_ell_dev",
-    "ias_csr_to_coo", "ias_coo_mul_coo_dev", "ias_download_coo", "ias_free_coo_dev",
+    "ias_csr_to_dia", "ias_dia_mul_dia_dev", "ias_download_dia", "ias_free_dia_dev", "ias_dia_relayout",
+    "ias_csr_to_ell", "ias_ell_mul_ell_dev", "ias_ell_mul_ell_dev64", "ias_download_ell", "ias_free_ell_dev", "ias_free_ell64_dev",
+    "ias_csr_to_coo", "ias_coo_mul_coo_dev", "ias_coo_mul_coo_dev64", "ias_download_coo", "ias_download_coo64",
+    "ias_free_coo_dev", "ias_free_coo64_dev",
     "ias_density_image", "ias_getinfo1", "ias_getinfo2", "ias_getinfo3", "ias_count_diagonals",
     "ias_max_row_nnz", "ias_features26",
     "ias_sizeof_csr", "ias_sizeof_dia", "ias_sizeof_ell", "ias_sizeof_coo",
@@ -179,6 +203,9 @@ def load_library():
         "ias_set_option": [C.c_char_p, C.c_longlong], "ias_get_option": [C.c_char_p, C.c_void_p],
         "ias_set_stream": [C.c_void_p], "ias_checksum": [C.c_void_p, C.c_longlong, _D],
         "ias_csr_mul_csr_stream": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p],
+        "ias_csr_mul_csr_stream_cb": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, STREAM_CONSUMER, C.c_void_p,
+                                      C.c_void_p],
+        "ias_dia_relayout": [C.c_void_p, C.c_int, C.c_void_p],
         "ias_getinfo3": [C.c_int, C.c_longlong, C.c_int, _D],
         "ias_gen_rmat": [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p],
         "ias_csr_to_dia": [C.c_void_p, C.c_double, C.c_void_p], "ias_csr_to_ell": [C.c_void_p, C.c_double, C.c_void_p],
@@ -227,6 +254,8 @@ class DeviceCsr:
     def close(self):
         if self.owned and self.dev.row_ind_dev:
             self.eng.lib.ias_free_csr_dev(C.byref(self.dev))
+        elif self.dev.col_ind_dev:
+            self.eng.lib.ias_forget_operand(C.byref(self.dev))      # caller-owned memory may be re-used at the same address
         self.owned = False
 
     def __del__(self):
@@ -247,7 +276,11 @@ class Engine:
 
     # -- context -----------------------------------------------------------------------
     def set_stream(self, cuda_stream_handle):
+        """Run on the caller's cudaStream_t; 0 / None is the legacy default stream (torch's default stream handle)."""
         self._ck(self.lib.ias_set_stream(C.c_void_p(cuda_stream_handle or 0)))
+
+    def use_own_stream(self):
+        self._ck(self.lib.ias_use_own_stream())
 
     def sync(self):
         self._ck(self.lib.ias_sync())
@@ -297,7 +330,9 @@ class Engine:
 
     def wrap_device(self, rows, cols, nnz, rp_ptr, ci_ptr, v_ptr):
         """Operand living in caller-owned device memory (e.g. torch tensors)."""
-        return DeviceCsr(self, CsrMatrixDev(True, rows, cols, nnz, rp_ptr, ci_ptr, v_ptr), owned=False)
+        d = DeviceCsr(self, CsrMatrixDev(True, rows, cols, nnz, rp_ptr, ci_ptr, v_ptr), owned=False)
+        self.lib.ias_forget_operand(C.byref(d.dev))                 # whatever lived at these addresses before is gone
+        return d
 
     def copy(self, dst_ptr, src_ptr, nbytes, kind):
         """kind: 0 host->device, 1 device->host, 2 device->device."""
@@ -373,7 +408,9 @@ class Engine:
                np.ctypeslib.as_array(v, shape=(n,)) if n else np.zeros(0, np.float64))
         return out, st.as_dict(), h2d.value, d2h.value
 
-    def csr_mul_csr_stream(self, A, B, rows=None, budget_bytes=0, want_row_nnz=False):
+    def csr_mul_csr_stream(self, A, B, rows=None, budget_bytes=0, want_row_nnz=False, consumer=None):
+        """consumer(batch_dict) is called once per row batch with host copies of the batch (row_begin, row_end,
+        row_ptr relative to the batch, col_ind, values, nnz_total): the §8(b) streaming consumer."""
         r0, r1 = rows if rows is not None else (0, A.dev.row)
         st = SpgemmStats()
         row_nnz = None
@@ -382,7 +419,30 @@ class Engine:
             import torch
             row_nnz = torch.empty(max(r1 - r0, 1), dtype=torch.int32, device="cuda")
             ptr = row_nnz.data_ptr()
-        self._ck(self.lib.ias_csr_mul_csr_stream(C.byref(A.dev), C.byref(B.dev), r0, r1, budget_bytes, ptr, C.byref(st)))
+        if consumer is not None:
+            def _cb(bp, _user):
+                b = bp.contents
+                n = b.row_end - b.row_begin
+                rp = np.empty(n + 1, np.int64)
+                ci = np.empty(b.batch_nnz, np.int32)
+                v = np.empty(b.batch_nnz, np.float64)
+                self.copy(rp.ctypes.data, b.row_ptr_dev, 8 * (n + 1), 1)
+                if b.batch_nnz:
+                    self.copy(ci.ctypes.data, b.col_ind_dev, 4 * b.batch_nnz, 1)
+                    self.copy(v.ctypes.data, b.values_dev, 8 * b.batch_nnz, 1)
+                try:
+                    rc = consumer({"row_begin": b.row_begin, "row_end": b.row_end, "batch_index": b.batch_index,
+                                   "batch_count": b.batch_count, "nnz_total": b.nnz_total, "entry_base": b.entry_base,
+                                   "row_ptr": rp - b.entry_base, "col_ind": ci, "values": v})
+                except Exception:          # an exception cannot cross the C boundary
+                    import traceback
+                    traceback.print_exc()
+                    return 99
+                return int(rc or 0)
+            cb = STREAM_CONSUMER(_cb)
+            self._ck(self.lib.ias_csr_mul_csr_stream_cb(C.byref(A.dev), C.byref(B.dev), r0, r1, budget_bytes, ptr, cb, None, C.byref(st)))
+        else:
+            self._ck(self.lib.ias_csr_mul_csr_stream(C.byref(A.dev), C.byref(B.dev), r0, r1, budget_bytes, ptr, C.byref(st)))
         d = st.as_dict()
         if want_row_nnz:
             d["row_nnz"] = row_nnz[: r1 - r0].cpu().numpy()
@@ -437,6 +497,11 @@ class Engine:
     def free_dia(self, d):
         self.lib.ias_free_dia_dev(C.byref(d))
 
+    def dia_relayout(self, d, to_row_major):
+        out = DiaDev()
+        self._ck(self.lib.ias_dia_relayout(C.byref(d), C.c_int(1 if to_row_major else 0), C.byref(out)))
+        return out
+
     # -- ELL -----------------------------------------------------------------------------
     def CSRtoELL(self, A, gate=20.0):
         e = EllDev()
@@ -452,13 +517,18 @@ class Engine:
         return {"row": e.row, "col": e.col, "width": w, "nnz": e.nnz, "choice": bool(e.choice), "nnz_row": nr[: e.row],
                 "col_ind": ci[: e.row * w].reshape(e.row, w), "values": v[: e.row * w].reshape(e.row, w)}
 
-    def ELL_MUL_ELL_DEV(self, A, B):
-        c, ms = EllDev(), C.c_double()
-        self._ck(self.lib.ias_ell_mul_ell_dev(C.byref(A), C.byref(B), C.byref(c), C.byref(ms)))
+    def ELL_MUL_ELL_DEV(self, A, B, int32=False):
+        """ELL_MUL_ELL_DEV (ell_dev:310).  Default: the 64-bit-nnz result; int32=True: the reference's EllMatrixDev."""
+        c, ms = (EllDev() if int32 else Ell64Dev()), C.c_double()
+        f = self.lib.ias_ell_mul_ell_dev if int32 else self.lib.ias_ell_mul_ell_dev64
+        self._ck(f(C.byref(A), C.byref(B), C.byref(c), C.byref(ms)))
         return c, ms.value
 
     def free_ell(self, e):
-        self.lib.ias_free_ell_dev(C.byref(e))
+        if isinstance(e, Ell64Dev):
+            self.lib.ias_free_ell64_dev(C.byref(e))
+        else:
+            self.lib.ias_free_ell_dev(C.byref(e))
 
     # -- COO -----------------------------------------------------------------------------
     def CSRtoCOO(self, A):
@@ -467,21 +537,30 @@ class Engine:
         return c
 
     def download_coo(self, c):
-        ro = np.zeros(c.row + 1, np.int64)
+        wide = isinstance(c, Coo64Dev)
+        ro = np.zeros(c.row + 1, np.int64 if wide else np.int32)
         ri = np.zeros(max(c.nnz, 1), np.int32)
         ci = np.zeros(max(c.nnz, 1), np.int32)
         v = np.zeros(max(c.nnz, 1), np.float64)
-        self._ck(self.lib.ias_download_coo(C.byref(c), ro.ctypes.data_as(_L), ri.ctypes.data_as(_I), ci.ctypes.data_as(_I), v.ctypes.data_as(_D)))
-        return {"row": c.row, "col": c.col, "nnz": c.nnz, "row_offset": ro, "row_ind": ri[: c.nnz], "col_ind": ci[: c.nnz],
+        if wide:
+            self._ck(self.lib.ias_download_coo64(C.byref(c), ro.ctypes.data_as(_L), ri.ctypes.data_as(_I), ci.ctypes.data_as(_I), v.ctypes.data_as(_D)))
+        else:
+            self._ck(self.lib.ias_download_coo(C.byref(c), ro.ctypes.data_as(_I), ri.ctypes.data_as(_I), ci.ctypes.data_as(_I), v.ctypes.data_as(_D)))
+        return {"row": c.row, "col": c.col, "nnz": c.nnz, "row_offset": ro.astype(np.int64), "row_ind": ri[: c.nnz], "col_ind": ci[: c.nnz],
                 "values": v[: c.nnz]}
 
-    def COO_MUL_COO_DEV(self, A, B):
-        c, ms = CooDev(), C.c_double()
-        self._ck(self.lib.ias_coo_mul_coo_dev(C.byref(A), C.byref(B), C.byref(c), C.byref(ms)))
+    def COO_MUL_COO_DEV(self, A, B, int32=False):
+        """COO_MUL_COO_DEV (coo_dev:279).  Default: the 64-bit result; int32=True: the reference's CooMatrixDev."""
+        c, ms = (CooDev() if int32 else Coo64Dev()), C.c_double()
+        f = self.lib.ias_coo_mul_coo_dev if int32 else self.lib.ias_coo_mul_coo_dev64
+        self._ck(f(C.byref(A), C.byref(B), C.byref(c), C.byref(ms)))
         return c, ms.value
 
     def free_coo(self, c):
-        self.lib.ias_free_coo_dev(C.byref(c))
+        if isinstance(c, Coo64Dev):
+            self.lib.ias_free_coo64_dev(C.byref(c))
+        else:
+            self.lib.ias_free_coo_dev(C.byref(c))
 
     # -- features ------------------------------------------------------------------------
     def density_image(self, A):

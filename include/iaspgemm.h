@@ -10,8 +10,11 @@
  *   - plain C: pointers and sizes only, no C++/torch types;
  *   - every function returns an int status (IAS_OK == 0); nothing calls exit() (the reference's
  *     DevMalloc/DevUpload exit(1), GPU/detail/common.h:62-97);
- *   - the struct layouts are byte-identical to GPU/detail/format.h so a reference `main` can
- *     pass its own CsrMatrix / CsrMatrixDev / DiaMatrixDev / EllMatrixDev / CooMatrixDev objects;
+ *   - IasCsrMatrix / IasCsrMatrixDev / IasCooDev / IasDiaDev / IasEllDev have the field order, types and
+ *     offsets of CsrMatrix / CsrMatrixDev / CooMatrixDev / DiaMatrixDev / EllMatrixDev in GPU/detail/format.h
+ *     (tests/abi_cxx/layout_check.cpp static_asserts it against the reference header itself), so a reference
+ *     `main` can pass its own objects; the one semantic difference is the DIA value order (see IasDiaDev);
+ *     the *64 structs are the engine's own, for results beyond int32;
  *   - callee allocates every array of C (as the reference kernels do) from the engine's
  *     stream-ordered device pool; the caller releases with ias_free_*;
  *   - index type is int32 (reference layout); counts that overflow int32 at the BASELINE sizes
@@ -66,34 +69,55 @@ typedef struct {           /* native result: 64-bit row pointers, column-sorted 
     double *values_dev;
 } IasCsr64Dev;
 
-typedef struct {           /* CooMatrixDev, GPU/detail/format.h:29-40 (+ 64-bit offsets) */
+typedef struct {           /* CooMatrixDev, GPU/detail/format.h:29-40 -- byte-identical */
     bool choice;
-    int row, col;
-    long long nnz;
-    long long *row_offset_dev;  /* row+1 entries (the reference keeps a CSR-like row_offset) */
+    int row, col, nnz;
+    int *row_offset_dev;        /* row+1 entries (the reference keeps a CSR-like row_offset) */
     int *row_ind_dev;
     int *col_ind_dev;
     double *values_dev;
 } IasCooDev;
 
-typedef struct {           /* DiaMatrixDev, GPU/detail/format.h:82-92 */
+typedef struct {           /* COO result whose nnz does not fit int32 (no reference counterpart: it is `int` everywhere) */
+    bool choice;
+    int row, col;
+    long long nnz;
+    long long *row_offset_dev;
+    int *row_ind_dev;
+    int *col_ind_dev;
+    double *values_dev;
+} IasCoo64Dev;
+
+typedef struct {           /* DiaMatrixDev, GPU/detail/format.h:82-92 -- same fields, same offsets */
     bool choice;
     int row, col, num_diagonals;
     int *diagonal_ind_dev;      /* row+col-1 entries: map index -> slot (0 for absent, as the reference) */
     int *diagonal_offsets_dev;  /* num_diagonals entries, ascending */
-    double *values_dev;         /* DIAGONAL-MAJOR on device: values[slot*row + i] (coalesced);
-                                   ias_download_dia returns the reference's row-major [i*nd + slot] */
+    double *values_dev;         /* The engine's kernels want DIAGONAL-MAJOR values[slot*row + i] (coalesced); the reference
+                                   stores row-major values[i*num_diagonals + slot] (GPU/detail/dia/common_dia.h:70-90).
+                                   ias_csr_to_dia / ias_dia_mul_dia_dev produce and consume diagonal-major;
+                                   ias_dia_relayout converts a reference-built DiaMatrixDev in either direction and
+                                   ias_download_dia returns the reference's row-major array. */
 } IasDiaDev;
 
-typedef struct {           /* EllMatrixDev, GPU/detail/format.h:108-119 */
+typedef struct {           /* EllMatrixDev, GPU/detail/format.h:108-119 -- byte-identical */
     bool choice;
-    int row, col;
-    long long nnz;
+    int row, col, nnz;
     int max_nnz_per_row;
     int *nnz_row_dev;
     int *col_ind_dev;           /* row-major [i*width + k] as the reference; padding 0 / 0.0 */
     double *values_dev;
 } IasEllDev;
+
+typedef struct {           /* ELL result whose nnz does not fit int32 */
+    bool choice;
+    int row, col;
+    long long nnz;
+    int max_nnz_per_row;
+    int *nnz_row_dev;
+    int *col_ind_dev;
+    double *values_dev;
+} IasEll64Dev;
 
 /* per-call statistics of the CSR pipeline (all times in ms, CUDA events on the engine stream) */
 typedef struct {
@@ -113,7 +137,8 @@ typedef struct {
 
 /* ---------------------------------------------------------------- context */
 int ias_init(int device);                       /* binds the engine to a CUDA device; idempotent */
-int ias_set_stream(void *cuda_stream);          /* run on the caller's cudaStream_t (NULL: engine stream) */
+int ias_set_stream(void *cuda_stream);          /* run on the caller's cudaStream_t; NULL is the legacy default stream */
+int ias_use_own_stream(void);                   /* back to the engine's own (non-blocking) stream, the default after ias_init */
 int ias_sync(void);
 const char *ias_last_error(void);
 const char *ias_version(void);
@@ -122,7 +147,8 @@ long long ias_kernel_launches(void);            /* engine kernels launched since
 /* Kernel-selection knobs (the reference has none: it hard-codes its library calls, GPU/main.cu:470-521).
  * Names: "global_rows_smem" (1 = windowed shared-memory kernels for rows beyond the CTA hash, 0 = L2 bitmap kernels),
  * "gwin_swords", "gwin_win", "gwin_sym_swords" (window sizes, 0 = automatic), "gwin_smem_kb", "gwin_max_sw" (numeric windowed
- * kernel only up to this many column super-windows per row, 0 = no limit), "g_win" (accumulate window of the L2 kernel), "g_coop", "gwin_takes_b2" (0/1 switches kept for A/B runs).  Also read from
+ * kernel only up to this many column super-windows per row, 0 = no limit), "g_win" (accumulate window of the L2 kernel), "g_coop", "gwin_takes_b2" (0/1 switches kept for A/B runs),
+ * "trust_operand_cache" (see ias_forget_operand).  Also read from
  * IAS_OPT_<NAME> in the environment by ias_init.  Results do not depend on any of them. */
 int ias_set_option(const char *name, long long value);
 int ias_get_option(const char *name, long long *value);
@@ -139,9 +165,11 @@ int ias_download_csr(const IasCsrMatrixDev *dev, int *row_ptr, int *col_ind, dou
 /* raw copies on the engine stream, synchronous: kind 0 = host->device, 1 = device->host, 2 = device->device
  * (DevUpload / DevDownload, GPU/detail/common.h:79-97, without the exit(1)) */
 int ias_copy(void *dst, const void *src, size_t bytes, int kind);
-/* The engine remembers, per B operand (pointer + shape), whether its rows are canonical.  A caller that
- * rewrites an operand's device arrays IN PLACE must call this before the next multiply (ias_free_csr_dev
- * does it for engine-owned operands; NULL forgets everything). */
+/* With ias_set_option("trust_operand_cache", 1) the engine remembers, per B operand (pointers + shape), whether its
+ * rows are canonical, so that repeated row-block multiplies against one B pay the 4 B/entry check once.  Off by
+ * default: a caller that turns it on promises to call this before the next multiply whenever it rewrites an
+ * operand's device arrays in place OR frees them (a caching allocator can hand the same address to a new operand of
+ * the same shape).  ias_free_csr_dev does it for engine-owned operands; NULL forgets everything. */
 int ias_forget_operand(const IasCsrMatrixDev *m);
 /* canonical = every row strictly increasing in column (sorted, duplicate free) */
 int ias_csr_is_canonical(const IasCsrMatrixDev *m, int *canonical);
@@ -164,6 +192,29 @@ int ias_csr_mul_csr_rows_dev64(const IasCsrMatrixDev *A, const IasCsrMatrixDev *
 int ias_csr_mul_csr_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B,
                            int row_begin, int row_end, size_t budget_bytes,
                            int *row_nnz_dev, IasSpgemmStats *stats);
+/* Same with a consumer: after each batch's numeric kernels are enqueued the engine calls consumer(batch, user) on the
+ * host.  The batch arrays are complete in stream order on batch->cuda_stream and are recycled when the callback
+ * returns, so the consumer copies them out (ias_copy, or its own work enqueued on that stream and synchronised) or
+ * reduces them before returning; a non-zero return aborts the multiply with that status.  consumer == NULL behaves
+ * like ias_csr_mul_csr_stream.  This is how a streamed C leaves the device (download, .mtx append, hand-over to a
+ * downstream operator) -- the role CUSP's workspace slices play in COO_MUL_COO_DEV
+ * (GPU/detail/coo_dev/common_coo_dev.h:326-337,388-450). */
+typedef struct {
+    int row_begin, row_end;         /* absolute rows of C in this batch */
+    int batch_index, batch_count;
+    long long nnz_total;            /* nnz(C) of the whole requested row range (known once the symbolic pass is done) */
+    long long entry_base;           /* offset of the batch's first entry within the range's C: entry e of row i sits at
+                                       col_ind_dev[row_ptr_dev[i - row_begin] - entry_base + e] */
+    long long batch_nnz;
+    const long long *row_ptr_dev;   /* row_end - row_begin + 1 offsets into the range's C */
+    const int *col_ind_dev;         /* batch_nnz entries, column-sorted inside each row */
+    const double *values_dev;
+    void *cuda_stream;
+} IasStreamBatch;
+typedef int (*ias_stream_consumer)(const IasStreamBatch *batch, void *user);
+int ias_csr_mul_csr_stream_cb(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B,
+                              int row_begin, int row_end, size_t budget_bytes, int *row_nnz_dev,
+                              ias_stream_consumer consumer, void *user, IasSpgemmStats *stats);
 /* host operands, host result: CSR_MUL_CSR(A,B,C), CPU/detail/csr/common_csr.h:85 -- uploads
  * A (and B unless it aliases A), multiplies on the GPU, downloads C into pinned host memory owned
  * by the engine (valid until the next host call or ias_release_host).  nnz(C) via C_nnz. */
@@ -191,24 +242,32 @@ int ias_csr_to_dia(const IasCsrMatrixDev *A, double gate, IasDiaDev *out);
 int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, double *elapsed_ms);
 int ias_download_dia(const IasDiaDev *dev, int *diagonal_ind, int *diagonal_offsets,
                      double *values_row_major);
+/* value order of a DIA matrix: to_row_major = 0 turns the reference's row-major values[i*nd + slot] (what
+ * UploadDiaMatrix, GPU/detail/dia_dev/common_dia_dev.h:10-24, puts on the device) into the engine's diagonal-major
+ * order; 1 goes back.  `out` gets its own arrays (release with ias_free_dia_dev). */
+int ias_dia_relayout(const IasDiaDev *in, int to_row_major, IasDiaDev *out);
 int ias_free_dia_dev(IasDiaDev *m);
 
 /* ---------------------------------------------------------------- ELL (Algorithm 4) */
 /* CSRtoELL, CPU/detail/ell/common_ell.h:30-77 */
 int ias_csr_to_ell(const IasCsrMatrixDev *A, double gate, IasEllDev *out);
 /* ELL_MUL_ELL_DEV, GPU/detail/ell_dev/common_ell_dev.h:310-382 */
-int ias_ell_mul_ell_dev(const IasEllDev *A, const IasEllDev *B, IasEllDev *C, double *elapsed_ms);
+int ias_ell_mul_ell_dev(const IasEllDev *A, const IasEllDev *B, IasEllDev *C, double *elapsed_ms);   /* IAS_E_OVERFLOW when nnz(C) >= 2^31 */
+int ias_ell_mul_ell_dev64(const IasEllDev *A, const IasEllDev *B, IasEll64Dev *C, double *elapsed_ms);
 int ias_download_ell(const IasEllDev *dev, int *nnz_row, int *col_ind, double *values);
 int ias_free_ell_dev(IasEllDev *m);
+int ias_free_ell64_dev(IasEll64Dev *m);
 
 /* ---------------------------------------------------------------- COO (Algorithm 5) */
 /* CSRtoCOO, CPU/detail/coo/common_coo.h:29-66 */
 int ias_csr_to_coo(const IasCsrMatrixDev *A, IasCooDev *out);
 /* COO_MUL_COO_DEV, GPU/detail/coo_dev/common_coo_dev.h:279-602 */
-int ias_coo_mul_coo_dev(const IasCooDev *A, const IasCooDev *B, IasCooDev *C, double *elapsed_ms);
-int ias_download_coo(const IasCooDev *dev, long long *row_offset, int *row_ind, int *col_ind,
-                     double *values);
+int ias_coo_mul_coo_dev(const IasCooDev *A, const IasCooDev *B, IasCooDev *C, double *elapsed_ms);   /* IAS_E_OVERFLOW when nnz(C) >= 2^31 */
+int ias_coo_mul_coo_dev64(const IasCooDev *A, const IasCooDev *B, IasCoo64Dev *C, double *elapsed_ms);
+int ias_download_coo(const IasCooDev *dev, int *row_offset, int *row_ind, int *col_ind, double *values);
+int ias_download_coo64(const IasCoo64Dev *dev, long long *row_offset, int *row_ind, int *col_ind, double *values);
 int ias_free_coo_dev(IasCooDev *m);
+int ias_free_coo64_dev(IasCoo64Dev *m);
 
 /* ---------------------------------------------------------------- features / density */
 /* density representation, CPU/main.cpp:516-577: 128x128 int64 image, row-major */

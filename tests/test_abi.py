@@ -51,7 +51,58 @@ def test_struct_layouts_match_reference_format_h():
         assert (S.choice.offset, S.row.offset, S.col.offset, S.nnz.offset) == (0, 4, 8, 12)
     assert E.CsrMatrix.row_ind.offset == 16 and E.CsrMatrix.values.offset == 32
     assert E.DiaDev.num_diagonals.offset == 12 and E.DiaDev.values_dev.offset == 32
+    # CooMatrixDev: bool, 3 int, 4 pointers; EllMatrixDev: bool, 4 int, (pad), 3 pointers (GPU/detail/format.h:29-40,108-119)
+    assert C.sizeof(E.CooDev) == 48 and E.CooDev.nnz.offset == 12 and E.CooDev.row_offset_dev.offset == 16 and E.CooDev.values_dev.offset == 40
+    assert C.sizeof(E.EllDev) == 48 and E.EllDev.max_nnz_per_row.offset == 16 and E.EllDev.nnz_row_dev.offset == 24 and E.EllDev.values_dev.offset == 40
     assert C.sizeof(E.SpgemmStats) == 8 * 8 + 16 * 8 + 16 * 8 + 2 * 4 + 8 + 8
+    assert C.sizeof(E.StreamBatch) == 4 * 4 + 3 * 8 + 4 * 8
+
+
+REF = "/root/reference"
+CXX = os.path.join(ROOT, "tests", "abi_cxx")
+
+
+def test_layouts_against_the_reference_headers(tmp_path):
+    """Compiles tests/abi_cxx/layout_check.cpp: the reference's own GPU/detail/format.h and CPU/detail/format.h
+    (included from where they lie) against include/iaspgemm.h, sizeof/offsetof static_asserts for CSR, COO, DIA, ELL."""
+    import subprocess
+    gpu_h = os.path.join(REF, "IA-SPGEMM-GPU_release", "detail", "format.h")
+    cpu_h = os.path.join(REF, "IA-SPGEMM-CPU_release", "detail", "format.h")
+    if not (os.path.exists(gpu_h) and os.path.exists(cpu_h)):
+        pytest.skip("reference checkout absent (GPU box): the layouts were proven where it is present")
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", "-DVALUE_TYPE=double",
+                        "-I", os.path.join(CXX, "cusp_stub"), "-I", os.path.join(ROOT, "oracle", "ref_shim"),
+                        '-DREF_GPU_FORMAT_H="%s"' % gpu_h, '-DREF_CPU_FORMAT_H="%s"' % cpu_h,
+                        os.path.join(CXX, "layout_check.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    # and the check bites: a struct with a widened field must be refused
+    bad = tmp_path / "bad.cpp"
+    src = open(os.path.join(CXX, "layout_check.cpp")).read().replace('#include "../../include/iaspgemm.h"',
+                                                                     '#include "%s"' % (tmp_path / "iaspgemm_bad.h"))
+    hdr = open(os.path.join(ROOT, "include", "iaspgemm.h")).read()
+    marker = "    int row, col, nnz;\n    int *row_offset_dev;"
+    assert marker in hdr
+    (tmp_path / "iaspgemm_bad.h").write_text(hdr.replace(marker, "    int row, col; long long nnz;\n    int *row_offset_dev;"))
+    bad.write_text(src)
+    r = subprocess.run(["g++", "-std=c++14", "-fsyntax-only", "-w", "-DVALUE_TYPE=double",
+                        "-I", os.path.join(CXX, "cusp_stub"), "-I", os.path.join(ROOT, "oracle", "ref_shim"),
+                        '-DREF_GPU_FORMAT_H="%s"' % gpu_h, '-DREF_CPU_FORMAT_H="%s"' % cpu_h, str(bad)], capture_output=True, text=True)
+    assert r.returncode != 0 and "CooMatrixDev" in r.stderr
+
+
+def test_cxx_caller_compiles_and_links(lib, tmp_path):
+    """tests/abi_cxx/abi_driver.cpp (a compiled C++ caller, no ctypes) builds against the header and the library;
+    it runs on the GPU box (tests/test_abi_cxx_gpu.py)."""
+    import subprocess
+    out = tmp_path / "abi_driver"
+    r = subprocess.run(["g++", "-std=c++14", "-O1", "-o", str(out), os.path.join(CXX, "abi_driver.cpp"),
+                        "-L", os.path.dirname(E.LIB_PATH), "-liaspgemm", "-Wl,-rpath," + os.path.dirname(E.LIB_PATH)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([str(out)], capture_output=True, text=True)
+    import torch
+    if not torch.cuda.is_available():
+        assert r.returncode == 1 and "no CPU fallback" in r.stdout       # loud, not silent
 
 
 def test_no_cpu_fallback(lib):
@@ -141,7 +192,7 @@ def test_options_round_trip_without_a_device(lib):
     """ias_set_option / ias_get_option are host-only bookkeeping: every documented knob exists, unknown names and
     negative values are refused (status 2 = IAS_E_ARG), and nothing needs a GPU."""
     names = ["global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win",
-             "g_coop", "gwin_takes_b2"]
+             "g_coop", "gwin_takes_b2", "trust_operand_cache"]
     header = open(os.path.join(ROOT, "include", "iaspgemm.h")).read()
     for n in names:
         assert '"%s"' % n in header, n            # documented where the entry point is declared

@@ -208,6 +208,32 @@ def test_streaming_matches_materialised(eng, oracle):
     dA.close()
 
 
+def test_stream_consumer_reassembles_c(eng, oracle):
+    """The streaming entry with a consumer callback: the batches, concatenated on the host, are C."""
+    A = W.rmat(11, 16, seed=5)
+    dA = eng.upload(*A)
+    (rp, ci, v), st = eng.CSR_MUL_CSR_DEV(dA, dA)
+    parts = []
+
+    def consumer(b):
+        assert b["nnz_total"] == st["nnz"] and b["row_ptr"][0] == 0
+        parts.append(b)
+
+    d = eng.csr_mul_csr_stream(dA, dA, budget_bytes=12 * 30000, consumer=consumer)
+    assert d["batches"] == len(parts) > 1 and [b["batch_index"] for b in parts] == list(range(len(parts)))
+    assert parts[0]["row_begin"] == 0 and parts[-1]["row_end"] == A[0]
+    assert all(x["row_end"] == y["row_begin"] for x, y in zip(parts, parts[1:]))
+    assert np.array_equal(np.concatenate([b["col_ind"] for b in parts]), ci)
+    assert np.array_equal(np.concatenate([b["values"] for b in parts]), v)
+    assert np.array_equal(np.concatenate([b["row_ptr"][:-1] + b["entry_base"] for b in parts] + [[st["nnz"]]]), rp)
+    # a consumer that fails stops the multiply with its status
+    from ia_spgemm_b200.engine import EngineError
+    with pytest.raises(EngineError) as ei:
+        eng.csr_mul_csr_stream(dA, dA, budget_bytes=12 * 30000, consumer=lambda b: 7)
+    assert ei.value.code == 7
+    dA.close()
+
+
 def test_int32_layout_and_host_path(eng, oracle):
     A = W.random_sparse(200, 200, 0.05, seed=9)
     dA = eng.upload(*A)
@@ -231,18 +257,79 @@ def test_launch_counter_moves(eng):
 
 
 def test_canonical_flag_cache_is_invalidated(eng, oracle):
-    """Row-block multiplies remember whether B is canonical; freeing or forgetting the operand drops that."""
-    for sort_columns in (True, False, True, False):        # the pool hands the same addresses out again
-        A = W.random_sparse(300, 300, 0.03, seed=11, sort_columns=sort_columns)
-        dA = eng.upload(*A)
-        want = sort_rows(*_oracle(oracle, A))
-        for _ in range(2):                                  # second call hits the cache
-            (rp, ci, v), st = eng.CSR_MUL_CSR_DEV(dA, dA, rows=(100, 250))
-            assert np.array_equal(rp, want[0][100:251] - want[0][100])
-            assert np.array_equal(ci, want[1][want[0][100]:want[0][250]])
-            assert np.allclose(v, want[2][want[0][100]:want[0][250]], rtol=1e-12, atol=1e-15)
-        eng.forget_operand(dA)
-        dA.close()
+    """Opt-in cache ("trust_operand_cache"): row-block multiplies remember whether B is canonical; freeing or
+    forgetting the operand drops that."""
+    eng.set_option("trust_operand_cache", 1)
+    try:
+        for sort_columns in (True, False, True, False):        # the pool hands the same addresses out again
+            A = W.random_sparse(300, 300, 0.03, seed=11, sort_columns=sort_columns)
+            dA = eng.upload(*A)
+            want = sort_rows(*_oracle(oracle, A))
+            for _ in range(2):                                  # second call hits the cache
+                (rp, ci, v), st = eng.CSR_MUL_CSR_DEV(dA, dA, rows=(100, 250))
+                assert np.array_equal(rp, want[0][100:251] - want[0][100])
+                assert np.array_equal(ci, want[1][want[0][100]:want[0][250]])
+                assert np.allclose(v, want[2][want[0][100]:want[0][250]], rtol=1e-12, atol=1e-15)
+            eng.forget_operand(dA)
+            dA.close()
+    finally:
+        eng.set_option("trust_operand_cache", 0)
+
+
+def test_caller_owned_operand_reallocated_at_the_same_address(eng, oracle):
+    """a torch tensor freed and re-allocated at the same address with the same shape and nnz must not
+    inherit the previous operand's canonical flag.  Default (cache off) and wrap_device's forget both cover it."""
+    import torch
+    A1 = W.random_sparse(300, 300, 0.03, seed=11, sort_columns=True)
+    perm_rows = np.repeat(np.arange(300), np.diff(A1[2]))
+    rng = np.random.default_rng(5)
+    order = np.lexsort((rng.random(len(A1[3])), perm_rows))        # same shape, same nnz, columns shuffled inside rows
+    A2 = (A1[0], A1[1], A1[2], A1[3][order], A1[4][order])
+    for trust in (0, 1):
+        eng.set_option("trust_operand_cache", trust)
+        ptrs = []
+        for A in (A1, A2):
+            t = [torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in A[2:]]
+            ptrs.append(t[1].data_ptr())
+            d = eng.wrap_device(A[0], A[1], len(A[3]), t[0].data_ptr(), t[1].data_ptr(), t[2].data_ptr())
+            want = sort_rows(*_oracle(oracle, A))
+            (rp, ci, v), st = eng.CSR_MUL_CSR_DEV(d, d, rows=(50, 250))
+            assert np.array_equal(rp, want[0][50:251] - want[0][50])
+            assert np.array_equal(ci, want[1][want[0][50]:want[0][250]])
+            d.close()
+            del t, d
+            torch.cuda.synchronize()
+        # (the caching allocator normally returns the same block: the test is meaningful when it does, harmless otherwise)
+    eng.set_option("trust_operand_cache", 0)
+
+
+def test_long_row_inside_a_small_row_block(eng, oracle):
+    """a row block with few rows that contains an A row of more than 64 entries, in a matrix whose
+    average row is short.  The long-row analysis kernel must run for it (it used to be gated on avg * block rows)."""
+    n = 4000
+    rng = np.random.default_rng(3)
+    rows_ci = [np.sort(rng.choice(n, size=2, replace=False)) for _ in range(n)]
+    for hub, ln in ((7, 65), (1234, 200), (3999, 900)):
+        rows_ci[hub] = np.sort(rng.choice(n, size=ln, replace=False))
+    rp = np.zeros(n + 1, np.int32)
+    rp[1:] = np.cumsum([len(r) for r in rows_ci])
+    ci = np.concatenate(rows_ci).astype(np.int32)
+    v = W.hash_values(1, W.row_index(rp), ci)
+    A = (n, n, rp, ci, v)
+    dA = eng.upload(*A)
+    for r0, r1 in ((7, 8), (1234, 1235), (1230, 1240), (3999, 4000), (0, 16)):
+        s, e = int(rp[r0]), int(rp[r1])
+        blk_rp = (rp[r0:r1 + 1] - rp[r0]).astype(np.int32)
+        want = oracle.csr_mul_csr(r1 - r0, n, blk_rp, ci[s:e], v[s:e], rp, ci, v)
+        got, st = eng.CSR_MUL_CSR_DEV(dA, dA, rows=(r0, r1))
+        assert_csr_parity(got, want)
+        assert st["products"] == oracle.getflop(blk_rp, ci[s:e], rp)
+        d = eng.csr_mul_csr_stream(dA, dA, rows=(r0, r1), want_row_nnz=True)
+        assert d["nnz"] == st["nnz"] and np.array_equal(d["row_nnz"], np.diff(want[0]))
+    bounds = eng.partition_rows(dA, dA, 64)                      # many parts: blocks of a handful of rows
+    total = sum(eng.CSR_MUL_CSR_DEV(dA, dA, rows=(x, y), download=False)[1]["nnz"] for x, y in zip(bounds, bounds[1:]) if y > x)
+    assert total == eng.CSR_MUL_CSR_DEV(dA, dA, download=False)[1]["nnz"]
+    dA.close()
 
 
 def test_touched_b_bytes(eng):

@@ -207,6 +207,11 @@ def test_coo_matches_oracle(eng, oracle, name, make):
         assert np.array_equal(got["col_ind"], wc["col_ind"][o]) and np.array_equal(got["row_offset"], wc["row_offset"])
         assert _close(got["values"], wc["values"][o], scale=abs_product(oracle, A, A))
     assert eng.lib.ias_sizeof_coo(A[0], c.nnz) == oracle.sizeof_coo(A[0], c.nnz)
+    c32, _ = eng.COO_MUL_COO_DEV(k, k, int32=True)               # the reference's CooMatrixDev layout (int32 nnz / row_offset)
+    got32 = eng.download_coo(c32)
+    for key in ("row_offset", "row_ind", "col_ind", "values"):
+        assert np.array_equal(got32[key], got[key]), key
+    eng.free_coo(c32)
     eng.free_coo(c); eng.free_coo(k); dA.close()
 
 
