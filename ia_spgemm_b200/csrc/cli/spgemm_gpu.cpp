@@ -55,17 +55,6 @@ static int write_image(const char *path, const long long *img)
     return 0;
 }
 
-// Rule-based stand-in for MatNet.Pred (CPU/MatNet.py:24-96): class index in the CPU numbering
-// 1 = CSR (the reference's slots 0/1 are MKL/CSR), 2 = DIA, 3 = ELL, 4 = COO.
-static int select_format(const double *f, bool dia_ok, bool ell_ok)
-{
-    double diag_fill = f[2] / (f[18] * f[0]);          // nnz / (ndiag * rows): how full the stored diagonals are
-    double ell_eff = f[24];
-    if (dia_ok && diag_fill > 0.5) return 2;
-    if (ell_ok && ell_eff > 0.9 && f[8] < 0.05) return 3;
-    return 1;
-}
-
 static bool file_exists(const char *p)
 {
     struct stat st;
@@ -208,7 +197,7 @@ int main(int argc, char **argv)
     now(&t1); trans[3] = ms(t0, t1);
     bool dia_ok = a_dia.choice && b_dia.choice, ell_ok = a_ell.choice && b_ell.choice;
 
-    int c = select_format(feat, dia_ok, ell_ok);
+    int c = ias_select_format(feat, dia_ok, ell_ok);      // the rule; MatNet overrides it below when weights are present
     // MatNet.Pred (CPU/MatNet.py:24-96, GPU/MatNet.py) on the two density images and the feature vector.  The reference
     // always loads ./NetWeights/<machine>_weights.h5 from the working directory; so does this front end when the files
     // are there.  A 5-class (CPU) net drives the format dispatch; the 3-class (GPU) net names a library SpGEMM, all of

@@ -21,6 +21,8 @@ struct Tuning {
     long long gwin_takes_b2 = 1;      // rows of the large CTA hash bin go to the windowed kernel when it is selected
     long long gwin_max_sw = 1;        // numeric: use the windowed kernel up to this many super-windows per row (0: always);
                                       // beyond, the per-window scans of the cells cost more than the L2 lookups they replace
+    long long g_ldca = 0;             // L2 bitmap kernel: accumulate-pass cell lookups go through L1
+    long long g_block = 1024;         // L2 bitmap kernel: threads per CTA (1024: one row per SM, 512: two)
     long long trust_operand_cache = 0; // 1: remember B's canonical flag per operand (pointers + shape) across calls; the caller
                                       // promises not to rewrite or re-allocate an operand without ias_forget_operand
 };

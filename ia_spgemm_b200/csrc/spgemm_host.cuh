@@ -116,11 +116,12 @@ inline bool g_wide(int ncols)
     return (double)L.slot_words * 4.0 * 2.0 * ctx().sm_count > 160e6;
 }
 
-inline int ensure_gwork(RangeWork &rw, int ncols, long long nrows_g, bool one_per_sm = false)
+inline int ensure_gwork(RangeWork &rw, int ncols, long long nrows_g, int per_sm = 0 /* 0: by slot size */)
 {
     if (nrows_g <= 0) return IAS_OK;
     GLayout L = GLayout::make(ncols);
-    int slots = (int)std::min<long long>(nrows_g, ((one_per_sm || g_wide(ncols)) ? 1LL : 2LL) * ctx().sm_count);
+    if (per_sm == 0) per_sm = g_wide(ncols) ? 1 : 2;
+    int slots = (int)std::min<long long>(nrows_g, (long long)per_sm * ctx().sm_count);
     if (rw.gslots >= slots && rw.gwork.p) return IAS_OK;
     IAS_TRY(rw.gwork.alloc((size_t)slots * L.slot_words));
     IAS_CUDA(cudaMemsetAsync(rw.gwork.p, 0, (size_t)slots * L.slot_words * sizeof(unsigned), ctx().stream));
@@ -162,11 +163,11 @@ inline int gwin_grid(K kernel, size_t smem, long long nrows_g, int *grid)
 // phase clocks of the windowed kernels since the last dump (stderr), in SM clocks summed over CTAs
 inline void gwin_profile_dump(const char *what)
 {
-    unsigned long long h[32];
+    unsigned long long h[64];
     cudaStreamSynchronize(ctx().stream);
     if (cudaMemcpyFromSymbol(h, g_gwin_prof, sizeof h) != cudaSuccess) return;
     fprintf(stderr, "[gwin %s]", what);
-    for (int i = 0; i < 32; ++i) fprintf(stderr, " %d:%llu", i, h[i]);
+    for (int i = 0; i < 64; ++i) if (h[i]) fprintf(stderr, " %d:%llu", i, h[i]);
     fprintf(stderr, "\n");
     memset(h, 0, sizeof h);
     cudaMemcpyToSymbol(g_gwin_prof, h, sizeof h);
@@ -468,20 +469,31 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
     } else if (bl.count[BIN_G]) {
         IAS_BIN_BEGIN(8 + BIN_G);
         int m = (int)bl.count[BIN_G];
-        IAS_TRY(ensure_gwork(rw, ncols_b, m, true));
+        const bool two = c.tune.g_block == 512;
+        IAS_TRY(ensure_gwork(rw, ncols_b, m, two ? 2 : 1));
         IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
         {
-            auto k = k_num_global<AV, BV, 1024>;
-            int win = (int)std::min<long long>(20480, std::max<long long>(16, c.tune.g_win & ~15LL));   // 160 KB tile of fp64 partial sums (192 KB would leave 28 KB of L1 for the
-                                                               // B-row stream: ncu/clock64 showed the mark pass 1.6x slower)
+            // 160 KB tile of fp64 partial sums per SM (192 KB would leave 28 KB of L1 for the B-row stream: ncu/clock64
+            // showed the mark pass 1.6x slower); with two 512-thread CTAs per SM each gets half
+            int win = (int)std::min<long long>(two ? 10240 : 20480, std::max<long long>(16, c.tune.g_win & ~15LL));
             size_t sm = (size_t)win * sizeof(double);
-            IAS_TRY(opt_in_smem(k, sm));
             int smem_mark = rw.b_canonical && c.tune.global_rows_smem != 0 && (win % 16) == 0 ? 1 : 0;      // bit 0: mark pass in smem
             if (rw.b_canonical && c.tune.g_coop) smem_mark |= 2;                                            // bit 1: accumulate via gwin_build / gwin_run
-            IAS_LAUNCH(k, rw.gslots, 1024, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p, GLayout::make(ncols_b),
-                       rw.cursor.p, win, rw.b_canonical, smem_mark, ncols_b);
+            if (c.tune.g_ldca) smem_mark |= 4;                                                              // bit 2: cell lookups through L1
+            if (two) {
+                auto k = k_num_global<AV, BV, 512>;
+                IAS_TRY(opt_in_smem(k, sm));
+                IAS_LAUNCH(k, std::min<long long>(rw.gslots, 2LL * c.sm_count), 512, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
+                           GLayout::make(ncols_b), rw.cursor.p, win, rw.b_canonical, smem_mark, ncols_b);
+            } else {
+                auto k = k_num_global<AV, BV, 1024>;
+                IAS_TRY(opt_in_smem(k, sm));
+                IAS_LAUNCH(k, std::min<long long>(rw.gslots, (long long)c.sm_count), 1024, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
+                           GLayout::make(ncols_b), rw.cursor.p, win, rw.b_canonical, smem_mark, ncols_b);
+            }
         }
         IAS_BIN_END(8 + BIN_G);
+        GWIN_PROFILE_DUMP("num_global");
         rw.num_timed[BIN_G] = true;
     }
     (void)st;

@@ -927,7 +927,7 @@ __global__ void __launch_bounds__(BLOCK) k_esc_warp(const int *__restrict__ rows
 
 // optional phase clocks (make prof): thread 0 of every CTA adds up clock64 deltas per phase
 #ifdef IAS_GWIN_PROFILE
-static __device__ unsigned long long g_gwin_prof[32];
+static __device__ unsigned long long g_gwin_prof[64];
 #define GP_START() long long gp_t = clock64()
 #define GP_ADD(slot)                                                                           \
     do {                                                                                       \
@@ -1230,6 +1230,8 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
         long long gs = out.start(li);
         const int n = out.count(li);
         typename AV::off_t pa = A.begin(i), pe = A.end(i);
+        GP_START();
+        GP_CNT(32, 1);
         // 1. mark the columns of the row.  Canonical B: in shared memory, one super-window of 2*win*32 columns at a
         //    time (the bitmap borrows the accumulate tile), each flushed to the row's cells with coalesced stores --
         //    no L2 atomic per product (that pass was 38 % of this kernel at R-MAT scale 22).
@@ -1245,6 +1247,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
                 bool any = false;
                 for (typename AV::off_t base = pa; base < pe; base += BLOCK) {
                     const int total = gwin_build<false, BLOCK>(A, B, base, pe, tile, c_lo, c_hi);
+                    GP_ADD(33);
                     if (total) {
                         any = true;
                         gwin_run<false, BLOCK>(tile, total, [&](const typename BV::off_t (&q)[PB], const double (&)[PB], unsigned valid) {
@@ -1262,6 +1265,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
                         });
                     }
                     __syncthreads();
+                    GP_ADD(34);
                 }
                 if (!any) continue;
                 // flush: a warp per block of 32 words; the block's word mask comes from one ballot
@@ -1275,6 +1279,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
                     if (m && (threadIdx.x & 31) == 0) wsum[(w0g + wb) >> 5] = m;
                 }
                 __syncthreads();
+                GP_ADD(35);
             }
         } else {
             int dummy = 0;
@@ -1323,6 +1328,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
         }
         __threadfence();          // window bounds below are read back from c_ci by another thread
         __syncthreads();
+        GP_ADD(36);
         // 3. one window of `win` ranks at a time: accumulate in the shared-memory tile, then write it out
         for (int wbase = 0; wbase < n; wbase += win) {
             const int wn = min(win, n - wbase);
@@ -1332,6 +1338,8 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
             }
             for (int t = threadIdx.x; t < wn; t += BLOCK) acc[t] = 0.0;
             __syncthreads();
+            GP_ADD(37);
+            GP_CNT(42, 1);
             const int c_lo = s_lo, c_hi = s_hi;
             auto add = [&](const typename BV::off_t (&q)[PB], const double (&av)[PB], unsigned valid) {
                 int k[PB];
@@ -1345,7 +1353,9 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
 #pragma unroll
                 for (int u = 0; u < PB; ++u) {
                     if (k[u] < c_lo || k[u] >= c_hi) k[u] = -1;
-                    cell[u] = k[u] >= 0 ? __ldcg(wp + (k[u] >> 5)) : make_uint2(0, 0);
+                    // (smem_mark & 4: through L1 -- the cells of a dense window's column range are re-read many times and
+                    // nothing else writes them during the pass; the __threadfence above dropped every stale line)
+                    cell[u] = k[u] < 0 ? make_uint2(0, 0) : (smem_mark & 4) ? wp[k[u] >> 5] : __ldcg(wp + (k[u] >> 5));
                 }
 #pragma unroll
                 for (int u = 0; u < PB; ++u) {
@@ -1359,18 +1369,22 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
                 const bool cut = n > win;
                 for (typename AV::off_t base = pa; base < pe; base += BLOCK) {
                     const int total = gwin_build<true, BLOCK>(A, B, base, pe, tile, cut ? c_lo : 0, cut ? c_hi : 0x7fffffff);
+                    GP_ADD(38);
                     if (total) gwin_run<true, BLOCK>(tile, total, add);
                     __syncthreads();
+                    GP_ADD(39);
                 }
             } else if (b_canonical && n > win) cta_products<true, BLOCK>(A, B, pa, pe, tile, add, ColumnWindow<BV>{B, c_lo, c_hi});
             else cta_products<true, BLOCK>(A, B, pa, pe, tile, add);
             __syncthreads();
             for (int t = threadIdx.x; t < wn; t += BLOCK) c_v[gs + wbase + t] = acc[t];
             __syncthreads();
+            GP_ADD(40);
         }
         // 4. leave the slot clean for the next row
         g_clear<BLOCK>(wp, summary, wsum, L);
         __syncthreads();
+        GP_ADD(41);
     }
 }
 

@@ -69,6 +69,16 @@ class StreamBatch(C.Structure):        # IasStreamBatch
                 ("cuda_stream", C.c_void_p)]
 
 
+class AutoResult(C.Structure):         # IasAutoResult
+    _fields_ = [("format", C.c_int), ("row", C.c_int), ("col", C.c_int), ("nnz", C.c_longlong),
+                ("row_ptr", _L), ("col_ind", _I), ("values", _D),
+                ("num_diagonals", C.c_int), ("diagonal_ind", _I), ("diagonal_offsets", _I),
+                ("max_nnz_per_row", C.c_int), ("nnz_row", _I),
+                ("features", C.c_double * 26),
+                ("ms_h2d", C.c_double), ("ms_select", C.c_double), ("ms_convert", C.c_double), ("ms_multiply", C.c_double),
+                ("ms_d2h", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong)]
+
+
 STREAM_CONSUMER = C.CFUNCTYPE(C.c_int, C.POINTER(StreamBatch), C.c_void_p)
 
 
@@ -120,6 +130,7 @@ ABI_SYMBOLS = [
     "ias_gen_poisson2d", "ias_gen_uniform", "ias_gen_rmat",
     "ias_matnet_load", "ias_matnet_create", "ias_matnet_set_tensor", "ias_matnet_get_tensor", "ias_matnet_shape",
     "ias_matnet_predict", "ias_matnet_free",
+    "ias_select_format", "ias_spgemm_auto_host",
 ]
 
 
@@ -206,6 +217,8 @@ def load_library():
         "ias_csr_mul_csr_stream_cb": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, STREAM_CONSUMER, C.c_void_p,
                                       C.c_void_p],
         "ias_dia_relayout": [C.c_void_p, C.c_int, C.c_void_p],
+        "ias_select_format": [C.c_void_p, C.c_int, C.c_int],
+        "ias_spgemm_auto_host": [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p],
         "ias_getinfo3": [C.c_int, C.c_longlong, C.c_int, _D],
         "ias_gen_rmat": [C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double, C.c_void_p],
         "ias_csr_to_dia": [C.c_void_p, C.c_double, C.c_void_p], "ias_csr_to_ell": [C.c_void_p, C.c_double, C.c_void_p],
@@ -407,6 +420,39 @@ class Engine:
                np.ctypeslib.as_array(ci, shape=(n,)) if n else np.zeros(0, np.int32),
                np.ctypeslib.as_array(v, shape=(n,)) if n else np.zeros(0, np.float64))
         return out, st.as_dict(), h2d.value, d2h.value
+
+    def spgemm_auto(self, A, B, gate=20.0, matnet=None):
+        """The front end's path on host operands (ias_spgemm_auto_host): features -> selection -> conversion ->
+        multiply -> host result in the selected format.  Returns a dict with views of engine-owned pinned memory."""
+        hA = self.host_csr(*A)
+        hB = hA if B is A else self.host_csr(*B)
+        r = AutoResult()
+        self._ck(self.lib.ias_spgemm_auto_host(C.byref(hA), C.byref(hB), gate, matnet.h if matnet is not None else None, C.byref(r)))
+        out = {"format": {1: "csr", 2: "dia", 3: "ell"}[r.format], "row": r.row, "col": r.col, "nnz": r.nnz,
+               "features": np.array(r.features), "h2d_bytes": r.h2d_bytes, "d2h_bytes": r.d2h_bytes,
+               "ms": {k: getattr(r, "ms_" + k) for k in ("h2d", "select", "convert", "multiply", "d2h")}}
+        arr = np.ctypeslib.as_array
+        if r.format == 1:
+            out["row_ptr"] = arr(r.row_ptr, shape=(r.row + 1,))
+            out["col_ind"] = arr(r.col_ind, shape=(r.nnz,)) if r.nnz else np.zeros(0, np.int32)
+            out["values"] = arr(r.values, shape=(r.nnz,)) if r.nnz else np.zeros(0)
+        elif r.format == 2:
+            nd = r.num_diagonals
+            out["num_diagonals"] = nd
+            out["diagonal_offsets"] = arr(r.diagonal_offsets, shape=(nd,)) if nd else np.zeros(0, np.int32)
+            out["diagonal_ind"] = arr(r.diagonal_ind, shape=(max(r.row + r.col - 1, 1),))
+            out["values"] = arr(r.values, shape=(r.row, nd)) if r.row * nd else np.zeros((r.row, nd))
+        else:
+            w = r.max_nnz_per_row
+            out["width"] = w
+            out["nnz_row"] = arr(r.nnz_row, shape=(r.row,)) if r.row else np.zeros(0, np.int32)
+            out["col_ind"] = arr(r.col_ind, shape=(r.row, w)) if r.row * w else np.zeros((r.row, w), np.int32)
+            out["values"] = arr(r.values, shape=(r.row, w)) if r.row * w else np.zeros((r.row, w))
+        return out
+
+    def select_format(self, features26, dia_ok=True, ell_ok=True):
+        f = np.ascontiguousarray(features26, dtype=np.float64)
+        return int(self.lib.ias_select_format(f.ctypes.data_as(_D), int(dia_ok), int(ell_ok)))
 
     def csr_mul_csr_stream(self, A, B, rows=None, budget_bytes=0, want_row_nnz=False, consumer=None):
         """consumer(batch_dict) is called once per row batch with host copies of the batch (row_begin, row_end,

@@ -315,6 +315,35 @@ int ias_matnet_predict(void *net, const long long *img1_16384, const long long *
                        int *cls, double *probs);
 void ias_matnet_free(void *net);
 
+/* ---------------------------------------------------------------- the front end's path in one call */
+/* Fallback rule of the selector when no MatNet weights are at hand.  f = the 26 features; returns the class in the
+ * CPU numbering of MatNet.Pred (CPU/MatNet.py:92; 1 = CSR, 2 = DIA, 3 = ELL). */
+int ias_select_format(const double *features26, int dia_ok, int ell_ok);
+/* features -> selection -> conversion -> multiply -> host result, i.e. CPU/main.cpp:655-935 with the selected
+ * algorithm being the one that runs.  Operands are host CSR (as the loader leaves them); the result comes back in the
+ * selected format's own layout, in pinned host memory owned by the engine (valid until the next host call or
+ * ias_release_host):  format 1 CSR   row_ptr[row+1], col_ind[nnz], values[nnz]            (CSR_MUL_CSR, csr:85)
+ *                     format 2 DIA   diagonal_ind[row+col-1], diagonal_offsets[num_diagonals],
+ *                                    values[row][num_diagonals] row-major                  (DIA_mul_DIA, dia:101)
+ *                     format 3 ELL   nnz_row[row], col_ind / values [row][max_nnz_per_row] (ELL_MUL_ELL, ell:80)
+ * matnet: handle from ias_matnet_load (a 5-class net drives the dispatch) or NULL for the rule; gate: 20 (GPU release). */
+typedef struct {
+    int format;
+    int row, col;
+    long long nnz;                 /* CSR: entries; DIA: row*num_diagonals cells; ELL: sum of the row lengths */
+    long long *row_ptr;            /* CSR */
+    int *col_ind;                  /* CSR, ELL */
+    double *values;                /* all formats */
+    int num_diagonals;             /* DIA */
+    int *diagonal_ind, *diagonal_offsets;
+    int max_nnz_per_row;           /* ELL */
+    int *nnz_row;
+    double features[26];
+    double ms_h2d, ms_select, ms_convert, ms_multiply, ms_d2h;     /* CUDA events on the engine stream */
+    long long h2d_bytes, d2h_bytes;
+} IasAutoResult;
+int ias_spgemm_auto_host(const IasCsrMatrix *A, const IasCsrMatrix *B, double gate, void *matnet, IasAutoResult *out);
+
 /* ---------------------------------------------------------------- synthetic operands (device) */
 /* BASELINE.json configs, bit-identical to ia_spgemm_b200/workloads.py */
 int ias_gen_poisson2d(int nx, int ny, IasCsrMatrixDev *out);   /* nx*ny nodes, row-major node order */

@@ -69,6 +69,9 @@ class Oracle:
     def threads(self):
         return int(self.lib.ora_num_threads())
 
+    def set_threads(self, n):
+        self.lib.ora_set_threads(C.c_int(int(n)))
+
     # -- loader ---------------------------------------------------------------
     def mtx_load(self, path):
         r, c, n = C.c_int(), C.c_int(), C.c_int()
@@ -256,6 +259,10 @@ class Ref:
 
     def threads(self):
         return int(self.lib.ref_omp_threads()), int(self.lib.ref_mkl_threads())
+
+    def set_threads(self, n):
+        """OpenMP and MKL thread counts for the timed baseline (torchrun exports OMP_NUM_THREADS=1)."""
+        self.lib.ref_set_threads(C.c_int(int(n)))
 
     def mkl_version(self):
         buf = C.create_string_buffer(256)

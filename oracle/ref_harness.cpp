@@ -42,6 +42,14 @@ extern "C" {
 void ref_free(void *p) { free(p); }
 int ref_mkl_threads() { return mkl_get_max_threads(); }
 int ref_omp_threads() { return omp_get_max_threads(); }
+/* launchers such as torchrun export OMP_NUM_THREADS=1: the timed baseline sets its thread counts explicitly */
+extern "C" void mkl_serv_set_num_threads(int);
+void ref_set_threads(int n)
+{
+    if (n < 1) n = 1;
+    omp_set_num_threads(n);
+    mkl_serv_set_num_threads(n);
+}
 void ref_mkl_version(char *buf, int len) { MKL_Get_Version_String(buf, len); }
 
 /* CSR_MUL_CSR (common_csr.h:85-193); returns elapsed ms of the call */

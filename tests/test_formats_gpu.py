@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 from ia_spgemm_b200 import workloads as W
-from util import RECT, RTOL, SQUARE, abs_product, decode_img, sort_rows
+from util import RECT, RTOL, SQUARE, abs_product, assert_csr_parity, decode_img, sort_rows
 
 pytestmark = pytest.mark.gpu
 
@@ -383,3 +383,50 @@ def test_ell_and_coo_views_through_every_bin(eng, oracle):
             eng.free_ell(eb); dB.close()
         dA.close()
     eng.set_option("gwin_takes_b2", 1)
+
+
+# ---------------------------------------------------------------- the front end's path in one call (ias_spgemm_auto_host)
+def test_auto_host_picks_the_format_and_matches_the_oracle(eng, oracle):
+    """features -> selection -> conversion -> multiply -> host result.  Banded operands come back as DIA, fixed-width
+    operands as ELL, everything else as CSR; each equals the reference kernel of that format on the same input."""
+    # DIA
+    A = W.poisson2d(48)
+    r = eng.spgemm_auto(A, A)
+    assert r["format"] == "dia" and r["num_diagonals"] == 13
+    wa = oracle.csr_to_dia(*A, gate=20.0)
+    want = oracle.dia_mul_dia(wa, wa)
+    assert np.array_equal(r["diagonal_offsets"], want["diagonal_offsets"]) and np.array_equal(r["diagonal_ind"], want["diagonal_ind"])
+    absa = dict(wa, values=np.abs(wa["values"]))
+    assert _close(r["values"], want["values"], scale=oracle.dia_mul_dia(absa, absa)["values"])
+    assert np.allclose(r["features"], oracle.features26(A, A, gate=20.0), rtol=1e-12)
+    assert r["h2d_bytes"] == 4 * (A[0] + 1) + 12 * len(A[3]) and r["d2h_bytes"] >= 8 * A[0] * 13
+    # ELL
+    U = W.uniform_rows(5000, 8, seed=3)
+    r = eng.spgemm_auto(U, U)
+    assert r["format"] == "ell"
+    we = oracle.csr_to_ell(*U, gate=20.0)
+    want = oracle.ell_mul_ell(we, we)
+    assert r["width"] == want["width"] and np.array_equal(r["nnz_row"], want["nnz_row"])
+    for i in range(0, U[0], 97):
+        n = int(want["nnz_row"][i])
+        o = np.argsort(want["col_ind"][i, :n], kind="stable")
+        assert np.array_equal(r["col_ind"][i, :n], want["col_ind"][i, :n][o])
+        assert np.allclose(r["values"][i, :n], want["values"][i, :n][o], rtol=1e-12, atol=0)
+        assert not r["values"][i, n:].any() and not r["col_ind"][i, n:].any()
+    # CSR (two different operands)
+    X, Y = W.random_sparse(300, 200, 0.05, seed=21), W.random_sparse(200, 500, 0.04, seed=22, sort_columns=False)
+    r = eng.spgemm_auto(X, Y)
+    assert r["format"] == "csr"
+    want = oracle.csr_mul_csr(X[0], Y[1], X[2], X[3], X[4], Y[2], Y[3], Y[4])
+    assert_csr_parity((r["row_ptr"].copy(), r["col_ind"].copy(), r["values"].copy()), want, mag=abs_product(oracle, X, Y))
+    eng.lib.ias_release_host()
+
+
+def test_select_format_rule(eng):
+    f = np.zeros(26)
+    f[0], f[2], f[18], f[24], f[8] = 1000, 4900, 5, 0.98, 0.01
+    assert eng.select_format(f, True, True) == 2 and eng.select_format(f, False, True) == 3 and eng.select_format(f, False, False) == 1
+    f[18] = 400
+    assert eng.select_format(f, True, True) == 3
+    f[8] = 0.5
+    assert eng.select_format(f, True, True) == 1

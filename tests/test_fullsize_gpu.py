@@ -99,3 +99,84 @@ def test_uniform_full_size_properties(eng):
     assert eng.checksum_ptr(c.values_dev, c.row * c.max_nnz_per_row) == pytest.approx(st["checksum"], rel=1e-11)
     eng.free_ell(c); eng.free_ell(e)
     dA.close()
+
+
+# ---------------------------------------------------------------- entry-wise parity at BASELINE.json's full sizes
+# C does not fit the host oracle as a whole, so deterministic row blocks are compared entry by
+# entry with CSR_MUL_CSR(A[r0:r1,:], A) (the reference function takes a rectangular A, csr:88-89): row_ptr and sorted
+# columns bit-exact, values within 1e-12 of the entry.  The device operand is downloaded (the generators are pinned
+# bit-identical to workloads.py in test_formats_gpu.py) so that the host never regenerates 10^8 entries.
+def _block_parity(eng, oracle, dA, host, blocks, mag=False):
+    rows, cols, rp, ci, v = host
+    for r0, r1 in blocks:
+        s, e = int(rp[r0]), int(rp[r1])
+        blk_rp = (rp[r0:r1 + 1] - rp[r0]).astype(np.int32)
+        want = oracle.csr_mul_csr(r1 - r0, cols, blk_rp, ci[s:e], v[s:e], rp, ci, v)
+        got, st = eng.CSR_MUL_CSR_DEV(dA, dA, rows=(r0, r1))
+        m = None
+        if mag:
+            a = oracle.csr_mul_csr(r1 - r0, cols, blk_rp, ci[s:e], np.abs(v[s:e]), rp, ci, np.abs(v))
+            m = sort_rows(*a)[2]
+        assert_csr_parity(got, want, mag=m)
+        assert st["products"] == oracle.getflop(blk_rp, ci[s:e], rp)
+        yield (r0, r1), got, st
+
+
+def test_poisson_4096_sampled_blocks_entrywise(eng, oracle):
+    """configs[1] at full size: the first grid line (boundary rows), an interior band, the last grid line."""
+    N = 4096
+    dA = eng.gen_poisson2d(N)
+    host = dA.download()
+    n = N * N
+    blocks = ((0, N + 5), (N * 2000 - 3, N * 2000 + 3000), (n - N - 7, n))
+    for (r0, r1), got, st in _block_parity(eng, oracle, dA, host, blocks, mag=True):      # 4 / -1 stencil: terms cancel
+        inner = np.diff(got[0])
+        assert inner.max() == 13 and inner.min() >= 6
+    dA.close()
+
+
+def test_uniform_8m_sampled_blocks_entrywise(eng, oracle):
+    """configs[2] at full size: three row blocks of the warp bin (16 x 16 products per row, nnz(C_i) <= 256)."""
+    n = 8_000_000
+    dA = eng.gen_uniform(n, 16, seed=1)
+    host = dA.download()
+    for (r0, r1), got, st in _block_parity(eng, oracle, dA, host, ((0, 3000), (n // 2 + 11, n // 2 + 3011), (n - 3000, n))):
+        assert st["products"] == 256 * (r1 - r0)
+    dA.close()
+
+
+def test_rmat22_sampled_blocks_entrywise_and_streamed_totals(eng, oracle):
+    """configs[3] at full size.  Rows 0-32 are the hub rows (tens of millions of products each, through the
+    multi-window global-row kernel), then a middle block and the tail.  The streamed run of the whole matrix must
+    report the same per-row nnz on those rows, and its totals must be self-consistent."""
+    dA = eng.gen_rmat(22, 16, seed=1)
+    host = dA.download()
+    rows = host[0]
+    blocks = ((0, 32), (40_000, 40_400), (rows // 2, rows // 2 + 3000), (rows - 30_000, rows))
+    seen = {}
+    for (r0, r1), got, st in _block_parity(eng, oracle, dA, host, blocks):
+        seen[(r0, r1)] = (np.diff(got[0]), float(got[2].sum()))
+        if r0 == 0:
+            assert st["num_bin_rows"][5] > 0 and np.diff(got[0]).max() > 500_000       # really the global-row path
+    st = eng.csr_mul_csr_stream(dA, dA, want_row_nnz=True)
+    assert st["batches"] > 1 and st["products"] == eng.GetFlop(dA, dA) and st["products"] > 2 ** 37
+    assert int(st["row_nnz"].astype(np.int64).sum()) == st["nnz"] and st["nnz"] > 2 ** 35      # beyond int32 by far
+    for (r0, r1), (cnt, _) in seen.items():
+        assert np.array_equal(st["row_nnz"][r0:r1], cnt)
+    dA.close()
+
+
+def test_rmat25_blocks_on_one_gpu(eng, oracle):
+    """configs[4]: the scale-25 operand (5.3e8 entries, 6.5 GB) on one GPU, two row blocks against the oracle --
+    33.5 M columns (1 M bitmap words, 8 MB workspace slots), products and offsets far beyond int32."""
+    info = eng.device_info()
+    if info["free_bytes"] < 60 * 10**9:
+        pytest.skip("needs ~60 GB of free HBM for the scale-25 generator")
+    dA = eng.gen_rmat(25, 16, seed=1)
+    assert dA.nnz > 500_000_000
+    host = dA.download()
+    rows = host[0]
+    for (r0, r1), got, st in _block_parity(eng, oracle, dA, host, ((64, 72), (rows // 2 + 5, rows // 2 + 2005))):
+        if r0 == 64:
+            assert st["num_bin_rows"][5] > 0
+    dA.close()
