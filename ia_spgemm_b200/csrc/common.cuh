@@ -16,13 +16,18 @@ struct Tuning {
     long long gwin_win = 0;           // numeric: entries per rank window (0: whatever shared memory is left)
     long long gwin_sym_swords = 0;    // symbolic: bitmap words per super-window (0: as many as fit)
     long long gwin_smem_kb = 0;       // cap on the dynamic shared memory of the windowed kernels (0: device limit)
-    long long g_win = 20480;          // L2 bitmap kernel: entries per accumulate window (multiple of 16; 160 KB tile by default)
+    long long g_win = 20480;          // L2 bitmap kernel: entries per accumulate window (multiple of 16; capped at 20480, 16384 for the second generation)
     long long g_coop = 1;             // L2 bitmap kernel: accumulate pass enumerates products with gwin_build / gwin_run
     long long gwin_takes_b2 = 1;      // rows of the large CTA hash bin go to the windowed kernel when it is selected
     long long gwin_max_sw = 1;        // numeric: use the windowed kernel up to this many super-windows per row (0: always);
                                       // beyond, the per-window scans of the cells cost more than the L2 lookups they replace
     long long g_ldca = 0;             // L2 bitmap kernel: accumulate-pass cell lookups go through L1
+    long long g_v2 = 1;               // L2 bitmap kernel, canonical B: second generation (rank + emit from shared memory, split tables)
+    long long g_tbl = 8192;           // ... its split-table capacity (ints of shared memory)
+    long long g_lpt = 1;              // global rows are handed out in order of decreasing work
     long long g_block = 1024;         // L2 bitmap kernel: threads per CTA (1024: one row per SM, 512: two)
+    long long bulk_store = 1;         // shared -> global bulk copies (cp.async.bulk) for staged output tiles (0: per-thread stores)
+    long long ell_onepass = 1;        // ELL x ELL: one-pass register-sort kernel when a row's products fit (0: always the pipeline)
     long long trust_operand_cache = 0; // 1: remember B's canonical flag per operand (pointers + shape) across calls; the caller
                                       // promises not to rewrite or re-allocate an operand without ias_forget_operand
 };
@@ -107,6 +112,37 @@ struct DBuf {
 };
 
 inline unsigned grid_for(long long n, int block) { return (unsigned)((n + block - 1) / block); }
+
+// ---------------------------------------------------------------- bulk asynchronous copies (TMA, 1-D: cp.async.bulk -> SASS UBLKCP)
+// shared -> global: the issuing thread's earlier generic-proxy writes to the source (and, after a barrier, everyone's) are
+// made visible to the async proxy with fence.proxy.async; source, destination and size must be multiples of 16 bytes.
+__device__ __forceinline__ void fence_proxy_async_shared() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void bulk_store_shared_to_global(void *gdst, const void *ssrc, unsigned bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 :: "l"(gdst), "r"((unsigned)__cvta_generic_to_shared(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_commit_group() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_group_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+// global -> shared with an mbarrier that counts the bytes (SASS: UBLKCP + SYNCS)
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_load_global_to_shared(void *sdst, const void *gsrc, unsigned bytes, unsigned long long *bar)
+{
+    asm volatile("cp.async.bulk.shared::cta.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((unsigned)__cvta_generic_to_shared(sdst)), "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity)
+{
+    asm volatile("{\n\t.reg .pred p;\n\tWAIT_%=:\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t@p bra DONE_%=;\n\tbra WAIT_%=;\n\tDONE_%=:\n\t}"
+                 :: "r"((unsigned)__cvta_generic_to_shared(bar)), "r"(parity) : "memory");
+}
 
 // ---------------------------------------------------------------- device helpers
 __device__ __forceinline__ unsigned hash_col(int k) { return (unsigned)k * 0x9E3779B1u; }

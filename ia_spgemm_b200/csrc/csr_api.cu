@@ -211,7 +211,8 @@ static int host_arena(size_t bytes, void **p)
         c.h_arena = nullptr; c.h_arena_bytes = 0;
         size_t want = bytes + bytes / 8;
         cudaError_t e = cudaMallocHost(&c.h_arena, want);
-        if (e != cudaSuccess) { cudaGetLastError(); return fail(IAS_E_NOMEM, "pinned host allocation of %zu bytes failed", want); }
+        if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMallocHost(&c.h_arena, want); }      // without the growth slack
+        if (e != cudaSuccess) { cudaGetLastError(); c.h_arena = nullptr; return fail(IAS_E_NOMEM, "pinned host allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); }
         c.h_arena_bytes = want;
     }
     *p = c.h_arena;

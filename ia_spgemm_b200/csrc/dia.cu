@@ -71,7 +71,7 @@ struct DiaPair {
 };
 
 template <int BLOCK, bool TABLES_IN_SMEM>
-__global__ void __launch_bounds__(BLOCK) k_dia_mul_dia(int rows, int c_nd, const double *__restrict__ a_val,
+__global__ void __launch_bounds__(BLOCK) k_dia_mul_dia(int row0, int rows /* one past the last row */, int c_nd, const double *__restrict__ a_val,
                                                        const double *__restrict__ b_val,
                                                        const int *__restrict__ pair_start /* c_nd+1 */,
                                                        const DiaPair *__restrict__ pairs, int npairs,
@@ -88,7 +88,8 @@ __global__ void __launch_bounds__(BLOCK) k_dia_mul_dia(int rows, int c_nd, const
         __syncthreads();
         s_pairs = w_pairs; s_start = w_start;
     }
-    for (long long base = (long long)blockIdx.x * (2 * BLOCK); base < rows; base += (long long)gridDim.x * (2 * BLOCK)) {
+    const size_t out_rows = (size_t)(rows - row0);          // C holds rows [row0, rows): values[d * out_rows + (i - row0)]
+    for (long long base = row0 + (long long)blockIdx.x * (2 * BLOCK); base < rows; base += (long long)gridDim.x * (2 * BLOCK)) {
         const long long i0 = base + threadIdx.x, i1 = i0 + BLOCK;
         const bool v0 = i0 < rows, v1 = i1 < rows;
         for (int d = 0; d < c_nd; ++d) {
@@ -99,8 +100,8 @@ __global__ void __launch_bounds__(BLOCK) k_dia_mul_dia(int rows, int c_nd, const
                 if (i0 >= P.lo && i0 < P.hi) acc0 += __ldg(a_val + P.a0 + i0) * __ldg(b_val + P.b0 + i0);
                 if (i1 >= P.lo && i1 < P.hi) acc1 += __ldg(a_val + P.a0 + i1) * __ldg(b_val + P.b0 + i1);
             }
-            if (v0) c_val[(size_t)d * rows + i0] = acc0;
-            if (v1) c_val[(size_t)d * rows + i1] = acc1;
+            if (v0) c_val[(size_t)d * out_rows + (i0 - row0)] = acc0;
+            if (v1) c_val[(size_t)d * out_rows + (i1 - row0)] = acc1;
         }
     }
 }
@@ -205,14 +206,22 @@ int ias_free_dia_dev(IasDiaDev *m)
 
 int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, double *elapsed_ms)
 {
+    if (!A) return fail(IAS_E_ARG, "NULL");
+    return ias_dia_mul_dia_rows_dev(A, B, 0, A->row, C, elapsed_ms);
+}
+
+int ias_dia_mul_dia_rows_dev(const IasDiaDev *A, const IasDiaDev *B, int r0, int r1, IasDiaDev *C, double *elapsed_ms)
+{
     IAS_TRY(ensure_init());
     if (!A || !B || !C) return fail(IAS_E_ARG, "NULL");
+    if (r0 < 0 || r1 > A->row || r0 > r1) return fail(IAS_E_ARG, "row range [%d,%d) outside A (%d rows)", r0, r1, A->row);
     if (!A->choice || !B->choice) return fail(IAS_E_GATE, "DIA operand was rejected by the size gate (choice == false)");
     if (A->col > B->row) return fail(IAS_E_ARG, "shape mismatch: A is %dx%d, B is %dx%d", A->row, A->col, B->row, B->col);
     Ctx &c = ctx();
     cudaStream_t s = c.stream;
     memset(C, 0, sizeof *C);
-    C->row = A->row; C->col = B->col; C->choice = true;
+    const int nrows = r1 - r0;
+    C->row = nrows; C->col = B->col; C->choice = true;
     IAS_CUDA(cudaEventRecord(c.ev[0], s));
 
     // offsets are tiny: fetch them and enumerate the reachable output diagonals on the host.
@@ -243,6 +252,7 @@ int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, do
     int c_nd = (int)c_off.size();
     C->num_diagonals = c_nd;
 
+    // (diagonal_ind keeps the index space of the whole product, rows(A) + cols(B) - 1 entries, for every row block)
     int span = A->row + B->col - 1;
     DBuf<int> di, off, d_pstart;
     DBuf<DiaPair> d_pairs;
@@ -251,7 +261,7 @@ int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, do
     IAS_TRY(off.alloc((size_t)std::max(c_nd, 1)));
     IAS_TRY(d_pstart.alloc(pstart.size()));
     IAS_TRY(d_pairs.alloc(std::max<size_t>(pab.size(), 1)));
-    IAS_TRY(val.alloc((size_t)A->row * c_nd));
+    IAS_TRY(val.alloc((size_t)nrows * c_nd));
     IAS_CUDA(cudaMemsetAsync(di.p, 0, sizeof(int) * (size_t)std::max(span, 1), s));
     if (c_nd) {
         IAS_CUDA(cudaMemcpyAsync(off.p, c_off.data(), sizeof(int) * c_nd, cudaMemcpyHostToDevice, s));
@@ -261,14 +271,14 @@ int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, do
     if (!pab.empty()) IAS_CUDA(cudaMemcpyAsync(d_pairs.p, pab.data(), sizeof(DiaPair) * pab.size(), cudaMemcpyHostToDevice, s));
 
     size_t sm = sizeof(DiaPair) * pab.size() + sizeof(int) * ((size_t)c_nd + 1);
-    if (A->row && c_nd) {
+    if (nrows && c_nd) {
         constexpr int BLOCK = 256;
-        unsigned grid = (unsigned)std::min<long long>(grid_for(A->row, 2 * BLOCK), (long long)c.sm_count * 8 * 64);
+        unsigned grid = (unsigned)std::min<long long>(grid_for(nrows, 2 * BLOCK), (long long)c.sm_count * 8 * 64);
         if (sm <= 32 * 1024) {
-            IAS_LAUNCH((k_dia_mul_dia<BLOCK, true>), grid, BLOCK, sm, A->row, c_nd, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p,
+            IAS_LAUNCH((k_dia_mul_dia<BLOCK, true>), grid, BLOCK, sm, r0, r1, c_nd, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p,
                        (int)pab.size(), val.p);
         } else {                               // many diagonals: the tables stay in global memory (L1/L2 resident)
-            IAS_LAUNCH((k_dia_mul_dia<BLOCK, false>), grid, BLOCK, 0, A->row, c_nd, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p,
+            IAS_LAUNCH((k_dia_mul_dia<BLOCK, false>), grid, BLOCK, 0, r0, r1, c_nd, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p,
                        (int)pab.size(), val.p);
         }
     }

@@ -3,8 +3,9 @@
 // ELL replaces CSRtoELL (CPU/detail/ell/common_ell.h:30-77), ELL_MUL_ELL (ell:80-189) and the
 // never-called ELL_MUL_ELL_DEV chain (GPU/detail/ell_dev/common_ell_dev.h:170-382: expand every
 // product into a width-`max_upper` array, O(w^2) in-row dedup, serial <<<1,1>>> scans).  The
-// multiply is the same Gustavson pipeline as CSR run on fixed-width rows (EllView: no row-pointer
-// gathers, row j of B starts at j*w), writing a row-major ELL result of width max nnz(C_i) with
+// multiply is a one-pass kernel of its own when a row's products fit a warp's register sort (k_ell_mul_ell below)
+// and otherwise the same Gustavson pipeline as CSR run on fixed-width rows (EllView: no row-pointer
+// gathers, row j of B starts at j*w); either way the result is a row-major ELL of width max nnz(C_i) with
 // column-sorted rows and 0 / 0.0 padding (the reference pads with 0, ell:54-56).
 //
 // COO replaces CSRtoCOO (CPU/detail/coo/common_coo.h:29-66), COO_MUL_COO (coo:72-161) and
@@ -66,6 +67,203 @@ __global__ void __launch_bounds__(256) k_expand_rows(int nrows, const long long 
         while (rp[row + 1] <= e) ++row;
         row_ind[e] = row;
     }
+}
+
+// ---------------------------------------------------------------- ELL x ELL in one pass (fixed-width operands)
+// Replaces ELL_MUL_ELL_DEV (GPU/detail/ell_dev/common_ell_dev.h:310-382: upper bound, expand every product into a
+// width-`max_upper` array, O(w^2) in-row dedup, serial scans, compaction).  What the fixed width buys:
+//   * no row pointers anywhere: product (a, b) of row i is B[A.ci[i][a]][b], found by index arithmetic -- no scan, no
+//     search, and every lane reads IPL consecutive entries of one B row (128-bit loads when the width allows);
+//   * the output row starts at i * width: no prefix sum over rows, hence no separate symbolic pass -- one kernel
+//     expands, sorts, compresses and writes, padding included (no memset of the result);
+//   * the products arrive as P2(wa) sorted runs of P2(wb) slots (B rows are column sorted when B is canonical), so the
+//     register sorting network starts at the first level that merges two runs: 26 compare-exchange stages instead of
+//     36 for 16 x 16.
+// A warp owns a row; element e = lane * IPL + r of its 32 * IPL slots is product (a, b) = (e / R, e % R), R = slots per
+// run.  Key = column << IDX_BITS | e (ties keep the arrival order, the order CSR_MUL_CSR / ELL_MUL_ELL accumulate in);
+// values wait in shared memory.  The network is the all-ascending form of the bitonic sorter: a merge level first
+// compares e with its mirror image e ^ (kk - 1), then halves the distance.  After the sort: segmented sum over equal
+// columns, the last product of a column writes the entry (same epilogue as k_esc_warp).
+// C is written with the upper-bound width w_ub = min(wa * wb, cols); the host re-strides it when the largest row
+// turns out narrower (ell:117-128 defines the width as max nnz(C_i)).
+template <class KeyT, int IPL>
+__device__ __forceinline__ void warp_sort_runs(KeyT (&key)[IPL], int lane, int run /* slots per sorted run, power of two */)
+{
+    constexpr int N = 32 * IPL;
+#pragma unroll
+    for (int kk = 2; kk <= N; kk <<= 1) {
+        if (kk <= run) continue;                                   // warp-uniform: these levels are already in order
+        // mirror step: e <-> e ^ (kk - 1)
+        if (kk <= IPL) {
+#pragma unroll
+            for (int r = 0; r < IPL; ++r) {
+                const int p = r ^ (kk - 1);
+                if (r < p) { KeyT lo = key[r] < key[p] ? key[r] : key[p], hi = key[r] < key[p] ? key[p] : key[r]; key[r] = lo; key[p] = hi; }
+            }
+        } else {
+            const int lm = kk / IPL - 1;                           // lanes e and e' differ in these bits; registers are mirrored
+            const bool low = (lane & (kk / (2 * IPL))) == 0;
+            KeyT other[IPL];
+#pragma unroll
+            for (int r = 0; r < IPL; ++r) other[r] = __shfl_xor_sync(0xffffffffu, key[IPL - 1 - r], lm);
+#pragma unroll
+            for (int r = 0; r < IPL; ++r) key[r] = low ? (key[r] < other[r] ? key[r] : other[r]) : (key[r] < other[r] ? other[r] : key[r]);
+        }
+#pragma unroll
+        for (int jj = kk >> 2; jj > 0; jj >>= 1) {
+            if (jj >= IPL) {
+                const int lj = jj / IPL;
+                const bool low = (lane & lj) == 0;
+#pragma unroll
+                for (int r = 0; r < IPL; ++r) {
+                    const KeyT other = __shfl_xor_sync(0xffffffffu, key[r], lj);
+                    key[r] = low ? (key[r] < other ? key[r] : other) : (key[r] < other ? other : key[r]);
+                }
+            } else {
+#pragma unroll
+                for (int r = 0; r < IPL; ++r)
+                    if ((r & jj) == 0) { KeyT lo = key[r] < key[r | jj] ? key[r] : key[r | jj], hi = key[r] < key[r | jj] ? key[r | jj] : key[r]; key[r] = lo; key[r | jj] = hi; }
+            }
+        }
+    }
+}
+
+template <class KeyT, int IPL, bool FULL /* every row of A and B holds exactly `width` entries */, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_ell_mul_ell(int nrows, EllView A, EllView B, int log2_run, int sorted_runs, int vec_ok,
+                                                       int w_ub, int *__restrict__ c_nr, int *__restrict__ c_ci, double *__restrict__ c_v,
+                                                       unsigned long long *__restrict__ total_nnz, int *__restrict__ max_nnz)
+{
+    constexpr int N = 32 * IPL;
+    constexpr int IDX_BITS = IPL == 16 ? 9 : IPL == 8 ? 8 : IPL == 4 ? 7 : 6;
+    constexpr int WARPS = BLOCK / 32;
+    __shared__ double s_vals[WARPS][N];
+    __shared__ unsigned long long s_total;
+    __shared__ int s_max;
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) { s_total = 0; s_max = 0; }
+    __syncthreads();
+    const KeyT PAD = ~(KeyT)0;
+    const KeyT IDX_MASK = ((KeyT)1 << IDX_BITS) - 1;
+    double *svals = s_vals[w];
+    const int e0 = lane * IPL;                       // first slot of this lane
+    const int a = e0 >> log2_run;                    // its run = A entry (a run spans run / IPL >= 1 lanes)
+    const int b0 = e0 & ((1 << log2_run) - 1);       // first B position of this lane inside the run
+    long long my_total = 0;
+    int my_max = 0;
+    const int nwarps = gridDim.x * WARPS;
+    for (int i = blockIdx.x * WARPS + w; i < nrows; i += nwarps) {
+        const int na = FULL ? A.w : __ldg(A.nr + i);
+        int j = -1, lenb = 0;
+        double av = 0.0;
+        if (a < na) {
+            j = __ldg(A.ci + (long long)i * A.w + a);
+            av = __ldg(A.v + (long long)i * A.w + a);
+            lenb = FULL ? B.w : __ldg(B.nr + j);
+        }
+        KeyT key[IPL];
+        const long long qb = (long long)j * B.w + b0;
+        if (FULL && vec_ok && j >= 0 && b0 + IPL <= B.w) {
+            // IPL consecutive entries of B row j: 128-bit loads (IPL is a multiple of 4 here, the row start 16-byte aligned)
+#pragma unroll
+            for (int r = 0; r < IPL; r += 4) {
+                const int4 c4 = __ldg(reinterpret_cast<const int4 *>(B.ci + qb + r));
+                const double2 v01 = __ldg(reinterpret_cast<const double2 *>(B.v + qb + r));
+                const double2 v23 = __ldg(reinterpret_cast<const double2 *>(B.v + qb + r + 2));
+                const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
+                const double vv[4] = {v01.x, v01.y, v23.x, v23.y};
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    if (r + u < IPL) {
+                        key[r + u] = ((KeyT)(unsigned)cc[u] << IDX_BITS) | (KeyT)(e0 + r + u);
+                        svals[e0 + r + u] = av * vv[u];
+                    }
+                }
+            }
+        } else {
+#pragma unroll
+            for (int r = 0; r < IPL; ++r) {
+                const bool valid = j >= 0 && b0 + r < lenb;
+                key[r] = valid ? (((KeyT)(unsigned)__ldg(B.ci + qb + r) << IDX_BITS) | (KeyT)(e0 + r)) : PAD;
+                svals[e0 + r] = valid ? av * __ldg(B.v + qb + r) : 0.0;
+            }
+        }
+        __syncwarp();
+        warp_sort_runs<KeyT, IPL>(key, lane, sorted_runs ? (1 << log2_run) : 1);
+        // tails: last product of every column
+        KeyT next_first = __shfl_down_sync(0xffffffffu, key[0], 1);
+        if (lane == 31) next_first = PAD;
+        int tails = 0;
+        bool is_tail[IPL];
+#pragma unroll
+        for (int r = 0; r < IPL; ++r) {
+            const KeyT nxt = r + 1 < IPL ? key[r + 1] : next_first;
+            is_tail[r] = key[r] != PAD && (nxt == PAD || (nxt >> IDX_BITS) != (key[r] >> IDX_BITS));
+            tails += is_tail[r];
+        }
+        int tincl = tails;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, tincl, o); if (lane >= o) tincl += u; }
+        const int count = __shfl_sync(0xffffffffu, tincl, 31);
+        // segmented sums (heads = first product of a column)
+        const KeyT prev_last = __shfl_up_sync(0xffffffffu, key[IPL - 1], 1);
+        double v[IPL];
+        bool head[IPL];
+        bool any_head = false;
+        double tail_sum = 0.0;
+#pragma unroll
+        for (int r = 0; r < IPL; ++r) {
+            const bool valid = key[r] != PAD;
+            const KeyT prv = r > 0 ? key[r - 1] : prev_last;
+            head[r] = valid && ((r == 0 && lane == 0) || (prv >> IDX_BITS) != (key[r] >> IDX_BITS));
+            v[r] = valid ? svals[(unsigned)(key[r] & IDX_MASK)] : 0.0;
+            tail_sum = head[r] ? v[r] : tail_sum + v[r];
+            any_head |= head[r];
+        }
+        double carry = tail_sum;
+        bool flag = any_head;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const double uc = __shfl_up_sync(0xffffffffu, carry, o);
+            const bool uf = __shfl_up_sync(0xffffffffu, flag, o);
+            if (lane >= o && !flag) { carry += uc; flag = uf; }
+        }
+        double carry_in = __shfl_up_sync(0xffffffffu, carry, 1);
+        if (lane == 0) carry_in = 0.0;
+        const long long gs = (long long)i * w_ub;
+        int opos = tincl - tails;
+        double run_sum = carry_in;
+#pragma unroll
+        for (int r = 0; r < IPL; ++r) {
+            run_sum = head[r] ? v[r] : run_sum + v[r];
+            if (is_tail[r]) { c_ci[gs + opos] = (int)(key[r] >> IDX_BITS); c_v[gs + opos] = run_sum; ++opos; }
+        }
+        for (int p = count + lane; p < w_ub; p += 32) { c_ci[gs + p] = 0; c_v[gs + p] = 0.0; }      // padding = 0 / 0.0 (ell:54-56)
+        if (lane == 0) { c_nr[i] = count; my_total += count; my_max = max(my_max, count); }
+        __syncwarp();                                              // svals is rewritten by the next row
+    }
+    if (lane == 0) { if (my_total) atomicAdd(&s_total, (unsigned long long)my_total); atomicMax(&s_max, my_max); }
+    __syncthreads();
+    if (threadIdx.x == 0) { if (s_total) atomicAdd(total_nnz, s_total); if (s_max) atomicMax(max_nnz, s_max); }
+}
+
+// C was written with stride w_in; the reference's width is max nnz(C_i) = w_out <= w_in
+__global__ void __launch_bounds__(256) k_ell_restride(long long cells_out, int w_in, int w_out, const int *__restrict__ ci_in,
+                                                      const double *__restrict__ v_in, int *__restrict__ ci_out, double *__restrict__ v_out)
+{
+    long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= cells_out) return;
+    long long i = t / w_out;
+    int k = (int)(t - i * w_out);
+    ci_out[t] = ci_in[i * w_in + k];
+    v_out[t] = v_in[i * w_in + k];
+}
+
+__global__ void __launch_bounds__(256) k_min_count(int n, const int *__restrict__ counts, int *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int v = i < n ? counts[i] : 0x7fffffff;
+    v = __reduce_min_sync(0xffffffffu, v);
+    if ((threadIdx.x & 31) == 0 && v < *out) atomicMin(out, v);
 }
 
 int max_of_counts(const int *counts, int n, int *out)
@@ -136,6 +334,105 @@ int ias_free_ell_dev(IasEllDev *m)
     return IAS_OK;
 }
 
+static int p2_ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// one-pass ELL x ELL (k_ell_mul_ell) when the products of a row fit a warp's register sort: P2(wa) * P2(wb) <= 512
+// slots, at most 32 runs, and the upper-bound-width result fits comfortably in memory.  *done = 0: not applicable.
+static int ell_mul_onepass(const IasEllDev *A, const IasEllDev *B, IasEll64Dev *C, double *elapsed_ms, int *done)
+{
+    *done = 0;
+    Ctx &c = ctx();
+    if (c.tune.ell_onepass == 0) return IAS_OK;
+    const int wa = A->max_nnz_per_row, wb = B->max_nnz_per_row;
+    if (A->row <= 0 || wa <= 0 || wb <= 0) return IAS_OK;
+    int runs = p2_ceil(wa), run = p2_ceil(wb);
+    if (runs > 32 || (long long)runs * run > 512) return IAS_OK;
+    while (runs * run < 64) run <<= 1;                       // at least two slots per lane
+    const int n_slots = runs * run, ipl = n_slots / 32;
+    if (run < ipl) return IAS_OK;                            // a lane's slots must lie inside one run
+    int log2_run = 0;
+    while ((1 << log2_run) < run) ++log2_run;
+    const long long w_ub = std::min<long long>((long long)wa * wb, (long long)B->col);
+    size_t f = 0, t = 0;
+    IAS_CUDA(cudaMemGetInfo(&f, &t));
+    const double need = (double)A->row * (double)w_ub * 12.0;
+    if (need > 0.45 * (double)f) return IAS_OK;              // the two-pass pipeline sizes C exactly
+    int col_bits = 1;
+    while (col_bits < 31 && (1LL << col_bits) < (long long)B->col) ++col_bits;
+    const int idx_bits = ipl == 16 ? 9 : ipl == 8 ? 8 : ipl == 4 ? 7 : 6;
+    const bool k32 = col_bits + idx_bits <= 32;              // the all-ones key is the padding marker: keep it unreachable
+    if (k32 && col_bits + idx_bits == 32 && (long long)B->col == (1LL << col_bits)) return IAS_OK;
+
+    cudaStream_t s = c.stream;
+    IAS_CUDA(cudaEventRecord(c.ev[0], s));
+    EllView av{A->nnz_row_dev, A->col_ind_dev, A->values_dev, wa};
+    EllView bv{B->nnz_row_dev, B->col_ind_dev, B->values_dev, wb};
+    // scalars: [0] total nnz (u64), [1] max nnz, min row length of A, of B, B not canonical
+    DBuf<unsigned long long> d_sc;
+    IAS_TRY(d_sc.alloc(8));
+    IAS_CUDA(cudaMemsetAsync(d_sc.p, 0, 8 * sizeof(unsigned long long), s));
+    int *d_int = reinterpret_cast<int *>(d_sc.p + 1);        // [0] max, [1] min A, [2] min B
+    const int big = 0x7fffffff;
+    IAS_CUDA(cudaMemcpyAsync(d_int + 1, &big, sizeof(int), cudaMemcpyHostToDevice, s));
+    IAS_CUDA(cudaMemcpyAsync(d_int + 2, &big, sizeof(int), cudaMemcpyHostToDevice, s));
+    IAS_LAUNCH(k_min_count, grid_for(A->row, 256), 256, 0, A->row, A->nnz_row_dev, d_int + 1);
+    IAS_LAUNCH(k_min_count, grid_for(B->row, 256), 256, 0, B->row, B->nnz_row_dev, d_int + 2);
+    IAS_LAUNCH((k_rows_canonical<EllView>), grid_for(B->row, 256), 256, 0, B->row, bv, d_sc.p + 4);
+    unsigned long long h_sc[8];
+    IAS_CUDA(cudaMemcpyAsync(h_sc, d_sc.p, sizeof h_sc, cudaMemcpyDeviceToHost, s));
+    IAS_CUDA(cudaStreamSynchronize(s));
+    const int *h_int = reinterpret_cast<const int *>(h_sc + 1);
+    const bool full = h_int[1] == wa && h_int[2] == wb;
+    const int sorted_runs = h_sc[4] == 0 ? 1 : 0;
+    const int vec_ok = (wb % 4 == 0 && ipl % 4 == 0) ? 1 : 0;
+
+    const size_t cells = (size_t)A->row * (size_t)w_ub;
+    DBuf<int> nr, ci;
+    DBuf<double> cv;
+    IAS_TRY(nr.alloc((size_t)A->row));
+    IAS_TRY(ci.alloc(cells));
+    IAS_TRY(cv.alloc(cells));
+    constexpr int EB = 128;
+    const unsigned grid = (unsigned)std::min<long long>(grid_for(A->row, EB / 32), (long long)c.sm_count * 16);
+#define IAS_ELL1(KT, IPL, FULLROWS)                                                                                          \
+    IAS_LAUNCH((k_ell_mul_ell<KT, IPL, FULLROWS, EB>), grid, EB, 0, A->row, av, bv, log2_run, sorted_runs, vec_ok, (int)w_ub, \
+               nr.p, ci.p, cv.p, d_sc.p, d_int)
+#define IAS_ELL2(KT, FULLROWS)                                                                     \
+    do {                                                                                           \
+        if (ipl == 2) IAS_ELL1(KT, 2, FULLROWS); else if (ipl == 4) IAS_ELL1(KT, 4, FULLROWS);     \
+        else if (ipl == 8) IAS_ELL1(KT, 8, FULLROWS); else IAS_ELL1(KT, 16, FULLROWS);             \
+    } while (0)
+    if (k32) { if (full) IAS_ELL2(unsigned, true); else IAS_ELL2(unsigned, false); }
+    else     { if (full) IAS_ELL2(unsigned long long, true); else IAS_ELL2(unsigned long long, false); }
+#undef IAS_ELL2
+#undef IAS_ELL1
+    IAS_CUDA(cudaMemcpyAsync(h_sc, d_sc.p, sizeof h_sc, cudaMemcpyDeviceToHost, s));
+    IAS_CUDA(cudaStreamSynchronize(s));
+    const long long nnz = (long long)h_sc[0];
+    const int w = h_int[0];
+    memset(C, 0, sizeof *C);
+    C->choice = true; C->row = A->row; C->col = B->col; C->nnz = nnz; C->max_nnz_per_row = w;
+    if (w < w_ub) {                                          // the reference's width is max nnz(C_i): re-stride
+        const size_t out_cells = (size_t)A->row * (size_t)w;
+        DBuf<int> ci2;
+        DBuf<double> cv2;
+        IAS_TRY(ci2.alloc(out_cells));
+        IAS_TRY(cv2.alloc(out_cells));
+        if (out_cells) IAS_LAUNCH(k_ell_restride, grid_for((long long)out_cells, 256), 256, 0, (long long)out_cells, (int)w_ub, w, ci.p, cv.p, ci2.p, cv2.p);
+        IAS_CUDA(cudaEventRecord(c.ev[4], s));
+        IAS_CUDA(cudaStreamSynchronize(s));
+        C->col_ind_dev = ci2.release(); C->values_dev = cv2.release();
+    } else {
+        IAS_CUDA(cudaEventRecord(c.ev[4], s));
+        IAS_CUDA(cudaStreamSynchronize(s));
+        C->col_ind_dev = ci.release(); C->values_dev = cv.release();
+    }
+    C->nnz_row_dev = nr.release();
+    if (elapsed_ms) *elapsed_ms = ev_ms(0, 4);
+    *done = 1;
+    return IAS_OK;
+}
+
 static int ell_mul(const IasEllDev *A, const IasEllDev *B, IasEll64Dev *C, double *elapsed_ms)
 {
     IAS_TRY(ensure_init());
@@ -143,6 +440,10 @@ static int ell_mul(const IasEllDev *A, const IasEllDev *B, IasEll64Dev *C, doubl
     if (!A->choice || !B->choice) return fail(IAS_E_GATE, "ELL operand was rejected by the size gate (choice == false)");
     if (A->col > B->row) return fail(IAS_E_ARG, "shape mismatch: A is %dx%d, B is %dx%d", A->row, A->col, B->row, B->col);
     Ctx &c = ctx();
+    int done = 0;
+    IAS_TRY(ell_mul_onepass(A, B, C, elapsed_ms, &done));
+    if (done) return IAS_OK;
+    // general case: the Gustavson pipeline on fixed-width rows (EllView: no row-pointer gathers, row j of B starts at j*w)
     memset(C, 0, sizeof *C);
     C->row = A->row; C->col = B->col; C->choice = true;
     EllView av{A->nnz_row_dev, A->col_ind_dev, A->values_dev, A->max_nnz_per_row};
@@ -221,6 +522,15 @@ int ias_download_ell(const IasEllDev *d, int *nnz_row, int *col_ind, double *val
     if (values && cells) IAS_CUDA(cudaMemcpyAsync(values, d->values_dev, sizeof(double) * cells, cudaMemcpyDeviceToHost, s));
     IAS_CUDA(cudaStreamSynchronize(s));
     return IAS_OK;
+}
+
+int ias_download_ell64(const IasEll64Dev *d, int *nnz_row, int *col_ind, double *values)
+{
+    if (!d) return fail(IAS_E_ARG, "NULL");
+    IasEllDev v;
+    v.choice = d->choice; v.row = d->row; v.col = d->col; v.nnz = (int)std::min<long long>(d->nnz, 0x7fffffffLL);
+    v.max_nnz_per_row = d->max_nnz_per_row; v.nnz_row_dev = d->nnz_row_dev; v.col_ind_dev = d->col_ind_dev; v.values_dev = d->values_dev;
+    return ias_download_ell(&v, nnz_row, col_ind, values);
 }
 
 // ---------------------------------------------------------------- COO

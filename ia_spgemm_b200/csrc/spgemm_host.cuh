@@ -49,6 +49,31 @@ inline int build_bin_lists(int nrows, const unsigned char *bin_dev, const long l
     return IAS_OK;
 }
 
+// Rows of a bin ordered by decreasing work (longest processing time first): the persistent kernels hand rows out through
+// an atomic cursor, so the tail of a launch is bounded by the smallest rows instead of whatever hub row came last.
+struct WorkOrder {
+    DBuf<unsigned> keys, keys_sorted;
+    DBuf<int> vals, list;
+    DBuf<char> tmp;
+};
+inline int order_by_work(const int *list_in, int n, const int *ub, WorkOrder &wo, const int **out)
+{
+    *out = list_in;
+    if (n < 2 || ctx().tune.g_lpt == 0) return IAS_OK;
+    IAS_TRY(wo.keys.alloc(n));
+    IAS_TRY(wo.keys_sorted.alloc(n));
+    IAS_TRY(wo.vals.alloc(n));
+    IAS_TRY(wo.list.alloc(n));
+    IAS_LAUNCH(k_work_keys, grid_for(n, 256), 256, 0, n, list_in, ub, wo.keys.p, wo.vals.p);
+    size_t tb = 0;
+    IAS_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, wo.keys.p, wo.keys_sorted.p, wo.vals.p, wo.list.p, n, 0, 32, ctx().stream));
+    IAS_TRY(wo.tmp.alloc(tb));
+    IAS_CUDA(cub::DeviceRadixSort::SortPairsDescending(wo.tmp.p, tb, wo.keys.p, wo.keys_sorted.p, wo.vals.p, wo.list.p, n, 0, 32, ctx().stream));
+    ctx().launches += 2;
+    *out = wo.list.p;
+    return IAS_OK;
+}
+
 template <class K>
 inline int opt_in_smem(K kernel, size_t bytes)
 {
@@ -326,7 +351,10 @@ int symbolic_range(const AV &A, const BV &B, int r0, int r1, int ncols_b, double
         IAS_TRY(gwin_grid(k, sm, n, &grid));
         if (!rw.cursor.p) IAS_TRY(rw.cursor.alloc(1));
         IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
-        IAS_LAUNCH(k, grid, GW_BLOCK, sm, bl.rows_of(BIN_G), n, r0, A, B, rw.nnz_row.p, rw.cursor.p, ncols_b, swords);
+        WorkOrder wo;
+        const int *glist = nullptr;
+        IAS_TRY(order_by_work(bl.rows_of(BIN_G), n, rw.ub.p, wo, &glist));
+        IAS_LAUNCH(k, grid, GW_BLOCK, sm, glist, n, r0, A, B, rw.nnz_row.p, rw.cursor.p, ncols_b, swords);
         IAS_BIN_END(BIN_G);
         GWIN_PROFILE_DUMP("sym");
         rw.sym_timed[BIN_G] = true;
@@ -385,12 +413,12 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         IAS_BIN_BEGIN(8 + BIN_T);
         int m = (int)bl.count[BIN_T];
         int cap = std::max(1, (int)h[NBINS]);
-        size_t sm = (size_t)TINY_BLOCK * cap * (sizeof(double) + sizeof(int));
+        size_t sm = (size_t)TINY_BLOCK * cap * (sizeof(double) + sizeof(int)) + 48;       // + the alignment shift of the bulk copy-out
         int merge = rw.max_tiny_na <= 4 ? 4 : rw.max_tiny_na <= 5 ? 5 : rw.max_tiny_na <= 6 ? 6 : 8;
         auto k = merge == 4 ? k_num_tiny<AV, BV, TINY_BLOCK, 4> : merge == 5 ? k_num_tiny<AV, BV, TINY_BLOCK, 5>
                : merge == 6 ? k_num_tiny<AV, BV, TINY_BLOCK, 6> : k_num_tiny<AV, BV, TINY_BLOCK, 8>;
         IAS_TRY(opt_in_smem(k, sm));
-        IAS_LAUNCH(k, grid_for(m, TINY_BLOCK), TINY_BLOCK, sm, bl.rows_of(BIN_T), m, r0, A, B, out, c_ci, c_v, cap, rw.b_canonical);
+        IAS_LAUNCH(k, grid_for(m, TINY_BLOCK), TINY_BLOCK, sm, bl.rows_of(BIN_T), m, r0, A, B, out, c_ci, c_v, cap, rw.b_canonical, (int)(c.tune.bulk_store != 0));
         IAS_BIN_END(8 + BIN_T);
         rw.num_timed[BIN_T] = true;
     }
@@ -462,7 +490,10 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         IAS_TRY(gwin_grid(k, sm, m, &grid));
         if (!rw.cursor.p) IAS_TRY(rw.cursor.alloc(1));
         IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
-        IAS_LAUNCH(k, grid, GW_BLOCK, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.cursor.p, ncols_b, swords, win, tbl_cap);
+        WorkOrder wo;
+        const int *glist = nullptr;
+        IAS_TRY(order_by_work(bl.rows_of(BIN_G), m, rw.ub.p + b0, wo, &glist));
+        IAS_LAUNCH(k, grid, GW_BLOCK, sm, glist, m, r0, A, B, out, c_ci, c_v, rw.cursor.p, ncols_b, swords, win, tbl_cap);
         IAS_BIN_END(8 + BIN_G);
         GWIN_PROFILE_DUMP("num");
         rw.num_timed[BIN_G] = true;
@@ -470,9 +501,24 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         IAS_BIN_BEGIN(8 + BIN_G);
         int m = (int)bl.count[BIN_G];
         const bool two = c.tune.g_block == 512;
+        const bool v2 = rw.b_canonical && c.tune.global_rows_smem != 0 && c.tune.g_v2 != 0 && !two;
         IAS_TRY(ensure_gwork(rw, ncols_b, m, two ? 2 : 1));
         IAS_CUDA(cudaMemsetAsync(rw.cursor.p, 0, sizeof(int), c.stream));
-        {
+        WorkOrder wo;
+        const int *glist = nullptr;
+        IAS_TRY(order_by_work(bl.rows_of(BIN_G), m, rw.ub.p + b0, wo, &glist));
+        if (v2) {
+            // second generation (canonical B): rank + emit from the shared-memory bitmap, split tables for the windows.
+            // 128 KB tile + 32 KB of split points = the 160 KB the first generation gives to its tile alone, so the
+            // L1 that is left for the B-row stream is the same.
+            auto k = k_num_global2<AV, BV, 1024>;
+            int win = (int)std::min<long long>(16384, std::max<long long>(16, c.tune.g_win & ~15LL));
+            int tbl_cap = (int)std::min<long long>(16384, std::max<long long>(0, c.tune.g_tbl));
+            size_t sm = (size_t)win * sizeof(double) + (size_t)tbl_cap * sizeof(int);
+            IAS_TRY(opt_in_smem(k, sm));
+            IAS_LAUNCH(k, std::min<long long>(rw.gslots, (long long)c.sm_count), 1024, sm, glist, m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
+                       GLayout::make(ncols_b), rw.cursor.p, win, tbl_cap, ncols_b);
+        } else {
             // 160 KB tile of fp64 partial sums per SM (192 KB would leave 28 KB of L1 for the B-row stream: ncu/clock64
             // showed the mark pass 1.6x slower); with two 512-thread CTAs per SM each gets half
             int win = (int)std::min<long long>(two ? 10240 : 20480, std::max<long long>(16, c.tune.g_win & ~15LL));
@@ -483,12 +529,12 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
             if (two) {
                 auto k = k_num_global<AV, BV, 512>;
                 IAS_TRY(opt_in_smem(k, sm));
-                IAS_LAUNCH(k, std::min<long long>(rw.gslots, 2LL * c.sm_count), 512, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
+                IAS_LAUNCH(k, std::min<long long>(rw.gslots, 2LL * c.sm_count), 512, sm, glist, m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
                            GLayout::make(ncols_b), rw.cursor.p, win, rw.b_canonical, smem_mark, ncols_b);
             } else {
                 auto k = k_num_global<AV, BV, 1024>;
                 IAS_TRY(opt_in_smem(k, sm));
-                IAS_LAUNCH(k, std::min<long long>(rw.gslots, (long long)c.sm_count), 1024, sm, bl.rows_of(BIN_G), m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
+                IAS_LAUNCH(k, std::min<long long>(rw.gslots, (long long)c.sm_count), 1024, sm, glist, m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
                            GLayout::make(ncols_b), rw.cursor.p, win, rw.b_canonical, smem_mark, ncols_b);
             }
         }

@@ -319,6 +319,17 @@ static __global__ void __launch_bounds__(256) k_classify_num(int nrows, const in
     if (threadIdx.x >= NBINS && threadIdx.x < NBINS + 2) atomicMax(&g_hist[threadIdx.x], (unsigned long long)s_max[threadIdx.x - NBINS]);
 }
 
+// (key, value) = (work of the row, row) for ordering a bin's rows by decreasing work
+static __global__ void __launch_bounds__(256) k_work_keys(int n, const int *__restrict__ list, const int *__restrict__ ub,
+                                                   unsigned *__restrict__ keys, int *__restrict__ vals)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int li = list ? list[t] : t;
+    keys[t] = (unsigned)ub[li];
+    vals[t] = li;
+}
+
 static __global__ void k_iota(int n, int *out)
 {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -410,11 +421,11 @@ __global__ void __launch_bounds__(BLOCK) k_sym_tiny(const int *__restrict__ rows
 
 template <class AV, class BV, int BLOCK, int MERGE>
 __global__ void __launch_bounds__(BLOCK) k_num_tiny(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
-                                                    int *__restrict__ c_ci, double *__restrict__ c_v, int cap, int b_canonical)
+                                                    int *__restrict__ c_ci, double *__restrict__ c_v, int cap, int b_canonical, int bulk)
 {
-    extern __shared__ unsigned char smem_raw[];
-    double *vals = reinterpret_cast<double *>(smem_raw);      // every thread owns exactly nnz(C_i) slots
-    int *cols = reinterpret_cast<int *>(vals + (size_t)BLOCK * cap);
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *vals = reinterpret_cast<double *>(smem_raw);      // every thread owns exactly nnz(C_i) slots (+ 2: alignment shift)
+    int *cols = reinterpret_cast<int *>(vals + (size_t)BLOCK * cap + 2);
     typedef cub::BlockScan<int, BLOCK> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
 
@@ -426,12 +437,21 @@ __global__ void __launch_bounds__(BLOCK) k_num_tiny(const int *__restrict__ rows
         n = out.count(li);
         gstart = out.start(li);
     }
+    // identity row list: the CTA's rows are consecutive, so its output is one contiguous span starting at `base`.
+    // For the bulk copy-out the staged span is shifted so that a 16-byte boundary in shared memory is one in global memory.
+    const bool ident = rows == nullptr && out.rp != nullptr;
+    long long base = 0;
+    int sv = 0, sc = 0;
+    if (ident) {
+        base = out.start(blockIdx.x * BLOCK);
+        if (bulk) { sv = (int)(base & 1); sc = (int)(base & 3); }
+    }
     int off, total;
     Scan(scan_tmp).ExclusiveSum(n, off, total);
     if (n > 0) {
         int i = r0 + li;
-        int *mc = cols + off;
-        double *mv = vals + off;
+        int *mc = cols + sc + off;
+        double *mv = vals + sv + off;
         typename AV::off_t pa = A.begin(i), pe = A.end(i);
         int na = (int)(pe - pa);
         if (b_canonical && na <= MERGE) {
@@ -462,10 +482,25 @@ __global__ void __launch_bounds__(BLOCK) k_num_tiny(const int *__restrict__ rows
         }
     }
     __syncthreads();
-    if (rows == nullptr && out.rp != nullptr) {
-        // identity row list: the CTA's rows are consecutive, so its output is one contiguous span
-        long long base = out.start(blockIdx.x * BLOCK);
-        for (int e = threadIdx.x; e < total; e += BLOCK) { c_ci[base + e] = cols[e]; c_v[base + e] = vals[e]; }
+    if (ident && bulk && total >= 64) {
+        // one elected thread hands the 16-byte aligned middle of both arrays to the copy engine (cp.async.bulk, shared ->
+        // global); the few head / tail elements go out with ordinary stores
+        const int hv = sv, nv = (total - hv) & ~1;                 // values: 8-byte elements
+        const int hc = (4 - sc) & 3, nc = (total - hc) & ~3;       // columns: 4-byte elements
+        if (threadIdx.x == 0) {
+            fence_proxy_async_shared();
+            bulk_store_shared_to_global(c_v + base + hv, vals + sv + hv, (unsigned)nv * 8u);
+            bulk_store_shared_to_global(c_ci + base + hc, cols + sc + hc, (unsigned)nc * 4u);
+            bulk_commit_group();
+        }
+        const int e = threadIdx.x;                                 // at most 1 + 1 values and 3 + 3 columns are left over
+        if (e < hv) c_v[base + e] = vals[sv + e];
+        if (e >= 8 && e < 8 + (total - hv - nv)) c_v[base + hv + nv + (e - 8)] = vals[sv + hv + nv + (e - 8)];
+        if (e >= 16 && e < 16 + hc) c_ci[base + (e - 16)] = cols[sc + (e - 16)];
+        if (e >= 24 && e < 24 + (total - hc - nc)) c_ci[base + hc + nc + (e - 24)] = cols[sc + hc + nc + (e - 24)];
+        if (threadIdx.x == 0) bulk_wait_group_read0();             // shared memory must outlive the copy's reads
+    } else if (ident) {
+        for (int e = threadIdx.x; e < total; e += BLOCK) { c_ci[base + e] = cols[sc + e]; c_v[base + e] = vals[sv + e]; }
     } else {
         int lane = threadIdx.x & 31;
         for (int r = 0; r < 32; ++r) {
@@ -1383,6 +1418,276 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
         }
         // 4. leave the slot clean for the next row
         g_clear<BLOCK>(wp, summary, wsum, L);
+        __syncthreads();
+        GP_ADD(41);
+    }
+}
+
+// ---------------------------------------------------------------- global rows, second generation (canonical B)
+// Phase clocks of k_num_global at R-MAT scale 22 (profiles/r02_summary.md): the products themselves (mark + accumulate
+// runs) were a third of the kernel; the rest went to a separate rank + emit pass over the row's cells in L2 (23 %), to
+// the two lower bounds per A entry and window (acc build 13 %, mark build 5 %) and to batch tails.  This version
+//   * ranks and emits straight from the shared-memory bitmap of the mark pass: a warp takes 32 words, scans their
+//     populations with shuffles, writes the {bitmap, rank} cells (only needed by the accumulate look-ups now) and the
+//     sorted column list -- no pass over L2 at all, no __threadfence;
+//   * finds every window boundary of every B row once per row, all in parallel (split tables in shared memory:
+//     tbl[e][k] = first entry of B row e with column >= boundary k), so that a window's product list is built from
+//     two shared-memory reads per A entry instead of two dependent binary searches in L2;
+//   * keeps the A row's entries (B row start, length, A value) in registers for rows of at most BLOCK entries.
+// Rows with more than BLOCK entries in A, or whose tables do not fit, take the per-window searches of the first
+// generation.  Dynamic shared memory: win doubles (accumulate tile, also the mark bitmap) + tbl_cap ints.
+constexpr int G2_MAX_BND = 512;          // window boundaries kept in shared memory (rows beyond read them from c_ci)
+
+template <class AV, class BV, int BLOCK>
+__global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
+                                                       int *__restrict__ c_ci, double *__restrict__ c_v,
+                                                       unsigned *__restrict__ work, GLayout L, int *__restrict__ cursor,
+                                                       int win, int tbl_cap, int ncols)
+{
+    typedef typename AV::off_t aoff;
+    typedef typename BV::off_t boff;
+    constexpr int NWARPS = BLOCK / 32;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    double *acc = reinterpret_cast<double *>(smem_raw);                       // win entries
+    unsigned *bits = reinterpret_cast<unsigned *>(smem_raw);                  // mark bitmap: 2 * win words in the same bytes
+    int *tbl = reinterpret_cast<int *>(smem_raw + (size_t)win * 8);           // tbl_cap split points
+    typedef cub::BlockScan<unsigned, BLOCK> Scan;
+    __shared__ typename Scan::TempStorage scan_tmp;
+    __shared__ int s_row;
+    __shared__ unsigned s_carry, s_swtot;
+    __shared__ unsigned s_blk[2 * BLOCK];                                     // per-block (32 words) populations of a super-window
+    __shared__ int s_bnd[G2_MAX_BND + 1];
+    __shared__ CtaTile<BV, BLOCK> tile;
+    uint2 *wp = reinterpret_cast<uint2 *>(work + (size_t)blockIdx.x * L.slot_words);
+    unsigned *summary = reinterpret_cast<unsigned *>(wp + L.words);
+    unsigned *wsum = summary + L.sumw + L.blocks;
+    const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
+    const int swords = min(win * 2, 2 * BLOCK * 32);                           // s_blk holds 2 * BLOCK blocks
+    const long long span = (long long)swords * 32;
+    const int nsw = (int)((ncols + span - 1) / span);
+    for (int w = tid; w < swords; w += BLOCK) bits[w] = 0;
+    while (true) {
+        if (tid == 0) { s_row = atomicAdd(cursor, 1); s_carry = 0; }
+        __syncthreads();
+        const int idx = s_row;
+        if (idx >= nrows) break;
+        const int li = rows ? rows[idx] : idx;
+        const int i = r0 + li;
+        const long long gs = out.start(li);
+        const int n = out.count(li);
+        const aoff pa = A.begin(i), pe = A.end(i);
+        const int n_a = (int)min((aoff)0x7fffffff, pe - pa);
+        const bool single_tile = pe - pa <= (aoff)BLOCK;
+        GP_START();
+        GP_CNT(32, 1);
+        boff my_qb = 0;
+        int my_len = 0;
+        double my_av = 0.0;
+        if (single_tile) gwin_load<true>(A, B, pa, pe, my_qb, my_len, my_av);
+        // split table of the mark pass: where every B row crosses the super-window boundaries
+        const int mstride = (nsw + 1) | 1;
+        const bool use_mtbl = single_tile && nsw > 1 && (long long)n_a * mstride <= tbl_cap;
+        if (use_mtbl) {
+            tile.rel[tid] = my_qb;
+            tile.incl[tid] = my_len;
+            __syncthreads();
+            const int items = n_a * (nsw - 1);
+            for (int it = tid; it < items; it += BLOCK) {
+                const int e = it / (nsw - 1), k = it - e * (nsw - 1) + 1;
+                const boff b = tile.rel[e];
+                const int c = (int)(k * span);
+                int lo = 0, hi = tile.incl[e];
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(B.ci + b + mid) < c) lo = mid + 1; else hi = mid; }
+                tbl[e * mstride + k] = lo;
+            }
+            if (tid < n_a) { tbl[tid * mstride] = 0; tbl[tid * mstride + nsw] = my_len; }
+            __syncthreads();
+        }
+        GP_ADD(33);
+        // 1. mark, rank and emit, one super-window of the column space at a time
+        auto mark = [&](const boff (&q)[PB], const double (&)[PB], unsigned valid, int c_lo) {
+            int k[PB];
+            unsigned cur[PB];
+#pragma unroll
+            for (int u = 0; u < PB; ++u) k[u] = (valid >> u) & 1u ? __ldg(B.ci + q[u]) - c_lo : -1;
+#pragma unroll
+            for (int u = 0; u < PB; ++u) cur[u] = k[u] >= 0 ? bits[k[u] >> 5] : 0xffffffffu;
+#pragma unroll
+            for (int u = 0; u < PB; ++u) {
+                const unsigned bit = 1u << (k[u] & 31);
+                if (!(cur[u] & bit)) atomicOr(&bits[k[u] >> 5], bit);
+            }
+        };
+        for (int k = 0; k < nsw; ++k) {
+            const long long sw_lo = k * span;
+            const int c_lo = (int)sw_lo;
+            const int c_hi = k + 1 == nsw ? 0x7fffffff : (int)(sw_lo + span);
+            bool any = false;
+            if (single_tile) {
+                boff qb = my_qb;
+                int len = my_len;
+                if (use_mtbl) {
+                    const int o0 = tid < n_a ? tbl[tid * mstride + k] : 0, o1 = tid < n_a ? tbl[tid * mstride + k + 1] : 0;
+                    qb = my_qb + o0; len = o1 - o0;
+                } else if (nsw > 1) gwin_restrict<BLOCK>(B, n_a, qb, len, tile, c_lo, c_hi);
+                const int total = gwin_scan<false, BLOCK>(tile, qb, len, 0.0);
+                if (total) {
+                    any = true;
+                    gwin_run<false, BLOCK>(tile, total, [&](const boff (&q)[PB], const double (&pv)[PB], unsigned valid) { mark(q, pv, valid, c_lo); });
+                }
+                __syncthreads();
+            } else {
+                for (aoff base = pa; base < pe; base += BLOCK) {
+                    const int total = gwin_build<false, BLOCK>(A, B, base, pe, tile, c_lo, c_hi);
+                    if (total) {
+                        any = true;
+                        gwin_run<false, BLOCK>(tile, total, [&](const boff (&q)[PB], const double (&pv)[PB], unsigned valid) { mark(q, pv, valid, c_lo); });
+                    }
+                    __syncthreads();
+                }
+            }
+            GP_ADD(34);
+            if (!any) continue;
+            const int w0g = c_lo >> 5;                                // first global word of the super-window
+            const int nwords = min(swords, L.words - w0g);            // a multiple of 32 (L.words and swords are)
+            const int nblk = nwords >> 5;
+            // populations of the blocks of 32 words
+            for (int b = wid; b < nblk; b += NWARPS) {
+                const int c = warp_sum((int)__popc(bits[b * 32 + lane]));
+                if (lane == 0) s_blk[b] = (unsigned)c;
+            }
+            __syncthreads();
+            {
+                const int b0i = tid * 2;
+                const unsigned v0 = b0i < nblk ? s_blk[b0i] : 0u, v1 = b0i + 1 < nblk ? s_blk[b0i + 1] : 0u;
+                unsigned excl, tot;
+                Scan(scan_tmp).ExclusiveSum(v0 + v1, excl, tot);
+                if (b0i < nblk) s_blk[b0i] = excl;
+                if (b0i + 1 < nblk) s_blk[b0i + 1] = excl + v0;
+                if (tid == 0) s_swtot = tot;
+            }
+            __syncthreads();
+            // cells + sorted columns of the super-window, a warp per block of 32 words; the bitmap is left clean
+            const unsigned base_rank = s_carry;
+            for (int b = wid; b < nblk; b += NWARPS) {
+                const int w = b * 32 + lane;
+                unsigned word = bits[w];
+                const unsigned m = __ballot_sync(0xffffffffu, word != 0u);
+                if (!m) continue;
+                const int c = __popc(word);
+                int incl = c;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+                if (word) {
+                    unsigned rank = base_rank + s_blk[b] + (unsigned)(incl - c);
+                    wp[w0g + w] = make_uint2(word, rank);
+                    bits[w] = 0;
+                    const int col0 = c_lo + w * 32;
+                    while (word) {
+                        const int bit = __ffs(word) - 1;
+                        word &= word - 1;
+                        c_ci[gs + rank] = col0 + bit;
+                        ++rank;
+                    }
+                }
+                if (lane == 0) wsum[(w0g >> 5) + b] = m;
+            }
+            __syncthreads();
+            if (tid == 0) s_carry = base_rank + s_swtot;
+            GP_ADD(36);
+        }
+        // 2. window boundaries (first column of every window of `win` ranks) and the split table of the accumulate pass
+        const int W = (n + win - 1) / win;
+        const bool bnd_in_smem = W - 1 <= G2_MAX_BND;
+        if (W > 1 && bnd_in_smem) {
+            __threadfence_block();
+            __syncthreads();                                          // the emitted columns are read back by other threads
+            for (int w = tid + 1; w < W; w += BLOCK) s_bnd[w] = __ldcg(c_ci + gs + (long long)w * win);
+        }
+        const int astride = (W + 1) | 1;
+        const bool use_atbl = single_tile && W > 1 && bnd_in_smem && (long long)n_a * astride <= tbl_cap;
+        if (use_atbl) {
+            tile.rel[tid] = my_qb;
+            tile.incl[tid] = my_len;
+            __syncthreads();
+            const int items = n_a * (W - 1);
+            for (int it = tid; it < items; it += BLOCK) {
+                const int e = it / (W - 1), k = it - e * (W - 1) + 1;
+                const boff b = tile.rel[e];
+                const int c = s_bnd[k];
+                int lo = 0, hi = tile.incl[e];
+                while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(B.ci + b + mid) < c) lo = mid + 1; else hi = mid; }
+                tbl[e * astride + k] = lo;
+            }
+            if (tid < n_a) { tbl[tid * astride] = 0; tbl[tid * astride + W] = my_len; }
+        }
+        __syncthreads();
+        GP_ADD(38);
+        // 3. one window of `win` ranks at a time: accumulate in the shared-memory tile, then write it out
+        for (int w = 0; w < W; ++w) {
+            const int wbase = w * win;
+            const int wn = min(win, n - wbase);
+            int c_lo = 0, c_hi = 0x7fffffff;
+            if (W > 1) {
+                if (bnd_in_smem) { c_lo = w == 0 ? 0 : s_bnd[w]; c_hi = w + 1 < W ? s_bnd[w + 1] : 0x7fffffff; }
+                else { c_lo = w == 0 ? 0 : __ldcg(c_ci + gs + wbase); c_hi = w + 1 < W ? __ldcg(c_ci + gs + wbase + win) : 0x7fffffff; }
+            }
+            for (int t = tid; t < wn; t += BLOCK) acc[t] = 0.0;
+            __syncthreads();
+            GP_ADD(37);
+            GP_CNT(42, 1);
+            auto add = [&](const boff (&q)[PB], const double (&av)[PB], unsigned valid) {
+                int k[PB];
+                double x[PB];
+                uint2 cell[PB];
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    k[u] = -1; x[u] = 0.0;
+                    if ((valid >> u) & 1u) { k[u] = __ldg(B.ci + q[u]); x[u] = av[u] * __ldg(B.v + q[u]); }
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    if (k[u] < c_lo || k[u] >= c_hi) k[u] = -1;
+                    cell[u] = k[u] >= 0 ? __ldcg(wp + (k[u] >> 5)) : make_uint2(0, 0);
+                }
+#pragma unroll
+                for (int u = 0; u < PB; ++u) {
+                    if (k[u] < 0) continue;
+                    const unsigned below = cell[u].x & ((1u << (k[u] & 31)) - 1u);
+                    atomicAdd(&acc[(int)(cell[u].y + __popc(below)) - wbase], x[u]);
+                }
+            };
+            if (single_tile) {
+                boff qb = my_qb;
+                int len = my_len;
+                if (use_atbl) {
+                    const int o0 = tid < n_a ? tbl[tid * astride + w] : 0, o1 = tid < n_a ? tbl[tid * astride + w + 1] : 0;
+                    qb = my_qb + o0; len = o1 - o0;
+                } else if (W > 1) gwin_restrict<BLOCK>(B, n_a, qb, len, tile, c_lo, c_hi);
+                const int total = gwin_scan<true, BLOCK>(tile, qb, len, my_av);
+                GP_ADD(38);
+                if (total) gwin_run<true, BLOCK>(tile, total, add);
+            } else {
+                for (aoff base = pa; base < pe; base += BLOCK) {
+                    const int total = gwin_build<true, BLOCK>(A, B, base, pe, tile, W > 1 ? c_lo : 0, W > 1 ? c_hi : 0x7fffffff);
+                    GP_ADD(38);
+                    if (total) gwin_run<true, BLOCK>(tile, total, add);
+                    __syncthreads();
+                }
+            }
+            __syncthreads();
+            GP_ADD(39);
+            for (int t = tid; t < wn; t += BLOCK) c_v[gs + wbase + t] = acc[t];
+            __syncthreads();
+            GP_ADD(40);
+        }
+        // 4. leave the slot and the bitmap clean for the next row (the tile held partial sums: the bitmap words it
+        //    covers are zeroed again)
+        g_clear<BLOCK>(wp, summary, wsum, L);
+        {
+            const int used = min(swords, 2 * min(win, n));             // words overwritten by acc[0, min(win, n))
+            for (int w = tid; w < used; w += BLOCK) bits[w] = 0;
+        }
         __syncthreads();
         GP_ADD(41);
     }

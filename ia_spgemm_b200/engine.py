@@ -119,8 +119,8 @@ ABI_SYMBOLS = [
     "ias_csr_mul_csr_stream_cb",
     "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_touched_b_bytes", "ias_partition_rows", "ias_checksum",
     "ias_structure_hash",
-    "ias_csr_to_dia", "ias_dia_mul_dia_dev", "ias_download_dia", "ias_free_dia_dev", "ias_dia_relayout",
-    "ias_csr_to_ell", "ias_ell_mul_ell_dev", "ias_ell_mul_ell_dev64", "ias_download_ell", "ias_free_ell_dev", "ias_free_ell64_dev",
+    "ias_csr_to_dia", "ias_dia_mul_dia_dev", "ias_dia_mul_dia_rows_dev", "ias_download_dia", "ias_free_dia_dev", "ias_dia_relayout",
+    "ias_csr_to_ell", "ias_ell_mul_ell_dev", "ias_ell_mul_ell_dev64", "ias_download_ell", "ias_download_ell64", "ias_free_ell_dev", "ias_free_ell64_dev",
     "ias_csr_to_coo", "ias_coo_mul_coo_dev", "ias_coo_mul_coo_dev64", "ias_download_coo", "ias_download_coo64",
     "ias_free_coo_dev", "ias_free_coo64_dev",
     "ias_density_image", "ias_getinfo1", "ias_getinfo2", "ias_getinfo3", "ias_count_diagonals",
@@ -535,9 +535,12 @@ class Engine:
                 "diagonal_ind": di[: d.row + d.col - 1], "diagonal_offsets": off[: d.num_diagonals],
                 "values": val[: d.row * d.num_diagonals].reshape(d.row, d.num_diagonals)}
 
-    def DIA_MUL_DIA_DEV(self, A, B):
+    def DIA_MUL_DIA_DEV(self, A, B, rows=None):
         c, ms = DiaDev(), C.c_double()
-        self._ck(self.lib.ias_dia_mul_dia_dev(C.byref(A), C.byref(B), C.byref(c), C.byref(ms)))
+        if rows is None:
+            self._ck(self.lib.ias_dia_mul_dia_dev(C.byref(A), C.byref(B), C.byref(c), C.byref(ms)))
+        else:
+            self._ck(self.lib.ias_dia_mul_dia_rows_dev(C.byref(A), C.byref(B), C.c_int(rows[0]), C.c_int(rows[1]), C.byref(c), C.byref(ms)))
         return c, ms.value
 
     def free_dia(self, d):
@@ -559,7 +562,8 @@ class Engine:
         nr = np.zeros(max(e.row, 1), np.int32)
         ci = np.zeros(max(e.row * w, 1), np.int32)
         v = np.zeros(max(e.row * w, 1), np.float64)
-        self._ck(self.lib.ias_download_ell(C.byref(e), nr.ctypes.data_as(_I), ci.ctypes.data_as(_I), v.ctypes.data_as(_D)))
+        f = self.lib.ias_download_ell64 if isinstance(e, Ell64Dev) else self.lib.ias_download_ell
+        self._ck(f(C.byref(e), nr.ctypes.data_as(_I), ci.ctypes.data_as(_I), v.ctypes.data_as(_D)))
         return {"row": e.row, "col": e.col, "width": w, "nnz": e.nnz, "choice": bool(e.choice), "nnz_row": nr[: e.row],
                 "col_ind": ci[: e.row * w].reshape(e.row, w), "values": v[: e.row * w].reshape(e.row, w)}
 

@@ -148,7 +148,9 @@ long long ias_kernel_launches(void);            /* engine kernels launched since
  * Names: "global_rows_smem" (1 = windowed shared-memory kernels for rows beyond the CTA hash, 0 = L2 bitmap kernels),
  * "gwin_swords", "gwin_win", "gwin_sym_swords" (window sizes, 0 = automatic), "gwin_smem_kb", "gwin_max_sw" (numeric windowed
  * kernel only up to this many column super-windows per row, 0 = no limit), "g_win" (accumulate window of the L2 kernel), "g_coop", "gwin_takes_b2" (0/1 switches kept for A/B runs),
- * "trust_operand_cache" (see ias_forget_operand).  Also read from
+ * "trust_operand_cache" (see ias_forget_operand), "ell_onepass" (1 = one-pass ELL x ELL kernel where a row's products fit a
+ * warp's register sort, 0 = always the pipeline), "g_block" (1024 / 512 threads per CTA of the L2 kernel), "g_ldca", "g_v2" (1 = second generation of the L2 kernel: rank + emit
+ * from shared memory, split tables), "g_tbl" (its split-table capacity), "g_lpt" (1 = global rows in order of decreasing work).  Also read from
  * IAS_OPT_<NAME> in the environment by ias_init.  Results do not depend on any of them. */
 int ias_set_option(const char *name, long long value);
 int ias_get_option(const char *name, long long *value);
@@ -240,6 +242,10 @@ int ias_structure_hash(const IasCsr64Dev *C, int row_base, unsigned long long *h
 int ias_csr_to_dia(const IasCsrMatrixDev *A, double gate, IasDiaDev *out);
 /* DIA_MUL_DIA_DEV, GPU/detail/dia_dev/common_dia_dev.h:138-182 */
 int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, double *elapsed_ms);
+/* rows [row_begin,row_end) of C only (multi-GPU row blocks): C->row = row_end-row_begin, values[slot*C->row + (i-row_begin)];
+ * offsets and diagonal_ind are those of the whole product */
+int ias_dia_mul_dia_rows_dev(const IasDiaDev *A, const IasDiaDev *B, int row_begin, int row_end, IasDiaDev *C,
+                             double *elapsed_ms);
 int ias_download_dia(const IasDiaDev *dev, int *diagonal_ind, int *diagonal_offsets,
                      double *values_row_major);
 /* value order of a DIA matrix: to_row_major = 0 turns the reference's row-major values[i*nd + slot] (what
@@ -255,6 +261,7 @@ int ias_csr_to_ell(const IasCsrMatrixDev *A, double gate, IasEllDev *out);
 int ias_ell_mul_ell_dev(const IasEllDev *A, const IasEllDev *B, IasEllDev *C, double *elapsed_ms);   /* IAS_E_OVERFLOW when nnz(C) >= 2^31 */
 int ias_ell_mul_ell_dev64(const IasEllDev *A, const IasEllDev *B, IasEll64Dev *C, double *elapsed_ms);
 int ias_download_ell(const IasEllDev *dev, int *nnz_row, int *col_ind, double *values);
+int ias_download_ell64(const IasEll64Dev *dev, int *nnz_row, int *col_ind, double *values);
 int ias_free_ell_dev(IasEllDev *m);
 int ias_free_ell64_dev(IasEll64Dev *m);
 

@@ -430,3 +430,56 @@ def test_select_format_rule(eng):
     assert eng.select_format(f, True, True) == 3
     f[8] = 0.5
     assert eng.select_format(f, True, True) == 1
+
+
+def test_dia_row_blocks_concatenate(eng):
+    """ias_dia_mul_dia_rows_dev (multi-GPU row blocks of the DIA path): the blocks stack up to the full product."""
+    A = W.banded(1500, [-40, -1, 0, 3, 41], seed=8)
+    dA = eng.upload(*A)
+    d = eng.CSRtoDIA(dA, gate=20.0)
+    c, _ = eng.DIA_MUL_DIA_DEV(d, d)
+    full = eng.download_dia(c)
+    parts = []
+    for r0, r1 in ((0, 1), (1, 700), (700, 700), (700, 1499), (1499, 1500)):
+        cb, ms = eng.DIA_MUL_DIA_DEV(d, d, rows=(r0, r1))
+        assert cb.row == r1 - r0 and cb.num_diagonals == c.num_diagonals
+        got = eng.download_dia(cb)
+        assert np.array_equal(got["diagonal_offsets"], full["diagonal_offsets"])
+        parts.append(got["values"].reshape(r1 - r0, c.num_diagonals))
+        eng.free_dia(cb)
+    assert np.array_equal(np.concatenate(parts, axis=0), full["values"])
+    eng.free_dia(c); eng.free_dia(d); dA.close()
+
+
+@pytest.mark.parametrize("make", [lambda: W.uniform_rows(6000, 16, seed=2), lambda: W.poisson2d(50), lambda: W.banded(900, [-7, 0, 1, 2, 30, 31], seed=3),
+                                  lambda: W.random_sparse(400, 400, 0.01, seed=8, sort_columns=False),
+                                  lambda: W.uniform_rows(70000, 3, seed=5)],
+                         ids=["uniform16", "poisson", "banded6", "unsorted", "wide_cols"])
+def test_ell_onepass_kernel_equals_pipeline_and_oracle(eng, oracle, make):
+    """The one-pass ELL x ELL kernel (register sort started from the sorted B rows, no symbolic pass) and the Gustavson
+    pipeline on fixed-width rows give the same matrix, and both match ELL_MUL_ELL of the oracle."""
+    A = make()
+    dA = eng.upload(*A)
+    e = eng.CSRtoELL(dA, gate=1e9)
+    res = {}
+    for onepass in (1, 0):
+        eng.set_option("ell_onepass", onepass)
+        c, ms = eng.ELL_MUL_ELL_DEV(e, e)
+        res[onepass] = (eng.download_ell(c), c.nnz)
+        eng.free_ell(c)
+    eng.set_option("ell_onepass", 1)
+    a, b = res[1][0], res[0][0]
+    assert res[1][1] == res[0][1] and a["width"] == b["width"]
+    assert np.array_equal(a["nnz_row"], b["nnz_row"]) and np.array_equal(a["col_ind"], b["col_ind"])
+    assert np.allclose(a["values"], b["values"], rtol=1e-12, atol=0)
+    we = oracle.csr_to_ell(*A, gate=1e9)
+    want = oracle.ell_mul_ell(we, we)
+    assert a["width"] == want["width"] and np.array_equal(a["nnz_row"], want["nnz_row"]) and res[1][1] == want["nnz"]
+    mag = oracle.ell_mul_ell(dict(we, values=np.abs(we["values"])), dict(we, values=np.abs(we["values"])))["values"]
+    for i in range(0, A[0], max(1, A[0] // 400)):
+        n = int(want["nnz_row"][i])
+        o = np.argsort(want["col_ind"][i, :n], kind="stable")
+        assert np.array_equal(a["col_ind"][i, :n], want["col_ind"][i, :n][o])
+        assert np.all(np.abs(a["values"][i, :n] - want["values"][i, :n][o]) <= 1e-12 * np.abs(mag[i, :n][o]))
+        assert not a["values"][i, n:].any() and not a["col_ind"][i, n:].any()
+    eng.free_ell(e); dA.close()

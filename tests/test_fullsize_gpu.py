@@ -106,8 +106,25 @@ def test_uniform_full_size_properties(eng):
 # entry with CSR_MUL_CSR(A[r0:r1,:], A) (the reference function takes a rectangular A, csr:88-89): row_ptr and sorted
 # columns bit-exact, values within 1e-12 of the entry.  The device operand is downloaded (the generators are pinned
 # bit-identical to workloads.py in test_formats_gpu.py) so that the host never regenerates 10^8 entries.
+def _host_memory_available():
+    """Bytes this process may still use: the smaller of the machine's available memory and the cgroup's headroom."""
+    import psutil
+    avail = psutil.virtual_memory().available
+    for lim, cur in (("/sys/fs/cgroup/memory.max", "/sys/fs/cgroup/memory.current"),
+                     ("/sys/fs/cgroup/memory/memory.limit_in_bytes", "/sys/fs/cgroup/memory/memory.usage_in_bytes")):
+        try:
+            limit = open(lim).read().strip()
+            if limit != "max" and int(limit) < 2**60:
+                avail = min(avail, int(limit) - int(open(cur).read().strip()))
+        except Exception:
+            pass
+    return avail
+
+
 def _block_parity(eng, oracle, dA, host, blocks, mag=False):
     rows, cols, rp, ci, v = host
+    # the oracle keeps a dense accumulator of `cols` entries per thread (16 bytes each): bound the host memory
+    oracle.set_threads(min(oracle.threads(), 8 if cols <= (1 << 23) else 2))
     for r0, r1 in blocks:
         s, e = int(rp[r0]), int(rp[r1])
         blk_rp = (rp[r0:r1 + 1] - rp[r0]).astype(np.int32)
@@ -172,6 +189,9 @@ def test_rmat25_blocks_on_one_gpu(eng, oracle):
     info = eng.device_info()
     if info["free_bytes"] < 60 * 10**9:
         pytest.skip("needs ~60 GB of free HBM for the scale-25 generator")
+    if _host_memory_available() < 24 * 2**30:
+        pytest.skip("needs ~10 GB of host memory (operand copy + the oracle's per-thread accumulators) with headroom")
+    oracle.set_threads(2)
     dA = eng.gen_rmat(25, 16, seed=1)
     assert dA.nnz > 500_000_000
     host = dA.download()
