@@ -162,9 +162,11 @@ def poisson_rows(nx, ny, r0, r1):
     return mask.sum(axis=1).astype(np.int64), cand[mask].astype(np.int32), np.ascontiguousarray(vals[mask])
 
 
-def cpu_sample(kind, grid=4096, world=1, n=8000000, scale=22, target_products=6e8):
+def cpu_sample(kind, grid=4096, world=1, n=8000000, scale=22, target_products=6e8, host=None):
     """A bounded sample of the workload for the CPU arm: a contiguous row block of A with about target_products
     intermediate products (the whole matrix when it is that small) and the operand B it multiplies.
+    `host`: the operand already on the host (downloaded from the device generator, which is bit-identical to
+    workloads.py) -- saves minutes of NumPy generation for the large configs.
     Returns (A_block, B, products, description)."""
     from ia_spgemm_b200 import workloads as W
     from ia_spgemm_b200.multigpu import per_row_products
@@ -173,7 +175,7 @@ def cpu_sample(kind, grid=4096, world=1, n=8000000, scale=22, target_products=6e
         rows = nx * ny
         total = W.poisson_counts(nx)[1] if world == 1 else None
         if world == 1 and total <= 1.5 * target_products:
-            A = W.poisson2d(nx)
+            A = host if host is not None else W.poisson2d(nx)
             return A, A, total, "the full workload (%d rows, %d products)" % (rows, total)
         # the N x grid: a block of rows in the middle and exactly the B rows it touches (the rest of B stays empty)
         nblk = int(target_products // 25)
@@ -190,7 +192,7 @@ def cpu_sample(kind, grid=4096, world=1, n=8000000, scale=22, target_products=6e
         B = (rows, rows, rp_b.astype(np.int32), cb, vb)
         products = int(per_row_products(A[2], A[3], B[2]).sum())
         return A, B, products, "rows [%d,%d) of %d (%d products) x the B rows they touch" % (r0, r1, rows, products)
-    A = W.uniform_rows(n, 16, seed=1) if kind == "uniform" else W.rmat(scale, 16, seed=1)
+    A = host if host is not None else (W.uniform_rows(n, 16, seed=1) if kind == "uniform" else W.rmat(scale, 16, seed=1))
     rows, cols, rp, ci, v = A
     per_row = per_row_products(rp, ci, rp)
     total = int(per_row.sum())
@@ -485,6 +487,7 @@ class Bench:
         e_ms = max(ev0.elapsed_time(ev1), wall) / e_steps
         out = {"ms_per_step": e_ms, "h2d_bytes_per_step": int(r["h2d_bytes"]), "d2h_bytes_per_step": int(r["d2h_bytes"]),
                "result_format": r["format"], "phase_ms": {k: round(float(v), 3) for k, v in r["ms"].items()},
+               "host_ms_at": r.get("host_ms_at"),
                "api": "ias_spgemm_auto_host (features -> selection -> conversion -> multiply -> host result)" if api == "auto"
                       else "ias_csr_mul_csr_host (CSR_MUL_CSR on host operands)"}
         eng.lib.ias_release_host()
@@ -706,11 +709,13 @@ def main():
     if dia is not None:
         eng.free_dia(dia)
     del hA, pins
+    host_main = dA.download() if (rank == 0 and world == 1 and not args.no_cpu) else None
     dA.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu = cpu_baseline(kind, **kw)
+        cpu = cpu_baseline(kind, host=host_main, **kw)
+        del host_main
 
     # ================================================================== the other BASELINE configs
     if default_run and not args.no_also:
@@ -765,25 +770,29 @@ def side_config(B, eng, kind, args, with_cpu, with_cusparse):
         if kind == "rmat":
             leg = B.csr_leg(dA, 0, rows, 2, 1, True, 0, wname)           # 1.5e11 products per step: one warm-up, two timed steps
         else:
-            leg = B.csr_leg(dA, 0, rows, 5, 3, True, 0, wname)           # C (24.6 GB) is consumed in row batches
+            leg = B.csr_leg(dA, 0, rows, 5, 3, False, 0, wname)          # C (24.6 GB) is materialised
         out.update({k: leg[k] for k in ("ms_per_step", "value", "unit", "products", "nnz_C", "roofline")})
         out["detail"] = leg["detail"]
         if fmt == "ell":
             out["ell_path"] = B.ell_leg(dA, rows, products, 5, 3, wname)
         if with_cusparse and kind != "rmat":
             out["cusparse"] = B.cusparse_leg(dA, products)
+        host = dA.download() if with_cpu else None          # the device generator's operand, for the CPU sample below
         dA.close()
         if kind == "rmat" and with_cusparse:
             # cusparseSpGEMM materialises C and its workspace: scale 22 (0.86 TB) is out of reach, scale 18 (15 GB) is
             # the largest it holds; the engine is timed on the same operand beside it
-            d18 = make_operand(eng, "rmat", scale=18)
-            p18 = eng.GetFlop(d18, d18)
-            e18 = B.csr_leg(d18, 0, d18.dev.row, 3, 3, False, 0, workload_name("rmat", scale=18))
-            out["scale18"] = {"engine": {k: e18[k] for k in ("ms_per_step", "value", "unit", "products", "nnz_C")},
-                              "cusparse": B.cusparse_leg(d18, p18)}
-            d18.close()
+            for sc in (18, 16, 14):
+                d18 = make_operand(eng, "rmat", scale=sc)
+                p18 = eng.GetFlop(d18, d18)
+                e18 = B.csr_leg(d18, 0, d18.dev.row, 3, 3, False, 0, workload_name("rmat", scale=sc))
+                cu = B.cusparse_leg(d18, p18)
+                out["scale%d" % sc] = {"engine": {k: e18[k] for k in ("ms_per_step", "value", "unit", "products", "nnz_C")}, "cusparse": cu}
+                d18.close()
+                if "error" not in cu:
+                    break
         if with_cpu:
-            out["cpu_baseline"] = cpu_baseline(kind, repeats=1, **kw)
+            out["cpu_baseline"] = cpu_baseline(kind, repeats=1, host=host, **kw)
     except Exception as ex:
         out["error"] = ("%s: %s" % (type(ex).__name__, ex))[:300]
     return out

@@ -6,6 +6,8 @@
 // selected algorithm is the one that runs (the reference predicts and then runs everything, Appendix D of SURVEY.md).
 // The result comes back in the selected format's own layout, as every reference kernel returns it:
 // CSR (CSR_MUL_CSR, csr:85), DIA row-major values[row][diag] (DIA_mul_DIA, dia:101), ELL row-major (ELL_MUL_ELL, ell:80).
+#include <time.h>
+
 #include <algorithm>
 
 #include "common.cuh"
@@ -79,6 +81,13 @@ int ias_spgemm_auto_host(const IasCsrMatrix *A, const IasCsrMatrix *B, double ga
     Ctx &c = ctx();
     cudaStream_t s = c.stream;
     memset(out, 0, sizeof *out);
+    struct timespec t_in, t_out;
+    clock_gettime(CLOCK_MONOTONIC, &t_in);
+    auto stamp = [&](int k) {
+        struct timespec t;
+        clock_gettime(CLOCK_MONOTONIC, &t);
+        out->ms_host[k] = (t.tv_sec - t_in.tv_sec) * 1e3 + (t.tv_nsec - t_in.tv_nsec) / 1e6;
+    };
     const bool alias = (A == B) || (A->row_ind == B->row_ind && A->col_ind == B->col_ind && A->values == B->values &&
                                     A->row == B->row && A->col == B->col);
     cudaEvent_t *ev = c.ev_bin + 24;             // eight events nobody else uses during this call
@@ -100,6 +109,7 @@ int ias_spgemm_auto_host(const IasCsrMatrix *A, const IasCsrMatrix *B, double ga
     AUTO_TRY(ias_upload_csr(A, &dA));
     if (alias) dB = dA; else AUTO_TRY(ias_upload_csr(B, &dB));
     cudaEventRecord(ev[1], s);
+    stamp(0);
 
     // ---- features (CPU/main.cpp:655-679).  The DIA conversion doubles as the diagonal census.
     double *f = out->features;
@@ -134,11 +144,13 @@ int ias_spgemm_auto_host(const IasCsrMatrix *A, const IasCsrMatrix *B, double ga
     out->format = cls;
     out->row = dA.row; out->col = dB.col;
     cudaEventRecord(ev[2], s);
+    stamp(1);
 
     // ---- conversion + multiply in the selected format, result into the pinned host arena
     void *base = nullptr;
     if (cls == 2) {
         cudaEventRecord(ev[3], s);                // DIA operands were built above (counted as selection + conversion)
+        stamp(2);
         double ms = 0;
         AUTO_TRY(ias_dia_mul_dia_dev(&a_dia, &b_dia, &c_dia, &ms));
         const int nd = c_dia.num_diagonals;
@@ -151,6 +163,7 @@ int ias_spgemm_auto_host(const IasCsrMatrix *A, const IasCsrMatrix *B, double ga
             c.launches++;
         }
         cudaEventRecord(ev[4], s);
+        stamp(3);
         const size_t span = (size_t)std::max(c_dia.row + c_dia.col - 1, 1);
         const size_t o_off = up256(cells * 8), o_ind = o_off + up256((size_t)std::max(nd, 1) * 4);
         AUTO_TRY(host_arena2(o_ind + span * 4 + 256, &base));
@@ -212,7 +225,11 @@ int ias_spgemm_auto_host(const IasCsrMatrix *A, const IasCsrMatrix *B, double ga
     out->ms_convert = ms_between(ev[2], ev[3]);
     out->ms_multiply = ms_between(ev[3], ev[4]);
     out->ms_d2h = ms_between(ev[4], ev[5]);
+    stamp(4);
     cleanup();
+    stamp(5);
+    clock_gettime(CLOCK_MONOTONIC, &t_out);
+    out->ms_wall = (t_out.tv_sec - t_in.tv_sec) * 1e3 + (t_out.tv_nsec - t_in.tv_nsec) / 1e6;
 #undef AUTO_TRY
     return IAS_OK;
 }

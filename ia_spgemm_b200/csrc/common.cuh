@@ -27,6 +27,8 @@ struct Tuning {
     long long g_lpt = 1;              // global rows are handed out in order of decreasing work
     long long g_block = 1024;         // L2 bitmap kernel: threads per CTA (1024: one row per SM, 512: two)
     long long bulk_store = 1;         // shared -> global bulk copies (cp.async.bulk) for staged output tiles (0: per-thread stores)
+    long long dia_vec = 0;            // DIA x DIA: two adjacent rows per thread with 128-bit accesses -- measured SLOWER than the scalar
+                                      // kernel on B200 (0.617 vs 0.542 ms on Poisson 4096^2), kept for the record
     long long ell_onepass = 1;        // ELL x ELL: one-pass register-sort kernel when a row's products fit (0: always the pipeline)
     long long trust_operand_cache = 0; // 1: remember B's canonical flag per operand (pointers + shape) across calls; the caller
                                       // promises not to rewrite or re-allocate an operand without ias_forget_operand

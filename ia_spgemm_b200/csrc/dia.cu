@@ -106,6 +106,56 @@ __global__ void __launch_bounds__(BLOCK) k_dia_mul_dia(int row0, int rows /* one
     }
 }
 
+// Same product with 128-bit accesses: a thread owns two ADJACENT rows (i, i + 1), i even.  ncu on the scalar kernel:
+// issue slots 76 % busy, DRAM at 0.76 of the copy peak -- instruction bound.  Here a pair whose A and B indices are
+// even for even i (flag bit 0 / bit 1 of DiaPair::pad0, set on the host) costs one LDG.128 per operand and two FMAs
+// for two rows; odd offsets (the +-1 diagonals of a stencil) fall back to two 64-bit loads for that operand.
+// Requires an even row0 and an even number of output rows per diagonal (so that every C store is 16-byte aligned).
+template <int BLOCK, bool TABLES_IN_SMEM>
+__global__ void __launch_bounds__(BLOCK) k_dia_mul_dia_v2(int row0, int rows /* one past the last row */, int c_nd, const double *__restrict__ a_val,
+                                                          const double *__restrict__ b_val,
+                                                          const int *__restrict__ pair_start /* c_nd+1 */,
+                                                          const DiaPair *__restrict__ pairs, int npairs,
+                                                          double *__restrict__ c_val)
+{
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    const DiaPair *s_pairs = pairs;
+    const int *s_start = pair_start;
+    if (TABLES_IN_SMEM) {
+        DiaPair *w_pairs = reinterpret_cast<DiaPair *>(sm_raw);
+        int *w_start = reinterpret_cast<int *>(w_pairs + npairs);
+        for (int t = threadIdx.x; t < npairs; t += BLOCK) w_pairs[t] = pairs[t];
+        for (int t = threadIdx.x; t <= c_nd; t += BLOCK) w_start[t] = pair_start[t];
+        __syncthreads();
+        s_pairs = w_pairs; s_start = w_start;
+    }
+    const size_t out_rows = (size_t)(rows - row0);
+    for (long long base = row0 + (long long)blockIdx.x * (2 * BLOCK); base < rows; base += (long long)gridDim.x * (2 * BLOCK)) {
+        const long long i = base + 2 * threadIdx.x;                    // rows i and i + 1 (rows is even: both or neither exist)
+        if (i >= rows) continue;
+        for (int d = 0; d < c_nd; ++d) {
+            double acc0 = 0.0, acc1 = 0.0;
+            const int pe = s_start[d + 1];
+            for (int p = s_start[d]; p < pe; ++p) {
+                const DiaPair P = s_pairs[p];
+                if (i >= P.lo && i + 1 < P.hi) {                       // both rows contribute: the common case
+                    double a0, a1, b0, b1;
+                    if (P.pad0 & 1) { const double2 t = __ldg(reinterpret_cast<const double2 *>(a_val + P.a0 + i)); a0 = t.x; a1 = t.y; }
+                    else { a0 = __ldg(a_val + P.a0 + i); a1 = __ldg(a_val + P.a0 + i + 1); }
+                    if (P.pad0 & 2) { const double2 t = __ldg(reinterpret_cast<const double2 *>(b_val + P.b0 + i)); b0 = t.x; b1 = t.y; }
+                    else { b0 = __ldg(b_val + P.b0 + i); b1 = __ldg(b_val + P.b0 + i + 1); }
+                    acc0 += a0 * b0;
+                    acc1 += a1 * b1;
+                } else {
+                    if (i >= P.lo && i < P.hi) acc0 += __ldg(a_val + P.a0 + i) * __ldg(b_val + P.b0 + i);
+                    if (i + 1 >= P.lo && i + 1 < P.hi) acc1 += __ldg(a_val + P.a0 + i + 1) * __ldg(b_val + P.b0 + i + 1);
+                }
+            }
+            *reinterpret_cast<double2 *>(c_val + (size_t)d * out_rows + (i - row0)) = make_double2(acc0, acc1);
+        }
+    }
+}
+
 // diagonal_ind[offset + rows - 1] = slot for the c_nd present diagonals (the rest stays 0)
 __global__ void k_scatter_diag_ind(int c_nd, int rows, const int *__restrict__ offsets, int *__restrict__ diag_ind)
 {
@@ -239,7 +289,12 @@ int ias_dia_mul_dia_rows_dev(const IasDiaDev *A, const IasDiaDev *B, int r0, int
             long long lo = std::max<long long>(0, std::max(-oa, -oa - ob));
             long long hi = std::min<long long>(A->row, std::min<long long>((long long)A->col - oa, (long long)B->col - oa - ob));
             if (lo < hi)
-                pairs.push_back({oa + ob, DiaPair{(long long)a * A->row, (long long)b * B->row + oa, (int)lo, (int)hi, 0, 0}});
+            {
+                // bit 0 / bit 1: the A / B value index of an even row is even (128-bit loads in k_dia_mul_dia_v2)
+                const long long a0 = (long long)a * A->row, b0 = (long long)b * B->row + oa;
+                const int al = ((a0 & 1) == 0 ? 1 : 0) | ((b0 & 1) == 0 ? 2 : 0);
+                pairs.push_back({oa + ob, DiaPair{a0, b0, (int)lo, (int)hi, al, 0}});
+            }
         }
     std::stable_sort(pairs.begin(), pairs.end(), [](const Pair &x, const Pair &y) { return x.off < y.off; });
     std::vector<int> c_off, pstart;
@@ -271,7 +326,15 @@ int ias_dia_mul_dia_rows_dev(const IasDiaDev *A, const IasDiaDev *B, int r0, int
     if (!pab.empty()) IAS_CUDA(cudaMemcpyAsync(d_pairs.p, pab.data(), sizeof(DiaPair) * pab.size(), cudaMemcpyHostToDevice, s));
 
     size_t sm = sizeof(DiaPair) * pab.size() + sizeof(int) * ((size_t)c_nd + 1);
-    if (nrows && c_nd) {
+    // 128-bit variant: even first row, even row count (C stores), 16-byte aligned value arrays
+    const bool vec = c.tune.dia_vec != 0 && (r0 & 1) == 0 && (nrows & 1) == 0 && sm <= 32 * 1024 &&
+                     ((uintptr_t)A->values_dev & 15) == 0 && ((uintptr_t)B->values_dev & 15) == 0;
+    if (nrows && c_nd && vec) {
+        constexpr int BLOCK = 256;
+        unsigned grid = (unsigned)std::min<long long>(grid_for(nrows, 2 * BLOCK), (long long)c.sm_count * 8 * 64);
+        IAS_LAUNCH((k_dia_mul_dia_v2<BLOCK, true>), grid, BLOCK, sm, r0, r1, c_nd, A->values_dev, B->values_dev, d_pstart.p, d_pairs.p,
+                   (int)pab.size(), val.p);
+    } else if (nrows && c_nd) {
         constexpr int BLOCK = 256;
         unsigned grid = (unsigned)std::min<long long>(grid_for(nrows, 2 * BLOCK), (long long)c.sm_count * 8 * 64);
         if (sm <= 32 * 1024) {

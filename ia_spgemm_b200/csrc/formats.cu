@@ -130,13 +130,15 @@ __device__ __forceinline__ void warp_sort_runs(KeyT (&key)[IPL], int lane, int r
 
 template <class KeyT, int IPL, bool FULL /* every row of A and B holds exactly `width` entries */, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_ell_mul_ell(int nrows, EllView A, EllView B, int log2_run, int sorted_runs, int vec_ok,
-                                                       int w_ub, int *__restrict__ c_nr, int *__restrict__ c_ci, double *__restrict__ c_v,
+                                                       int w_ub, int bulk, int *__restrict__ c_nr, int *__restrict__ c_ci, double *__restrict__ c_v,
                                                        unsigned long long *__restrict__ total_nnz, int *__restrict__ max_nnz)
 {
     constexpr int N = 32 * IPL;
     constexpr int IDX_BITS = IPL == 16 ? 9 : IPL == 8 ? 8 : IPL == 4 ? 7 : 6;
     constexpr int WARPS = BLOCK / 32;
-    __shared__ double s_vals[WARPS][N];
+    // per warp: the products' values, later the finished row (values and columns) on its way out
+    __shared__ __align__(16) double s_vals[WARPS][N];
+    __shared__ __align__(16) int s_cols[WARPS][N];
     __shared__ unsigned long long s_total;
     __shared__ int s_max;
     const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -145,11 +147,13 @@ __global__ void __launch_bounds__(BLOCK) k_ell_mul_ell(int nrows, EllView A, Ell
     const KeyT PAD = ~(KeyT)0;
     const KeyT IDX_MASK = ((KeyT)1 << IDX_BITS) - 1;
     double *svals = s_vals[w];
+    int *scols = s_cols[w];
     const int e0 = lane * IPL;                       // first slot of this lane
     const int a = e0 >> log2_run;                    // its run = A entry (a run spans run / IPL >= 1 lanes)
     const int b0 = e0 & ((1 << log2_run) - 1);       // first B position of this lane inside the run
     long long my_total = 0;
     int my_max = 0;
+    bool pending = false;                            // a bulk copy of the previous row may still be reading svals / scols
     const int nwarps = gridDim.x * WARPS;
     for (int i = blockIdx.x * WARPS + w; i < nrows; i += nwarps) {
         const int na = FULL ? A.w : __ldg(A.nr + i);
@@ -160,32 +164,40 @@ __global__ void __launch_bounds__(BLOCK) k_ell_mul_ell(int nrows, EllView A, Ell
             av = __ldg(A.v + (long long)i * A.w + a);
             lenb = FULL ? B.w : __ldg(B.nr + j);
         }
-        KeyT key[IPL];
+        // this lane's IPL consecutive entries of B row j, into registers first: the loads are in flight while the
+        // copy engine finishes reading the previous row out of shared memory
+        int cc[IPL];
+        double vv[IPL];
         const long long qb = (long long)j * B.w + b0;
         if (FULL && vec_ok && j >= 0 && b0 + IPL <= B.w) {
-            // IPL consecutive entries of B row j: 128-bit loads (IPL is a multiple of 4 here, the row start 16-byte aligned)
 #pragma unroll
-            for (int r = 0; r < IPL; r += 4) {
+            for (int r = 0; r < IPL; r += 4) {       // 128-bit loads (IPL is a multiple of 4 here, the row start 16-byte aligned)
                 const int4 c4 = __ldg(reinterpret_cast<const int4 *>(B.ci + qb + r));
                 const double2 v01 = __ldg(reinterpret_cast<const double2 *>(B.v + qb + r));
                 const double2 v23 = __ldg(reinterpret_cast<const double2 *>(B.v + qb + r + 2));
-                const int cc[4] = {c4.x, c4.y, c4.z, c4.w};
-                const double vv[4] = {v01.x, v01.y, v23.x, v23.y};
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    if (r + u < IPL) {
-                        key[r + u] = ((KeyT)(unsigned)cc[u] << IDX_BITS) | (KeyT)(e0 + r + u);
-                        svals[e0 + r + u] = av * vv[u];
-                    }
-                }
+                cc[r] = c4.x; vv[r] = v01.x;
+                if (r + 1 < IPL) { cc[r + 1] = c4.y; vv[r + 1] = v01.y; }
+                if (r + 2 < IPL) { cc[r + 2] = c4.z; vv[r + 2] = v23.x; }
+                if (r + 3 < IPL) { cc[r + 3] = c4.w; vv[r + 3] = v23.y; }
             }
         } else {
 #pragma unroll
             for (int r = 0; r < IPL; ++r) {
                 const bool valid = j >= 0 && b0 + r < lenb;
-                key[r] = valid ? (((KeyT)(unsigned)__ldg(B.ci + qb + r) << IDX_BITS) | (KeyT)(e0 + r)) : PAD;
-                svals[e0 + r] = valid ? av * __ldg(B.v + qb + r) : 0.0;
+                cc[r] = valid ? __ldg(B.ci + qb + r) : -1;
+                vv[r] = valid ? __ldg(B.v + qb + r) : 0.0;
             }
+        }
+        if (pending) {                               // warp-uniform
+            if (lane == 0) bulk_wait_group_read0();
+            __syncwarp();
+            pending = false;
+        }
+        KeyT key[IPL];
+#pragma unroll
+        for (int r = 0; r < IPL; ++r) {
+            key[r] = cc[r] >= 0 ? (((KeyT)(unsigned)cc[r] << IDX_BITS) | (KeyT)(e0 + r)) : PAD;
+            svals[e0 + r] = av * vv[r];
         }
         __syncwarp();
         warp_sort_runs<KeyT, IPL>(key, lane, sorted_runs ? (1 << log2_run) : 1);
@@ -229,18 +241,34 @@ __global__ void __launch_bounds__(BLOCK) k_ell_mul_ell(int nrows, EllView A, Ell
         }
         double carry_in = __shfl_up_sync(0xffffffffu, carry, 1);
         if (lane == 0) carry_in = 0.0;
+        __syncwarp();                                              // every product value is in a register: svals becomes the output row
         const long long gs = (long long)i * w_ub;
         int opos = tincl - tails;
         double run_sum = carry_in;
 #pragma unroll
         for (int r = 0; r < IPL; ++r) {
             run_sum = head[r] ? v[r] : run_sum + v[r];
-            if (is_tail[r]) { c_ci[gs + opos] = (int)(key[r] >> IDX_BITS); c_v[gs + opos] = run_sum; ++opos; }
+            if (is_tail[r]) { scols[opos] = (int)(key[r] >> IDX_BITS); svals[opos] = run_sum; ++opos; }
         }
-        for (int p = count + lane; p < w_ub; p += 32) { c_ci[gs + p] = 0; c_v[gs + p] = 0.0; }      // padding = 0 / 0.0 (ell:54-56)
+        for (int p = count + lane; p < w_ub; p += 32) { scols[p] = 0; svals[p] = 0.0; }      // padding = 0 / 0.0 (ell:54-56)
+        __syncwarp();
+        if (bulk) {
+            // the finished row (w_ub entries, padding included) leaves through the copy engine: two cp.async.bulk per
+            // row instead of 2 * w_ub / 32 strided stores per lane, and it overlaps the next row's loads
+            if (lane == 0) {
+                fence_proxy_async_shared();
+                bulk_store_shared_to_global(c_ci + gs, scols, (unsigned)w_ub * 4u);
+                bulk_store_shared_to_global(c_v + gs, svals, (unsigned)w_ub * 8u);
+                bulk_commit_group();
+            }
+            pending = true;
+        } else {
+            for (int p = lane; p < w_ub; p += 32) { c_ci[gs + p] = scols[p]; c_v[gs + p] = svals[p]; }
+            __syncwarp();
+        }
         if (lane == 0) { c_nr[i] = count; my_total += count; my_max = max(my_max, count); }
-        __syncwarp();                                              // svals is rewritten by the next row
     }
+    if (pending && lane == 0) bulk_wait_group_read0();             // shared memory must outlive the copy's reads
     if (lane == 0) { if (my_total) atomicAdd(&s_total, (unsigned long long)my_total); atomicMax(&s_max, my_max); }
     __syncthreads();
     if (threadIdx.x == 0) { if (s_total) atomicAdd(total_nnz, s_total); if (s_max) atomicMax(max_nnz, s_max); }
@@ -385,6 +413,7 @@ static int ell_mul_onepass(const IasEllDev *A, const IasEllDev *B, IasEll64Dev *
     const bool full = h_int[1] == wa && h_int[2] == wb;
     const int sorted_runs = h_sc[4] == 0 ? 1 : 0;
     const int vec_ok = (wb % 4 == 0 && ipl % 4 == 0) ? 1 : 0;
+    const int bulk = (c.tune.bulk_store != 0 && w_ub % 4 == 0 && w_ub <= n_slots) ? 1 : 0;     // 16-byte aligned rows of C
 
     const size_t cells = (size_t)A->row * (size_t)w_ub;
     DBuf<int> nr, ci;
@@ -396,7 +425,7 @@ static int ell_mul_onepass(const IasEllDev *A, const IasEllDev *B, IasEll64Dev *
     const unsigned grid = (unsigned)std::min<long long>(grid_for(A->row, EB / 32), (long long)c.sm_count * 16);
 #define IAS_ELL1(KT, IPL, FULLROWS)                                                                                          \
     IAS_LAUNCH((k_ell_mul_ell<KT, IPL, FULLROWS, EB>), grid, EB, 0, A->row, av, bv, log2_run, sorted_runs, vec_ok, (int)w_ub, \
-               nr.p, ci.p, cv.p, d_sc.p, d_int)
+               bulk, nr.p, ci.p, cv.p, d_sc.p, d_int)
 #define IAS_ELL2(KT, FULLROWS)                                                                     \
     do {                                                                                           \
         if (ipl == 2) IAS_ELL1(KT, 2, FULLROWS); else if (ipl == 4) IAS_ELL1(KT, 4, FULLROWS);     \

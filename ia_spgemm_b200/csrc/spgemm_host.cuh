@@ -512,7 +512,7 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
             // 128 KB tile + 32 KB of split points = the 160 KB the first generation gives to its tile alone, so the
             // L1 that is left for the B-row stream is the same.
             auto k = k_num_global2<AV, BV, 1024>;
-            int win = (int)std::min<long long>(16384, std::max<long long>(16, c.tune.g_win & ~15LL));
+            int win = (int)std::min<long long>(16384, std::max<long long>(64, c.tune.g_win & ~63LL));     // bitmap of 2 * win words, scanned 128 at a time
             int tbl_cap = (int)std::min<long long>(16384, std::max<long long>(0, c.tune.g_tbl));
             size_t sm = (size_t)win * sizeof(double) + (size_t)tbl_cap * sizeof(int);
             IAS_TRY(opt_in_smem(k, sm));

@@ -1455,14 +1455,14 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
     __shared__ typename Scan::TempStorage scan_tmp;
     __shared__ int s_row;
     __shared__ unsigned s_carry, s_swtot;
-    __shared__ unsigned s_blk[2 * BLOCK];                                     // per-block (32 words) populations of a super-window
+    __shared__ unsigned s_blk[BLOCK];                                         // populations of a super-window's chunks of 128 words
     __shared__ int s_bnd[G2_MAX_BND + 1];
     __shared__ CtaTile<BV, BLOCK> tile;
     uint2 *wp = reinterpret_cast<uint2 *>(work + (size_t)blockIdx.x * L.slot_words);
     unsigned *summary = reinterpret_cast<unsigned *>(wp + L.words);
     unsigned *wsum = summary + L.sumw + L.blocks;
     const int tid = threadIdx.x, wid = tid >> 5, lane = tid & 31;
-    const int swords = min(win * 2, 2 * BLOCK * 32);                           // s_blk holds 2 * BLOCK blocks
+    const int swords = min(win * 2, 2 * BLOCK * 32);                           // a multiple of 128 (the host rounds win to 64)
     const long long span = (long long)swords * 32;
     const int nsw = (int)((ncols + span - 1) / span);
     for (int w = tid; w < swords; w += BLOCK) bits[w] = 0;
@@ -1550,47 +1550,61 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
             if (!any) continue;
             const int w0g = c_lo >> 5;                                // first global word of the super-window
             const int nwords = min(swords, L.words - w0g);            // a multiple of 32 (L.words and swords are)
-            const int nblk = nwords >> 5;
-            // populations of the blocks of 32 words
-            for (int b = wid; b < nblk; b += NWARPS) {
-                const int c = warp_sum((int)__popc(bits[b * 32 + lane]));
-                if (lane == 0) s_blk[b] = (unsigned)c;
+            // The bitmap is scanned in chunks of 128 words, four consecutive words per lane (one 128-bit shared-memory
+            // load): one warp scan ranks 4096 columns.  (Ranking 32 words per warp scan cost more than the marking itself
+            // on sparse rows: the dependent shuffle chain is paid per scan, not per entry.)  Words between nwords and
+            // the next multiple of 128 exist in the bitmap and are zero.
+            const int nchunk = (nwords + 127) >> 7;
+            const uint4 *bits4 = reinterpret_cast<const uint4 *>(bits);
+            for (int c = wid; c < nchunk; c += NWARPS) {
+                const uint4 w4 = bits4[c * 32 + lane];
+                const int cnt = warp_sum((int)(__popc(w4.x) + __popc(w4.y) + __popc(w4.z) + __popc(w4.w)));
+                if (lane == 0) s_blk[c] = (unsigned)cnt;
             }
             __syncthreads();
             {
-                const int b0i = tid * 2;
-                const unsigned v0 = b0i < nblk ? s_blk[b0i] : 0u, v1 = b0i + 1 < nblk ? s_blk[b0i + 1] : 0u;
+                const unsigned v0 = tid < nchunk ? s_blk[tid] : 0u;       // nchunk <= 2 * BLOCK * 32 / 128 = BLOCK / 2
                 unsigned excl, tot;
-                Scan(scan_tmp).ExclusiveSum(v0 + v1, excl, tot);
-                if (b0i < nblk) s_blk[b0i] = excl;
-                if (b0i + 1 < nblk) s_blk[b0i + 1] = excl + v0;
+                Scan(scan_tmp).ExclusiveSum(v0, excl, tot);
+                if (tid < nchunk) s_blk[tid] = excl;
                 if (tid == 0) s_swtot = tot;
             }
             __syncthreads();
-            // cells + sorted columns of the super-window, a warp per block of 32 words; the bitmap is left clean
+            // cells + sorted columns of the super-window; the bitmap is left clean
             const unsigned base_rank = s_carry;
-            for (int b = wid; b < nblk; b += NWARPS) {
-                const int w = b * 32 + lane;
-                unsigned word = bits[w];
-                const unsigned m = __ballot_sync(0xffffffffu, word != 0u);
-                if (!m) continue;
-                const int c = __popc(word);
-                int incl = c;
+            for (int c = wid; c < nchunk; c += NWARPS) {
+                const uint4 w4 = bits4[c * 32 + lane];
+                const unsigned wd[4] = {w4.x, w4.y, w4.z, w4.w};
+                const unsigned nz = (wd[0] ? 1u : 0u) | (wd[1] ? 2u : 0u) | (wd[2] ? 4u : 0u) | (wd[3] ? 8u : 0u);
+                if (!__any_sync(0xffffffffu, nz != 0u)) continue;
+                const int cnt = __popc(wd[0]) + __popc(wd[1]) + __popc(wd[2]) + __popc(wd[3]);
+                int incl = cnt;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) { int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
-                if (word) {
-                    unsigned rank = base_rank + s_blk[b] + (unsigned)(incl - c);
-                    wp[w0g + w] = make_uint2(word, rank);
-                    bits[w] = 0;
-                    const int col0 = c_lo + w * 32;
-                    while (word) {
-                        const int bit = __ffs(word) - 1;
-                        word &= word - 1;
-                        c_ci[gs + rank] = col0 + bit;
-                        ++rank;
+                // which of a block's 32 words are non-zero (g_clear reads this): a block = 8 lanes x 4 words
+                unsigned part = nz << (4 * (lane & 7));
+                part |= __shfl_xor_sync(0xffffffffu, part, 1);
+                part |= __shfl_xor_sync(0xffffffffu, part, 2);
+                part |= __shfl_xor_sync(0xffffffffu, part, 4);
+                if ((lane & 7) == 0 && part) wsum[(w0g >> 5) + c * 4 + (lane >> 3)] = part;
+                if (nz) {
+                    unsigned rank = base_rank + s_blk[c] + (unsigned)(incl - cnt);
+                    const int w = c * 128 + lane * 4;
+                    *reinterpret_cast<uint4 *>(bits + w) = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+                    for (int x = 0; x < 4; ++x) {
+                        unsigned word = wd[x];
+                        if (!word) continue;
+                        wp[w0g + w + x] = make_uint2(word, rank);
+                        const int col0 = c_lo + (w + x) * 32;
+                        while (word) {
+                            const int bit = __ffs(word) - 1;
+                            word &= word - 1;
+                            c_ci[gs + rank] = col0 + bit;
+                            ++rank;
+                        }
                     }
                 }
-                if (lane == 0) wsum[(w0g >> 5) + b] = m;
             }
             __syncthreads();
             if (tid == 0) s_carry = base_rank + s_swtot;
@@ -2040,25 +2054,33 @@ __global__ void __launch_bounds__(BLOCK) k_num_gwin(const int *__restrict__ rows
 }
 
 // ---------------------------------------------------------------- consumers / small utilities
-// order-independent structure hash + checksum of a batch of C: sum over entries of mix64(row<<32 | col)
+// order-independent structure hash + checksum of a batch of C: sum over entries of mix64(row<<32 | col).
+// A warp takes 32 * PER consecutive entries and reads them lane-strided (coalesced); the rows they belong to lie
+// between the rows of the chunk's first and last entry (two searches per warp), so the per-entry search runs over
+// that span only -- zero steps for the long rows of a power-law result, five or six for a stencil's.
 static __global__ void __launch_bounds__(256) k_consume(int nrows, int row_base, const long long *__restrict__ rp, long long rp0,
                                                  const int *__restrict__ ci, const double *__restrict__ v,
                                                  unsigned long long *__restrict__ hash_out, double *__restrict__ sum_out)
 {
     constexpr int PER = 16;
-    long long n = rp[nrows] - rp0;
-    long long e0 = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * PER;
+    const long long n = rp[nrows] - rp0;
+    const int lane = threadIdx.x & 31;
+    const long long warp_id = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long c0 = warp_id * (32 * PER);
     unsigned long long h = 0;
     double s = 0.0;
-    if (e0 < n) {
-        long long e1 = min(e0 + PER, n);
-        int lo = 0, hi = nrows;                 // last row with rp[row]-rp0 <= e0
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (rp[mid] - rp0 <= e0) lo = mid; else hi = mid; }
-        int row = lo;
-        for (long long e = e0; e < e1; ++e) {
-            while (rp[row + 1] - rp0 <= e) ++row;
-            h += mix64(((unsigned long long)(unsigned)(row_base + row) << 32) | (unsigned)ci[e]);
-            s += v[e];
+    if (c0 < n) {
+        const long long c1 = min(c0 + 32 * PER, n);
+        auto row_of = [&](long long e, int lo, int hi) {        // last row in [lo, hi] with rp[row] - rp0 <= e
+            while (lo < hi) { int mid = (lo + hi + 1) >> 1; if (rp[mid] - rp0 <= e) lo = mid; else hi = mid - 1; }
+            return lo;
+        };
+        const int r_lo = row_of(c0, 0, nrows - 1), r_hi = row_of(c1 - 1, r_lo, nrows - 1);
+#pragma unroll 4
+        for (long long e = c0 + lane; e < c1; e += 32) {
+            const int row = r_lo == r_hi ? r_lo : row_of(e, r_lo, r_hi);
+            h += mix64(((unsigned long long)(unsigned)(row_base + row) << 32) | (unsigned)__ldg(ci + e));
+            s += __ldg(v + e);
         }
     }
     typedef cub::BlockReduce<unsigned long long, 256> RH;

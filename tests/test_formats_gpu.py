@@ -209,8 +209,9 @@ def test_coo_matches_oracle(eng, oracle, name, make):
     assert eng.lib.ias_sizeof_coo(A[0], c.nnz) == oracle.sizeof_coo(A[0], c.nnz)
     c32, _ = eng.COO_MUL_COO_DEV(k, k, int32=True)               # the reference's CooMatrixDev layout (int32 nnz / row_offset)
     got32 = eng.download_coo(c32)
-    for key in ("row_offset", "row_ind", "col_ind", "values"):
+    for key in ("row_offset", "row_ind", "col_ind"):
         assert np.array_equal(got32[key], got[key]), key
+    assert np.allclose(got32["values"], got["values"], rtol=1e-13, atol=0)      # two runs: shared-memory additions in another order
     eng.free_coo(c32)
     eng.free_coo(c); eng.free_coo(k); dA.close()
 
@@ -483,3 +484,24 @@ def test_ell_onepass_kernel_equals_pipeline_and_oracle(eng, oracle, make):
         assert np.all(np.abs(a["values"][i, :n] - want["values"][i, :n][o]) <= 1e-12 * np.abs(mag[i, :n][o]))
         assert not a["values"][i, n:].any() and not a["col_ind"][i, n:].any()
     eng.free_ell(e); dA.close()
+
+
+@pytest.mark.parametrize("make,rows", [(lambda: W.poisson2d(64), None), (lambda: W.banded(2000, [-301, -2, -1, 0, 1, 7, 300], seed=9), (100, 1700)),
+                                        (lambda: W.banded(1001, [-3, 0, 4], seed=2), None)], ids=["poisson", "banded_block", "odd_rows"])
+def test_dia_vectorised_kernel_equals_scalar(eng, make, rows):
+    """k_dia_mul_dia_v2 (two adjacent rows per thread, 128-bit loads where the diagonal offset keeps them aligned) adds the
+    pairs of a row in the same order as the scalar kernel: bit-identical results.  Odd row counts take the scalar kernel."""
+    A = make()
+    dA = eng.upload(*A)
+    d = eng.CSRtoDIA(dA, gate=1e9)
+    out = {}
+    saved = eng.get_option("dia_vec")
+    for vec in (1, 0):
+        eng.set_option("dia_vec", vec)
+        c, ms = eng.DIA_MUL_DIA_DEV(d, d, rows=rows)
+        out[vec] = eng.download_dia(c)
+        eng.free_dia(c)
+    eng.set_option("dia_vec", saved)
+    assert np.array_equal(out[1]["diagonal_offsets"], out[0]["diagonal_offsets"])
+    assert np.array_equal(out[1]["values"], out[0]["values"])
+    eng.free_dia(d); dA.close()
