@@ -85,7 +85,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -98,6 +98,22 @@ class ClockSampler:
 
     def mark(self):
         return time.perf_counter()
+
+    def pause(self):
+        """Stop polling while host-heavy legs run (e2e, CPU baseline): frequent NVML queries serialise with the many
+        small driver calls of those paths; the clocks record is about the device-timed region."""
+        if self.proc:
+            try:
+                self.proc.send_signal(19)       # SIGSTOP
+            except Exception:
+                pass
+
+    def resume(self):
+        if self.proc:
+            try:
+                self.proc.send_signal(18)       # SIGCONT
+            except Exception:
+                pass
 
     def summary(self, t0=None, t1=None):
         """Clocks seen between two marks (the whole run when omitted)."""
@@ -119,6 +135,7 @@ class ClockSampler:
 
     def stop(self):
         if self.proc:
+            self.resume()
             self.proc.terminate()
             self.thread.join(timeout=2)
 
@@ -669,6 +686,7 @@ def main():
     else:
         main = B.csr_leg(dA, r0, r1, args.steps, args.warmup, args.stream, budget, wname, blocks=blocks)
     t_mark1 = sampler.mark()
+    sampler.pause()
 
     also = {}
     e2e = None
@@ -718,6 +736,7 @@ def main():
         del host_main
 
     # ================================================================== the other BASELINE configs
+    sampler.resume()
     if default_run and not args.no_also:
         if world == 1:
             also["uniform"] = side_config(B, eng, "uniform", args, with_cpu=not args.no_cpu, with_cusparse=not args.no_cusparse)

@@ -186,7 +186,7 @@ inline int gwin_grid(K kernel, size_t smem, long long nrows_g, int *grid)
 
 #ifdef IAS_GWIN_PROFILE
 // phase clocks of the windowed kernels since the last dump (stderr), in SM clocks summed over CTAs
-inline void gwin_profile_dump(const char *what)
+static void gwin_profile_dump(const char *what)
 {
     unsigned long long h[64];
     cudaStreamSynchronize(ctx().stream);
