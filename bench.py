@@ -455,8 +455,8 @@ class Bench:
         w = ell.max_nnz_per_row
         alg_bytes = (12.0 * w + 4) * rows * 2 + (12.0 * st["c_width"] + 4) * rows
         eng.free_ell(ell)
-        roof = {"bound": "hbm", "kernel": "ELL kernels", "achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "peak": self.peak, "unit": "GB/s",
-                "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / self.peak, "traffic": None, "peak_source": self.peak_src,
+        roof = {"bound": "hbm", "kernel": "k_ell_mul_ell", "achieved": alg_bytes / (ms_step * 1e-3) / 1e9, "peak": self.peak, "unit": "GB/s",
+                "frac": alg_bytes / (ms_step * 1e-3) / 1e9 / self.peak, "traffic": self.traffic(wname, "k_ell_mul_ell"), "peak_source": self.peak_src,
                 "algorithmic_bytes": alg_bytes, "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / self.peak}
         return {"ms_per_step": ms_step, "value": 2.0 * products / (ms_step * 1e6), "unit": "GFLOP/s", "products": products,
                 "nnz_C": st["nnz"], "c_width": st["c_width"], "trans_ms": trans_ms, "roofline": roof, "launches": launches,
@@ -496,15 +496,18 @@ class Bench:
         torch.cuda.synchronize()
         t0 = time.perf_counter()
         ev0.record(self.stream)
+        per_call = []
         for _ in range(e_steps):
+            tc = time.perf_counter()
             r, sink = call()
+            per_call.append(round((time.perf_counter() - tc) * 1e3, 2))
         ev1.record(self.stream)
         torch.cuda.synchronize()
         wall = (time.perf_counter() - t0) * 1e3
         e_ms = max(ev0.elapsed_time(ev1), wall) / e_steps
         out = {"ms_per_step": e_ms, "h2d_bytes_per_step": int(r["h2d_bytes"]), "d2h_bytes_per_step": int(r["d2h_bytes"]),
                "result_format": r["format"], "phase_ms": {k: round(float(v), 3) for k, v in r["ms"].items()},
-               "host_ms_at": r.get("host_ms_at"),
+               "host_ms_at": r.get("host_ms_at"), "per_call_ms": per_call,
                "api": "ias_spgemm_auto_host (features -> selection -> conversion -> multiply -> host result)" if api == "auto"
                       else "ias_csr_mul_csr_host (CSR_MUL_CSR on host operands)"}
         eng.lib.ias_release_host()

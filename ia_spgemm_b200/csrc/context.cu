@@ -65,6 +65,8 @@ static long long *option_slot(const char *name)
     if (!strcmp(name, "g_v2")) return &t.g_v2;
     if (!strcmp(name, "g_tbl")) return &t.g_tbl;
     if (!strcmp(name, "g_lpt")) return &t.g_lpt;
+    if (!strcmp(name, "g_scr")) return &t.g_scr;
+    if (!strcmp(name, "g2_takes_b2")) return &t.g2_takes_b2;
     return nullptr;
 }
 
@@ -106,7 +108,7 @@ int ias_init(int device)
         if (!c.ev_bin[i]) IAS_CUDA(cudaEventCreate(&c.ev_bin[i]));
     if (!c.h_scalars) IAS_CUDA(cudaMallocHost((void **)&c.h_scalars, 64 * sizeof(long long)));
     static const char *const names[] = {"global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win", "g_coop", "gwin_takes_b2",
-                                        "trust_operand_cache", "g_ldca", "g_block", "ell_onepass", "g_v2", "g_tbl", "g_lpt", "bulk_store", "dia_vec"};
+                                        "trust_operand_cache", "g_ldca", "g_block", "ell_onepass", "g_v2", "g_tbl", "g_lpt", "bulk_store", "dia_vec", "g_scr", "g2_takes_b2"};
     for (const char *n : names) {                  // IAS_OPT_GWIN_WIN=4096 etc.
         char env[64] = "IAS_OPT_";
         size_t k = strlen(env);

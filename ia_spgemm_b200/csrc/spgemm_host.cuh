@@ -89,6 +89,8 @@ struct RangeWork {
     DBuf<unsigned char> bin;       // nrows
     DBuf<unsigned long long> hist; // 16 counters
     DBuf<unsigned> gwork;          // global-row workspace slots
+    DBuf<int> gscr;                // k_num_global2: split-table scratch of the rows with more than 1024 A entries
+    size_t gscr_ints = 0;
     DBuf<int> cursor;
     int gslots = 0;
     long long products = 0;
@@ -399,7 +401,8 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
         IAS_CUDA(cudaMemsetAsync(rw.hist.p, 0, 16 * sizeof(unsigned long long), c.stream));
         // rows the windowed kernel handles in one rank window go there instead of the large CTA hash (hash insert +
         // block radix sort cost more per product than mark + rank when the whole column space is one super-window)
-        const int b2_max = use_gwin(rw) && gwin_numeric_pays(ncols_b) && c.tune.gwin_takes_b2 ? NUM_B1_NNZ : NUM_B2_NNZ;
+        const bool g2 = rw.b_canonical && c.tune.global_rows_smem != 0 && c.tune.g_v2 != 0 && c.tune.g_block != 512 && !gwin_numeric_pays(ncols_b);
+        const int b2_max = (use_gwin(rw) && gwin_numeric_pays(ncols_b) && c.tune.gwin_takes_b2) || (g2 && c.tune.g2_takes_b2) ? NUM_B1_NNZ : NUM_B2_NNZ;
         IAS_LAUNCH(k_classify_num, grid_for(n, 256), 256, 0, n, rw.ub.p + b0, rw.nnz_row.p + b0, rw.bin.p + b0, rw.hist.p, b2_max);
         IAS_TRY(read_hist(rw, NBINS + 2, h));
         for (int b = 0; b < NBINS; ++b) rw.num_hist[b] += h[b];
@@ -516,8 +519,15 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
             int tbl_cap = (int)std::min<long long>(16384, std::max<long long>(0, c.tune.g_tbl));
             size_t sm = (size_t)win * sizeof(double) + (size_t)tbl_cap * sizeof(int);
             IAS_TRY(opt_in_smem(k, sm));
-            IAS_LAUNCH(k, std::min<long long>(rw.gslots, (long long)c.sm_count), 1024, sm, glist, m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
-                       GLayout::make(ncols_b), rw.cursor.p, win, tbl_cap, ncols_b);
+            // per-CTA scratch for the split tables of rows with more than 1024 entries in A (L2 / HBM, never initialised)
+            const int grid = (int)std::min<long long>(rw.gslots, (long long)c.sm_count);
+            const int scr_cap = (int)std::min<long long>(1 << 24, std::max<long long>(16, c.tune.g_scr));
+            if (rw.gscr_ints < (size_t)grid * scr_cap) {
+                IAS_TRY(rw.gscr.alloc((size_t)grid * scr_cap));
+                rw.gscr_ints = (size_t)grid * scr_cap;
+            }
+            IAS_LAUNCH(k, grid, 1024, sm, glist, m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
+                       GLayout::make(ncols_b), rw.cursor.p, win, tbl_cap, ncols_b, rw.gscr.p, scr_cap);
         } else {
             // 160 KB tile of fp64 partial sums per SM (192 KB would leave 28 KB of L1 for the B-row stream: ncu/clock64
             // showed the mark pass 1.6x slower); with two 512-thread CTAs per SM each gets half

@@ -1452,18 +1452,19 @@ template <class AV, class BV, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
                                                        int *__restrict__ c_ci, double *__restrict__ c_v,
                                                        unsigned *__restrict__ work, GLayout L, int *__restrict__ cursor,
-                                                       int win, int tbl_cap, int ncols)
+                                                       int win, int tbl_cap, int ncols, int *__restrict__ gscr, int gscr_cap)
 {
     typedef typename AV::off_t aoff;
     typedef typename BV::off_t boff;
     constexpr int NWARPS = BLOCK / 32;
+    constexpr bool QB32 = sizeof(boff) == 4;          // B row starts fit an int (CSR); otherwise the row index is kept
     extern __shared__ __align__(16) unsigned char smem_raw[];
     double *acc = reinterpret_cast<double *>(smem_raw);                       // win entries
     unsigned *bits = reinterpret_cast<unsigned *>(smem_raw);                  // mark bitmap: 2 * win words in the same bytes
     int *tbl = reinterpret_cast<int *>(smem_raw + (size_t)win * 8);           // tbl_cap split points
     typedef cub::BlockScan<unsigned, BLOCK> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
-    __shared__ int s_row;
+    __shared__ int s_row, s_next;
     __shared__ unsigned s_carry, s_swtot;
     __shared__ unsigned s_blk[BLOCK];                                         // populations of a super-window's chunks of 128 words
     __shared__ int s_bnd[G2_MAX_BND + 1];
@@ -1494,6 +1495,64 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
         int my_len = 0;
         double my_av = 0.0;
         if (single_tile) gwin_load<true>(A, B, pa, pe, my_qb, my_len, my_av);
+        // Rows with more than BLOCK entries in A (the hubs): the entries' B rows (start, length) and their split points
+        // go to a per-CTA scratch in global memory (L2), boundary-major so that a window's tile reads them coalesced.
+        // Every boundary of every B row is searched once (the upper bound of a window is the lower bound of the next),
+        // two searches in flight per thread; a window's tile then costs four coalesced loads instead of two dependent
+        // binary searches behind an A.ci -> B.rp gather.
+        int *gx = gscr + (size_t)blockIdx.x * gscr_cap;               // n_a starts (or B row indices), then n_a lengths, then the table
+        int *glen = gx + n_a;
+        int *gt = glen + n_a;
+        const bool long_cached = !single_tile && (long long)n_a * 4 <= gscr_cap;
+        if (long_cached) {
+            for (int e = tid; e < n_a; e += BLOCK) {
+                const int j = __ldg(A.ci + pa + e);
+                gx[e] = QB32 ? (int)B.begin(j) : j;
+                glen[e] = B.len(j);
+            }
+            __syncthreads();
+        }
+        auto long_table = [&](int K, auto boundary) {                 // gt[k * n_a + e], k = 0 .. K; boundary(k) = column of boundary k
+            for (int e = tid; e < n_a; e += BLOCK) { gt[e] = 0; gt[(size_t)K * n_a + e] = __ldcg(glen + e); }
+            const int items = n_a * (K - 1);
+            for (int it = tid; it < items; it += 2 * BLOCK) {
+                const int it1 = it + BLOCK;
+                const bool two = it1 < items;
+                const int k0 = it / n_a + 1, e0 = it - (k0 - 1) * n_a;
+                const int k1 = two ? it1 / n_a + 1 : k0, e1 = two ? it1 - (k1 - 1) * n_a : e0;
+                const int x0 = __ldcg(gx + e0), x1 = __ldcg(gx + e1);
+                const boff b0 = QB32 ? (boff)x0 : B.begin(x0), b1 = QB32 ? (boff)x1 : B.begin(x1);
+                const int c0 = boundary(k0), c1 = boundary(k1);
+                int lo0 = 0, hi0 = __ldcg(glen + e0), lo1 = 0, hi1 = two ? __ldcg(glen + e1) : 0;
+                while (lo0 < hi0 || lo1 < hi1) {
+                    const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
+                    const int v0 = lo0 < hi0 ? __ldg(B.ci + b0 + m0) : 0;
+                    const int v1 = lo1 < hi1 ? __ldg(B.ci + b1 + m1) : 0;
+                    if (lo0 < hi0) { if (v0 < c0) lo0 = m0 + 1; else hi0 = m0; }
+                    if (lo1 < hi1) { if (v1 < c1) lo1 = m1 + 1; else hi1 = m1; }
+                }
+                gt[(size_t)k0 * n_a + e0] = lo0;
+                if (two) gt[(size_t)k1 * n_a + e1] = lo1;
+            }
+            __syncthreads();
+        };
+        // one tile of a long row restricted to window k of the current table: returns the tile's product count
+        auto long_tile = [&](aoff base, int k, bool need_values) {
+            const int e = (int)(base - pa) + tid;
+            boff qb = 0;
+            int len = 0;
+            double av = 0.0;
+            if (e < n_a) {
+                const int o0 = __ldcg(gt + (size_t)k * n_a + e), o1 = __ldcg(gt + (size_t)(k + 1) * n_a + e);
+                const int x = __ldcg(gx + e);
+                qb = (QB32 ? (boff)x : B.begin(x)) + o0;
+                len = o1 - o0;
+                if (need_values) av = __ldg(A.v + pa + e);
+            }
+            return need_values ? gwin_scan<true, BLOCK>(tile, qb, len, av) : gwin_scan<false, BLOCK>(tile, qb, len, 0.0);
+        };
+        const bool use_gmtbl = long_cached && nsw > 1 && (long long)n_a * (nsw + 3) <= gscr_cap;
+        if (use_gmtbl) long_table(nsw, [&](int k) { return (int)(k * span); });
         // split table of the mark pass: where every B row crosses the super-window boundaries
         const int mstride = (nsw + 1) | 1;
         const bool use_mtbl = single_tile && nsw > 1 && (long long)n_a * mstride <= tbl_cap;
@@ -1548,7 +1607,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
                 __syncthreads();
             } else {
                 for (aoff base = pa; base < pe; base += BLOCK) {
-                    const int total = gwin_build<false, BLOCK>(A, B, base, pe, tile, c_lo, c_hi);
+                    const int total = use_gmtbl ? long_tile(base, k, false) : gwin_build<false, BLOCK>(A, B, base, pe, tile, c_lo, c_hi);
                     if (total) {
                         any = true;
                         gwin_run<false, BLOCK>(tile, total, [&](const boff (&q)[PB], const double (&pv)[PB], unsigned valid) { mark(q, pv, valid, c_lo); });
@@ -1577,12 +1636,18 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
                 unsigned excl, tot;
                 Scan(scan_tmp).ExclusiveSum(v0, excl, tot);
                 if (tid < nchunk) s_blk[tid] = excl;
-                if (tid == 0) s_swtot = tot;
+                if (tid == 0) { s_swtot = tot; s_next = 0; }
             }
             __syncthreads();
-            // cells + sorted columns of the super-window; the bitmap is left clean
+            // cells + sorted columns of the super-window; the bitmap is left clean.  Chunks are drawn from a counter:
+            // a chunk of hub columns (4096 entries) takes twenty times longer than a sparse one, and with a fixed
+            // assignment the barrier behind this loop was the largest single stall of the kernel (ncu: 15 % of samples).
             const unsigned base_rank = s_carry;
-            for (int c = wid; c < nchunk; c += NWARPS) {
+            while (true) {
+                int c = 0;
+                if (lane == 0) c = atomicAdd(&s_next, 1);
+                c = __shfl_sync(0xffffffffu, c, 0);
+                if (c >= nchunk) break;
                 const uint4 w4 = bits4[c * 32 + lane];
                 const unsigned wd[4] = {w4.x, w4.y, w4.z, w4.w};
                 const unsigned nz = (wd[0] ? 1u : 0u) | (wd[1] ? 2u : 0u) | (wd[2] ? 4u : 0u) | (wd[3] ? 8u : 0u);
@@ -1646,6 +1711,8 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
             if (tid < n_a) { tbl[tid * astride] = 0; tbl[tid * astride + W] = my_len; }
         }
         __syncthreads();
+        const bool use_gatbl = long_cached && W > 1 && bnd_in_smem && (long long)n_a * (W + 3) <= gscr_cap;
+        if (use_gatbl) long_table(W, [&](int k) { return s_bnd[k]; });
         GP_ADD(38);
         // 3. one window of `win` ranks at a time: accumulate in the shared-memory tile, then write it out
         for (int w = 0; w < W; ++w) {
@@ -1656,9 +1723,8 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
                 if (bnd_in_smem) { c_lo = w == 0 ? 0 : s_bnd[w]; c_hi = w + 1 < W ? s_bnd[w + 1] : 0x7fffffff; }
                 else { c_lo = w == 0 ? 0 : __ldcg(c_ci + gs + wbase); c_hi = w + 1 < W ? __ldcg(c_ci + gs + wbase + win) : 0x7fffffff; }
             }
-            for (int t = tid; t < wn; t += BLOCK) acc[t] = 0.0;
-            __syncthreads();
-            GP_ADD(37);
+            // (the tile is all zero here: the emit pass left the bitmap clean -- the same bytes -- and every write-out
+            //  below zeroes what it has read)
             GP_CNT(42, 1);
             auto add = [&](const boff (&q)[PB], const double (&av)[PB], unsigned valid) {
                 int k[PB];
@@ -1693,7 +1759,8 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
                 if (total) gwin_run<true, BLOCK>(tile, total, add);
             } else {
                 for (aoff base = pa; base < pe; base += BLOCK) {
-                    const int total = gwin_build<true, BLOCK>(A, B, base, pe, tile, W > 1 ? c_lo : 0, W > 1 ? c_hi : 0x7fffffff);
+                    const int total = use_gatbl ? long_tile(base, w, true)
+                                                : gwin_build<true, BLOCK>(A, B, base, pe, tile, W > 1 ? c_lo : 0, W > 1 ? c_hi : 0x7fffffff);
                     GP_ADD(38);
                     if (total) gwin_run<true, BLOCK>(tile, total, add);
                     __syncthreads();
@@ -1701,17 +1768,12 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
             }
             __syncthreads();
             GP_ADD(39);
-            for (int t = tid; t < wn; t += BLOCK) c_v[gs + wbase + t] = acc[t];
+            for (int t = tid; t < wn; t += BLOCK) { c_v[gs + wbase + t] = acc[t]; acc[t] = 0.0; }
             __syncthreads();
             GP_ADD(40);
         }
-        // 4. leave the slot and the bitmap clean for the next row (the tile held partial sums: the bitmap words it
-        //    covers are zeroed again)
+        // 4. leave the slot clean for the next row (the tile, hence the bitmap, already is)
         g_clear<BLOCK>(wp, summary, wsum, L);
-        {
-            const int used = min(swords, 2 * min(win, n));             // words overwritten by acc[0, min(win, n))
-            for (int w = tid; w < used; w += BLOCK) bits[w] = 0;
-        }
         __syncthreads();
         GP_ADD(41);
     }

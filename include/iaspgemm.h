@@ -150,7 +150,8 @@ long long ias_kernel_launches(void);            /* engine kernels launched since
  * kernel only up to this many column super-windows per row, 0 = no limit), "g_win" (accumulate window of the L2 kernel), "g_coop", "gwin_takes_b2" (0/1 switches kept for A/B runs),
  * "trust_operand_cache" (see ias_forget_operand), "ell_onepass" (1 = one-pass ELL x ELL kernel where a row's products fit a
  * warp's register sort, 0 = always the pipeline), "g_block" (1024 / 512 threads per CTA of the L2 kernel), "g_ldca", "g_v2" (1 = second generation of the L2 kernel: rank + emit
- * from shared memory, split tables), "g_tbl" (its split-table capacity), "g_lpt" (1 = global rows in order of decreasing work), "bulk_store" (1 = cp.async.bulk copy-out of staged tiles),
+ * from shared memory, split tables), "g_tbl" (its split-table capacity), "g_lpt" (1 = global rows in order of decreasing work), "g_scr" (per-CTA global scratch, in ints, for the split
+ * tables of rows with more than 1024 A entries), "g2_takes_b2" (rows of the large CTA hash go to that kernel), "bulk_store" (1 = cp.async.bulk copy-out of staged tiles),
  * "dia_vec" (1 = 128-bit DIA kernel).  Also read from
  * IAS_OPT_<NAME> in the environment by ias_init.  Results do not depend on any of them. */
 int ias_set_option(const char *name, long long value);

@@ -362,7 +362,7 @@ def test_wide_column_space_uses_64bit_sort_keys(eng, oracle):
 
 # ---------------------------------------------------------------- global rows: windowed shared-memory kernels
 _GWIN_OPTS = ("global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win", "g_coop", "gwin_takes_b2",
-              "g_v2", "g_tbl", "g_lpt", "g_block")
+              "g_v2", "g_tbl", "g_lpt", "g_block", "g_scr")
 
 
 @pytest.fixture
@@ -429,6 +429,21 @@ def test_global_rows_second_generation(eng, oracle, options, kind, g_win, g_tbl,
     options("g_win", g_win)
     options("g_tbl", g_tbl)
     options("g_lpt", g_lpt)
+    got, st = _check(eng, oracle, A, B, mag=False)
+    assert st["num_bin_rows"][5] > 0
+
+
+@pytest.mark.parametrize("g_win,g_scr", [(64, 8 << 20), (256, 8 << 20), (64, 0), (64, 40000), (16384, 8 << 20)])
+def test_global_rows_long_rows_use_global_split_tables(eng, oracle, options, g_win, g_scr):
+    """Rows with more than 1024 entries in A: their split tables live in a per-CTA global scratch (g_scr ints); too
+    small a scratch, or none, falls back to per-window searches."""
+    A, B = _global_operands("long_a_rows")
+    options("global_rows_smem", 1)
+    options("gwin_swords", 32)
+    options("gwin_max_sw", 1)
+    options("g_v2", 1)
+    options("g_win", g_win)
+    options("g_scr", g_scr)
     got, st = _check(eng, oracle, A, B, mag=False)
     assert st["num_bin_rows"][5] > 0
 
