@@ -356,11 +356,14 @@ class Bench:
             dia = None
         return {1: "csr", 2: "dia", 3: "ell"}[cls], dia, f
 
-    def csr_leg(self, dA, r0, r1, steps, warmup, stream_mode, budget, wname, blocks=None):
-        """CSR hot path on rows [r0, r1) (or on a list of row blocks): ms/step, totals, bins, step and kernel roofline."""
+    def csr_leg(self, dA, r0, r1, steps, warmup, stream_mode, budget, wname, blocks=None, rowlist=None):
+        """CSR hot path on rows [r0, r1) (or on a list of row blocks, or on a device list of rows): ms/step, totals, bins,
+        step and kernel roofline."""
         eng = self.eng
 
         def one(b0, b1):
+            if rowlist is not None:
+                return eng.csr_mul_csr_rowlist_stream(dA, dA, rowlist.data_ptr(), int(rowlist.numel()), budget_bytes=budget)
             if stream_mode:
                 return eng.csr_mul_csr_stream(dA, dA, rows=(b0, b1), budget_bytes=budget)
             return eng.CSR_MUL_CSR_DEV(dA, dA, rows=(b0, b1), download=False)[1]
@@ -381,12 +384,15 @@ class Bench:
 
         ms_step, stats, launches, n_warm = self.timed(step, steps, warmup)
         st = stats[-1]
-        my_rows = sum(b1 - b0 for b0, b1 in blocks)
+        my_rows = sum(b1 - b0 for b0, b1 in blocks) if rowlist is None else int(rowlist.numel())
         products, nnz_c, launches_all = self.all_sum(st["products"], st["nnz"], launches)
         # bytes_alg(CSR) = bytes(A block) + bytes of the B rows it references at least once + bytes(C block), SURVEY 8(d);
         # this rank's rows (N=1: the whole job)
         a_nnz, touched = 0, 0
-        for b0, b1 in blocks:
+        if rowlist is not None:               # a cyclic share of a skewed operand: 1/N of A's entries, (nearly) every B row touched
+            a_nnz = dA.dev.nnz // max(self.world, 1)
+            touched = bytes_csr(dA.dev.row, dA.dev.nnz)
+        for b0, b1 in (blocks if rowlist is None else []):
             if b1 <= b0:
                 continue
             a_rp = np.zeros(2, dtype=np.int32)
@@ -482,15 +488,27 @@ class Bench:
         e_steps = max(2, min(steps, 5))
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
+        # the C-ABI calls themselves (ctypes, no convenience wrapper): host structs are built once, like a C caller's
+        from ia_spgemm_b200.engine import AutoResult, SpgemmStats
+        h = eng.host_csr(*hA)
+        lib = eng.lib
+
         def call():
             if api == "auto":
-                r = eng.spgemm_auto(hA, hA)
-                sink = float(r["values"].reshape(-1)[-1]) if r["nnz"] else 0.0          # read the result on the host
-                return r, sink
-            (c_rp, c_ci, c_v), est, h2d, d2h = eng.CSR_MUL_CSR(hA, hA)
-            sink = float(c_v[-1]) if len(c_v) else 0.0
-            return {"format": "csr", "nnz": est["nnz"], "products": est["products"], "ms": {"h2d": h2d, "d2h": d2h},
-                    "h2d_bytes": bytes_csr(hA[0], len(hA[3])), "d2h_bytes": bytes_csr(hA[0], est["nnz"], 8)}, sink
+                r = AutoResult()
+                eng._ck(lib.ias_spgemm_auto_host(C.byref(h), C.byref(h), C.c_double(20.0), None, C.byref(r)))
+                cells = r.nnz if r.format != 3 else r.row * r.max_nnz_per_row
+                sink = float(r.values[cells - 1]) if cells else 0.0                       # read the result on the host
+                return {"format": {1: "csr", 2: "dia", 3: "ell"}[r.format], "nnz": r.nnz, "h2d_bytes": r.h2d_bytes, "d2h_bytes": r.d2h_bytes,
+                        "ms": {k: getattr(r, "ms_" + k) for k in ("h2d", "select", "convert", "multiply", "d2h", "wall")},
+                        "host_ms_at": [round(x, 3) for x in r.ms_host]}, sink
+            rp, ci, v = C.POINTER(C.c_longlong)(), C.POINTER(C.c_int)(), C.POINTER(C.c_double)()
+            nnz, st, h2d, d2h = C.c_longlong(), SpgemmStats(), C.c_double(), C.c_double()
+            eng._ck(lib.ias_csr_mul_csr_host(C.byref(h), C.byref(h), C.byref(rp), C.byref(ci), C.byref(v), C.byref(nnz), C.byref(st),
+                                             C.byref(h2d), C.byref(d2h)))
+            sink = float(v[nnz.value - 1]) if nnz.value else 0.0
+            return {"format": "csr", "nnz": nnz.value, "products": st.products, "ms": {"h2d": h2d.value, "d2h": d2h.value},
+                    "h2d_bytes": bytes_csr(hA[0], len(hA[3])), "d2h_bytes": bytes_csr(hA[0], nnz.value, 8)}, sink
 
         call()                                      # warm-up: sizes the pinned result arena
         torch.cuda.synchronize()
@@ -552,12 +570,6 @@ class Bench:
             return {"error": ("%s: %s" % (type(ex).__name__, ex))[:300]}
 
 
-def deal_blocks(bounds, rank, world):
-    """Cyclic dealing of contiguous row blocks: rank r takes blocks r, r + world, ...  With many more blocks than
-    ranks every rank gets hub rows and tail rows alike (un-permuted R-MAT keeps its heaviest rows at the low indices)."""
-    return [(bounds[b], bounds[b + 1]) for b in range(rank, len(bounds) - 1, world)]
-
-
 # ---------------------------------------------------------------------------------------------- main
 def main():
     ap = argparse.ArgumentParser()
@@ -577,7 +589,6 @@ def main():
     ap.add_argument("--no-also", action="store_true", help="main line only")
     ap.add_argument("--no-cusparse", action="store_true")
     ap.add_argument("--format", default="auto", choices=["auto", "csr", "dia", "ell"], help="kernel family for the main step")
-    ap.add_argument("--blocks-per-rank", type=int, default=32, help="strong scaling: row blocks dealt cyclically to each rank")
     args = ap.parse_args()
     default_run = args.workload is None
     if default_run:
@@ -665,11 +676,12 @@ def main():
     eng.sync()
     select_ms = (time.perf_counter() - t_sel) * 1e3
     strong = kind != "poisson" and world > 1
+    rowlist = None
     if world > 1:
         if strong:
-            bounds_all = eng.partition_rows(dA, dA, world * args.blocks_per_rank)
-            blocks = deal_blocks(bounds_all, rank, world)
-            r0, r1 = blocks[0][0], blocks[-1][1]
+            # rank r takes rows r, r + N, ...: one pass of the pipeline per rank, hubs and tail rows on every rank
+            rowlist = torch.arange(rank, rows, world, dtype=torch.int32, device="cuda")
+            r0, r1, blocks = 0, rows, None
         else:
             bounds = eng.partition_rows(dA, dA, world)
             r0, r1 = bounds[rank], bounds[rank + 1]
@@ -687,7 +699,7 @@ def main():
         if "error" in main:
             raise SystemExit(main["error"])
     else:
-        main = B.csr_leg(dA, r0, r1, args.steps, args.warmup, args.stream, budget, wname, blocks=blocks)
+        main = B.csr_leg(dA, r0, r1, args.steps, args.warmup, args.stream, budget, wname, blocks=blocks, rowlist=rowlist)
     t_mark1 = sampler.mark()
     sampler.pause()
 
@@ -764,7 +776,7 @@ def main():
                            "c_diagonals": main.get("c_diagonals"),
                            "l2": "inputs_exceed_l2 (A %.2f GB per step vs 126 MB L2)" % (bytes_csr(rows, nnz_a) / 1e9),
                            "parallelism": ("row blocks x%d (%s), B broadcast once over NCCL (%.1f ms, outside the timed region)"
-                                           % (world, "%d blocks per rank dealt cyclically" % args.blocks_per_rank if strong else "contiguous, balanced by products", t_bcast))
+                                           % (world, "rows r, r+N, ... to rank r" if strong else "contiguous, balanced by products", t_bcast))
                                           if world > 1 else "single GPU",
                            "tolerance": "structure bit-exact; values within 1e-12 x sum|a*b| of the entry (= 1e-12 x |c| on zero-free, cancellation-free operands)"},
                 "roofline": main["roofline"], "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(main["launches"]), "clocks": clocks}
@@ -821,27 +833,34 @@ def side_config(B, eng, kind, args, with_cpu, with_cusparse):
 
 
 def strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world):
-    """R-MAT scale 22 (fixed problem) over the N GPUs: B broadcast once, row blocks balanced by products and dealt
-    cyclically, every rank streams its blocks.  Rank 0 then times the whole problem alone: the 1-GPU figure of the
+    """R-MAT scale 22 (fixed problem) over the N GPUs: B broadcast once; rank r multiplies the rows r, r + N, r + 2N, ... of A
+    in ONE pass of the streaming pipeline (ias_csr_mul_csr_rowlist_stream): every rank gets its share of hub rows and of
+    tail rows, and no launch tail is paid per block.  Rank 0 then times the whole problem alone: the 1-GPU figure of the
     same box and run."""
     out = {}
     try:
         wname = workload_name("rmat", scale=22)
         dA, t_bcast = shared_operand("rmat", scale=22)
         rows = dA.dev.row
-        bounds = eng.partition_rows(dA, dA, world * args.blocks_per_rank)
-        blocks = deal_blocks(bounds, rank, world)
-        leg = B.csr_leg(dA, blocks[0][0], blocks[-1][1], 2, 1, True, 0, wname, blocks=blocks)
-        my = torch.zeros(world, dtype=torch.float64, device="cuda")
-        # per-rank device time of the last step (analysis + symbolic + numeric of its blocks)
-        my[rank] = sum(leg["detail"]["phase_ms"].values())
-        dist.all_reduce(my, op=dist.ReduceOp.SUM)
-        out = {"workload": wname, "scaling": "strong", "n_gpus": world, "ms_per_step": leg["ms_per_step"], "value": leg["value"],
-               "unit": "GFLOP/s", "products": leg["products"], "nnz_C": leg["nnz_C"], "per_rank_busy_ms": [round(float(x), 1) for x in my.tolist()],
-               "broadcast_ms": t_bcast, "blocks_per_rank": args.blocks_per_rank,
-               "e2e": {"ms_per_step": leg["ms_per_step"] + t_bcast, "value": 2.0 * leg["products"] / ((leg["ms_per_step"] + t_bcast) * 1e6),
-                       "unit": "GFLOP/s", "note": "operand resident on rank 0 -> NCCL broadcast of B (3 arrays) + multiply; C is reduced on device "
-                                                   "(nnz, checksum, structure hash), a few scalars come back"}}
+        my_rows = torch.arange(rank, rows, world, dtype=torch.int32, device="cuda")
+        n_mine = int(my_rows.numel())
+
+        def step():
+            return eng.csr_mul_csr_rowlist_stream(dA, dA, my_rows.data_ptr(), n_mine)
+
+        ms_step, stats, launches, n_warm = B.timed(step, 2, 1)
+        st = stats[-1]
+        products, nnz_c = B.all_sum(st["products"], st["nnz"])
+        busy = torch.zeros(world, dtype=torch.float64, device="cuda")
+        busy[rank] = st["ms_total"]                      # this rank's device time of the last step
+        dist.all_reduce(busy, op=dist.ReduceOp.SUM)
+        out = {"workload": wname, "scaling": "strong", "n_gpus": world, "ms_per_step": ms_step, "value": 2.0 * products / (ms_step * 1e6),
+               "unit": "GFLOP/s", "products": products, "nnz_C": nnz_c, "per_rank_busy_ms": [round(float(x), 1) for x in busy.tolist()],
+               "broadcast_ms": t_bcast, "partition": "rows r, r+N, r+2N, ... to rank r (ias_csr_mul_csr_rowlist_stream)",
+               "streaming_batches_rank0": st.get("batches"),
+               "e2e": {"ms_per_step": ms_step + t_bcast, "value": 2.0 * products / ((ms_step + t_bcast) * 1e6), "unit": "GFLOP/s",
+                       "note": "operand resident on rank 0 -> NCCL broadcast of B (3 arrays) + multiply; C is reduced on device "
+                               "(nnz, checksum, structure hash), a few scalars come back"}}
         dist.barrier()
         if rank == 0:
             world_saved, B.world = B.world, 1
@@ -850,10 +869,10 @@ def strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world):
             finally:
                 B.world = world_saved
             out["one_gpu_same_run"] = {"ms_per_step": one["ms_per_step"], "value": one["value"]}
-            out["speedup_vs_one_gpu"] = one["ms_per_step"] / leg["ms_per_step"]
+            out["speedup_vs_one_gpu"] = one["ms_per_step"] / ms_step
             out["efficiency"] = out["speedup_vs_one_gpu"] / world
-            busy = out["per_rank_busy_ms"]
-            out["limiter"] = "imbalance: slowest rank %.0f ms vs mean %.0f ms" % (max(busy), float(np.mean(busy)))
+            b = out["per_rank_busy_ms"]
+            out["limiter"] = "slowest rank %.0f ms vs mean %.0f ms of device time; step %.0f ms" % (max(b), float(np.mean(b)), ms_step)
         dist.barrier()
         dA.close()
     except Exception as ex:

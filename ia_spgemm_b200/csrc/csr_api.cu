@@ -39,51 +39,11 @@ __global__ void k_narrow_rp(int n, const long long *in, int *out)
 
 }  // namespace
 
-extern "C" {
-
-int ias_csr_mul_csr_rows_dev64(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, IasCsr64Dev *C,
-                               IasSpgemmStats *st)
+// rows [r0, r1) of the view `av` (a CsrView of A, or a CsrRowsView = an arbitrary list of A's rows) times B, streamed
+template <class AV>
+static int stream_impl(const AV &av, double avg, bool same, const IasCsrMatrixDev *B, int r0, int r1, size_t budget_bytes,
+                       int *row_nnz_dev, ias_stream_consumer consumer, void *user, IasSpgemmStats *st)
 {
-    return mul_rows(A, B, r0, r1, C, st);
-}
-
-int ias_csr_mul_csr_dev64(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, IasCsr64Dev *C, IasSpgemmStats *st)
-{
-    if (!A) return fail(IAS_E_ARG, "NULL operand");
-    return mul_rows(A, B, 0, A->row, C, st);
-}
-
-int ias_csr_mul_csr_dev(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, IasCsrMatrixDev *C, double *elapsed_ms)
-{
-    if (!A || !C) return fail(IAS_E_ARG, "NULL operand");
-    IasCsr64Dev c64;
-    IasSpgemmStats st;
-    IAS_TRY(mul_rows(A, B, 0, A->row, &c64, &st));
-    if (c64.nnz >= 0x7fffffffLL) {
-        ias_free_csr64_dev(&c64);
-        return fail(IAS_E_OVERFLOW, "nnz(C) = %lld does not fit the int32 CsrMatrixDev layout; use ias_csr_mul_csr_dev64", c64.nnz);
-    }
-    C->choice = true; C->row = c64.row; C->col = c64.col; C->nnz = (int)c64.nnz;
-    IAS_TRY(dalloc(&C->row_ind_dev, (size_t)c64.row + 1));
-    IAS_LAUNCH(k_narrow_rp, grid_for(c64.row + 1, 256), 256, 0, c64.row + 1, c64.row_ptr_dev, C->row_ind_dev);
-    C->col_ind_dev = c64.col_ind_dev; C->values_dev = c64.values_dev;
-    dfree(c64.row_ptr_dev);
-    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
-    if (elapsed_ms) *elapsed_ms = st.ms_total;
-    return IAS_OK;
-}
-
-int ias_csr_mul_csr_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, size_t budget_bytes,
-                           int *row_nnz_dev, IasSpgemmStats *st)
-{
-    return ias_csr_mul_csr_stream_cb(A, B, r0, r1, budget_bytes, row_nnz_dev, nullptr, nullptr, st);
-}
-
-int ias_csr_mul_csr_stream_cb(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, size_t budget_bytes,
-                              int *row_nnz_dev, ias_stream_consumer consumer, void *user, IasSpgemmStats *st)
-{
-    IAS_TRY(ensure_init());
-    IAS_TRY(check_operands(A, B, r0, r1));
     Ctx &c = ctx();
     long long l0 = c.launches;
     IasSpgemmStats local;
@@ -93,9 +53,7 @@ int ias_csr_mul_csr_stream_cb(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B
     IAS_CUDA(cudaEventRecord(c.ev[0], c.stream));
     IAS_CUDA(cudaEventRecord(c.ev[1], c.stream));
     RangeWork rw;
-    CsrView av = view(A), bv = view(B);
-    double avg = A->row ? (double)A->nnz / A->row : 0.0;
-    bool same = A->row_ind_dev == B->row_ind_dev && A->col_ind_dev == B->col_ind_dev;
+    CsrView bv = view(B);
     IAS_TRY(symbolic_range(av, bv, r0, r1, B->col, avg, rw, &local, same, B->row, B->nnz));
     IAS_CUDA(cudaEventRecord(c.ev[2], c.stream));
     DBuf<long long> rp;
@@ -180,6 +138,92 @@ int ias_csr_mul_csr_stream_cb(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B
     local.kernel_launches = (int)(c.launches - l0);
     if (st) *st = local;
     return IAS_OK;
+}
+
+
+extern "C" {
+
+int ias_csr_mul_csr_rows_dev64(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, IasCsr64Dev *C,
+                               IasSpgemmStats *st)
+{
+    return mul_rows(A, B, r0, r1, C, st);
+}
+
+int ias_csr_mul_csr_dev64(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, IasCsr64Dev *C, IasSpgemmStats *st)
+{
+    if (!A) return fail(IAS_E_ARG, "NULL operand");
+    return mul_rows(A, B, 0, A->row, C, st);
+}
+
+int ias_csr_mul_csr_dev(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, IasCsrMatrixDev *C, double *elapsed_ms)
+{
+    if (!A || !C) return fail(IAS_E_ARG, "NULL operand");
+    IasCsr64Dev c64;
+    IasSpgemmStats st;
+    IAS_TRY(mul_rows(A, B, 0, A->row, &c64, &st));
+    if (c64.nnz >= 0x7fffffffLL) {
+        ias_free_csr64_dev(&c64);
+        return fail(IAS_E_OVERFLOW, "nnz(C) = %lld does not fit the int32 CsrMatrixDev layout; use ias_csr_mul_csr_dev64", c64.nnz);
+    }
+    C->choice = true; C->row = c64.row; C->col = c64.col; C->nnz = (int)c64.nnz;
+    IAS_TRY(dalloc(&C->row_ind_dev, (size_t)c64.row + 1));
+    IAS_LAUNCH(k_narrow_rp, grid_for(c64.row + 1, 256), 256, 0, c64.row + 1, c64.row_ptr_dev, C->row_ind_dev);
+    C->col_ind_dev = c64.col_ind_dev; C->values_dev = c64.values_dev;
+    dfree(c64.row_ptr_dev);
+    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
+    if (elapsed_ms) *elapsed_ms = st.ms_total;
+    return IAS_OK;
+}
+
+int ias_csr_mul_csr_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, size_t budget_bytes,
+                           int *row_nnz_dev, IasSpgemmStats *st)
+{
+    return ias_csr_mul_csr_stream_cb(A, B, r0, r1, budget_bytes, row_nnz_dev, nullptr, nullptr, st);
+}
+
+int ias_csr_mul_csr_stream_cb(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int r0, int r1, size_t budget_bytes,
+                              int *row_nnz_dev, ias_stream_consumer consumer, void *user, IasSpgemmStats *st)
+{
+    IAS_TRY(ensure_init());
+    IAS_TRY(check_operands(A, B, r0, r1));
+    double avg = A->row ? (double)A->nnz / A->row : 0.0;
+    bool same = A->row_ind_dev == B->row_ind_dev && A->col_ind_dev == B->col_ind_dev;
+    return stream_impl(view(A), avg, same, B, r0, r1, budget_bytes, row_nnz_dev, consumer, user, st);
+}
+
+namespace {
+__global__ void __launch_bounds__(256) k_gather_rows(int n, int a_rows, const int *__restrict__ rows, const int *__restrict__ rp,
+                                                     int *__restrict__ rb, int *__restrict__ re, int *__restrict__ bad)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n) return;
+    int i = rows[t];
+    if (i < 0 || i >= a_rows) { *bad = 1; rb[t] = 0; re[t] = 0; return; }
+    rb[t] = rp[i]; re[t] = rp[i + 1];
+}
+}  // namespace
+
+int ias_csr_mul_csr_rowlist_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, const int *rows_dev, int nrows,
+                                   size_t budget_bytes, int *row_nnz_dev, ias_stream_consumer consumer, void *user,
+                                   IasSpgemmStats *st)
+{
+    IAS_TRY(ensure_init());
+    IAS_TRY(check_operands(A, B, 0, A ? A->row : 0));
+    if (nrows < 0 || (nrows > 0 && !rows_dev)) return fail(IAS_E_ARG, "bad row list");
+    Ctx &c = ctx();
+    DBuf<int> rb, re, bad;
+    IAS_TRY(rb.alloc((size_t)std::max(nrows, 1)));
+    IAS_TRY(re.alloc((size_t)std::max(nrows, 1)));
+    IAS_TRY(bad.alloc(1));
+    IAS_CUDA(cudaMemsetAsync(bad.p, 0, sizeof(int), c.stream));
+    if (nrows) IAS_LAUNCH(k_gather_rows, grid_for(nrows, 256), 256, 0, nrows, A->row, rows_dev, A->row_ind_dev, rb.p, re.p, bad.p);
+    int h_bad = 0;
+    IAS_CUDA(cudaMemcpyAsync(&h_bad, bad.p, sizeof(int), cudaMemcpyDeviceToHost, c.stream));
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    if (h_bad) return fail(IAS_E_ARG, "row list names a row outside A (%d rows)", A->row);
+    CsrRowsView av{rb.p, re.p, A->col_ind_dev, A->values_dev};
+    double avg = A->row ? (double)A->nnz / A->row : 0.0;
+    return stream_impl(av, avg, false, B, 0, nrows, budget_bytes, row_nnz_dev, consumer, user, st);
 }
 
 int ias_structure_hash(const IasCsr64Dev *C, int row_base, unsigned long long *hash)

@@ -76,6 +76,14 @@ struct CsrView {                       // CsrMatrixDev, GPU/detail/format.h:59-6
     __device__ __forceinline__ int len(int i) const { return __ldg(rp + i + 1) - __ldg(rp + i); }
     const void *rp_base() const { return rp; }
 };
+struct CsrRowsView {                   // an arbitrary list of rows of a CSR matrix: row li of the view = [rb[li], re[li]) in ci / v
+    const int *rb; const int *re; const int *ci; const double *v;
+    typedef int off_t;
+    __device__ __forceinline__ off_t begin(int i) const { return __ldg(rb + i); }
+    __device__ __forceinline__ off_t end(int i) const { return __ldg(re + i); }
+    __device__ __forceinline__ int len(int i) const { return __ldg(re + i) - __ldg(rb + i); }
+    const void *rp_base() const { return rb; }
+};
 struct Csr64View {                     // CSR with 64-bit row offsets (IasCooDev::row_offset_dev)
     const long long *rp; const int *ci; const double *v;
     typedef long long off_t;

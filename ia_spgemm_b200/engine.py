@@ -116,7 +116,7 @@ ABI_SYMBOLS = [
     "ias_upload_csr", "ias_free_csr_dev", "ias_free_csr64_dev", "ias_download_csr64", "ias_download_csr",
     "ias_csr_is_canonical", "ias_copy", "ias_forget_operand",
     "ias_csr_mul_csr_dev64", "ias_csr_mul_csr_dev", "ias_csr_mul_csr_rows_dev64", "ias_csr_mul_csr_stream",
-    "ias_csr_mul_csr_stream_cb",
+    "ias_csr_mul_csr_stream_cb", "ias_csr_mul_csr_rowlist_stream",
     "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_touched_b_bytes", "ias_partition_rows", "ias_checksum",
     "ias_structure_hash",
     "ias_csr_to_dia", "ias_dia_mul_dia_dev", "ias_dia_mul_dia_rows_dev", "ias_download_dia", "ias_free_dia_dev", "ias_dia_relayout",
@@ -217,6 +217,8 @@ def load_library():
         "ias_csr_mul_csr_stream_cb": [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_size_t, C.c_void_p, STREAM_CONSUMER, C.c_void_p,
                                       C.c_void_p],
         "ias_dia_relayout": [C.c_void_p, C.c_int, C.c_void_p],
+        "ias_csr_mul_csr_rowlist_stream": [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p,
+                                           C.c_void_p],
         "ias_select_format": [C.c_void_p, C.c_int, C.c_int],
         "ias_spgemm_auto_host": [C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p],
         "ias_getinfo3": [C.c_int, C.c_longlong, C.c_int, _D],
@@ -493,6 +495,43 @@ class Engine:
         d = st.as_dict()
         if want_row_nnz:
             d["row_nnz"] = row_nnz[: r1 - r0].cpu().numpy()
+        return d
+
+    def csr_mul_csr_rowlist_stream(self, A, B, rows_dev_ptr, nrows, budget_bytes=0, want_row_nnz=False, consumer=None):
+        """Rows rows_dev[0..nrows) of A*B, streamed (ias_csr_mul_csr_rowlist_stream).  rows_dev_ptr: device pointer to int32
+        row indices (e.g. a torch tensor's data_ptr()).  consumer(batch_dict) as in csr_mul_csr_stream; rows are in list order."""
+        st = SpgemmStats()
+        row_nnz, ptr = None, None
+        if want_row_nnz:
+            import torch
+            row_nnz = torch.empty(max(nrows, 1), dtype=torch.int32, device="cuda")
+            ptr = row_nnz.data_ptr()
+        cb = None
+        if consumer is not None:
+            def _cb(bp, _user):
+                b = bp.contents
+                n = b.row_end - b.row_begin
+                rp = np.empty(n + 1, np.int64)
+                ci = np.empty(b.batch_nnz, np.int32)
+                v = np.empty(b.batch_nnz, np.float64)
+                self.copy(rp.ctypes.data, b.row_ptr_dev, 8 * (n + 1), 1)
+                if b.batch_nnz:
+                    self.copy(ci.ctypes.data, b.col_ind_dev, 4 * b.batch_nnz, 1)
+                    self.copy(v.ctypes.data, b.values_dev, 8 * b.batch_nnz, 1)
+                try:
+                    rc = consumer({"row_begin": b.row_begin, "row_end": b.row_end, "nnz_total": b.nnz_total,
+                                   "row_ptr": rp - b.entry_base, "col_ind": ci, "values": v})
+                except Exception:
+                    import traceback
+                    traceback.print_exc()
+                    return 99
+                return int(rc or 0)
+            cb = STREAM_CONSUMER(_cb)
+        self._ck(self.lib.ias_csr_mul_csr_rowlist_stream(C.byref(A.dev), C.byref(B.dev), C.c_void_p(rows_dev_ptr), nrows, budget_bytes, ptr,
+                                                         cb if cb is not None else C.cast(None, STREAM_CONSUMER), None, C.byref(st)))
+        d = st.as_dict()
+        if want_row_nnz:
+            d["row_nnz"] = row_nnz[:nrows].cpu().numpy()
         return d
 
     def GetFlop(self, A, B):

@@ -219,6 +219,14 @@ typedef int (*ias_stream_consumer)(const IasStreamBatch *batch, void *user);
 int ias_csr_mul_csr_stream_cb(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B,
                               int row_begin, int row_end, size_t budget_bytes, int *row_nnz_dev,
                               ias_stream_consumer consumer, void *user, IasSpgemmStats *stats);
+/* The same for an arbitrary list of rows of A (device array of `nrows` row indices, any order, duplicates allowed): row k
+ * of the streamed result is row rows_dev[k] of A*B.  This is the multi-GPU entry for skewed operands: rank r takes the
+ * rows r, r + N, r + 2N, ... so that every rank gets its share of hub rows and of tail rows in ONE pass of the pipeline
+ * (contiguous blocks concentrate the hubs; many small blocks pay a launch tail each).  Batch row numbers seen by the
+ * consumer, the structure hash and row_nnz_dev are in list order (0 .. nrows-1). */
+int ias_csr_mul_csr_rowlist_stream(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, const int *rows_dev, int nrows,
+                                   size_t budget_bytes, int *row_nnz_dev, ias_stream_consumer consumer, void *user,
+                                   IasSpgemmStats *stats);
 /* host operands, host result: CSR_MUL_CSR(A,B,C), CPU/detail/csr/common_csr.h:85 -- uploads
  * A (and B unless it aliases A), multiplies on the GPU, downloads C into pinned host memory owned
  * by the engine (valid until the next host call or ias_release_host).  nnz(C) via C_nnz. */
