@@ -680,7 +680,7 @@ def main():
     if world > 1:
         if strong:
             # rank r takes rows r, r + N, ...: one pass of the pipeline per rank, hubs and tail rows on every rank
-            rowlist = torch.arange(rank, rows, world, dtype=torch.int32, device="cuda")
+            rowlist = eng.row_share(dA, dA, world, rank)
             r0, r1, blocks = 0, rows, None
         else:
             bounds = eng.partition_rows(dA, dA, world)
@@ -776,7 +776,7 @@ def main():
                            "c_diagonals": main.get("c_diagonals"),
                            "l2": "inputs_exceed_l2 (A %.2f GB per step vs 126 MB L2)" % (bytes_csr(rows, nnz_a) / 1e9),
                            "parallelism": ("row blocks x%d (%s), B broadcast once over NCCL (%.1f ms, outside the timed region)"
-                                           % (world, "rows r, r+N, ... to rank r" if strong else "contiguous, balanced by products", t_bcast))
+                                           % (world, "rows by decreasing products dealt in snake order" if strong else "contiguous, balanced by products", t_bcast))
                                           if world > 1 else "single GPU",
                            "tolerance": "structure bit-exact; values within 1e-12 x sum|a*b| of the entry (= 1e-12 x |c| on zero-free, cancellation-free operands)"},
                 "roofline": main["roofline"], "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": int(main["launches"]), "clocks": clocks}
@@ -833,16 +833,17 @@ def side_config(B, eng, kind, args, with_cpu, with_cusparse):
 
 
 def strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world):
-    """R-MAT scale 22 (fixed problem) over the N GPUs: B broadcast once; rank r multiplies the rows r, r + N, r + 2N, ... of A
-    in ONE pass of the streaming pipeline (ias_csr_mul_csr_rowlist_stream): every rank gets its share of hub rows and of
-    tail rows, and no launch tail is paid per block.  Rank 0 then times the whole problem alone: the 1-GPU figure of the
+    """R-MAT scale 22 (fixed problem) over the N GPUs: B broadcast once; the rows, sorted by decreasing products, are dealt
+    to the ranks in snake order (ias_row_share) and every rank multiplies its share in ONE pass of the streaming pipeline
+    (ias_csr_mul_csr_rowlist_stream): every rank gets its share of hub rows and of tail rows, and no launch tail is paid
+    per block.  (Rows r, r+N, ... would not do: the even rows of an un-permuted R-MAT hold 3/4 of the entries.)  Rank 0 then times the whole problem alone: the 1-GPU figure of the
     same box and run."""
     out = {}
     try:
         wname = workload_name("rmat", scale=22)
         dA, t_bcast = shared_operand("rmat", scale=22)
         rows = dA.dev.row
-        my_rows = torch.arange(rank, rows, world, dtype=torch.int32, device="cuda")
+        my_rows = eng.row_share(dA, dA, world, rank)          # rows by decreasing products, dealt in snake order
         n_mine = int(my_rows.numel())
 
         def step():
@@ -856,7 +857,7 @@ def strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world):
         dist.all_reduce(busy, op=dist.ReduceOp.SUM)
         out = {"workload": wname, "scaling": "strong", "n_gpus": world, "ms_per_step": ms_step, "value": 2.0 * products / (ms_step * 1e6),
                "unit": "GFLOP/s", "products": products, "nnz_C": nnz_c, "per_rank_busy_ms": [round(float(x), 1) for x in busy.tolist()],
-               "broadcast_ms": t_bcast, "partition": "rows r, r+N, r+2N, ... to rank r (ias_csr_mul_csr_rowlist_stream)",
+               "broadcast_ms": t_bcast, "partition": "rows sorted by products, dealt in snake order (ias_row_share + ias_csr_mul_csr_rowlist_stream)",
                "streaming_batches_rank0": st.get("batches"),
                "e2e": {"ms_per_step": ms_step + t_bcast, "value": 2.0 * products / ((ms_step + t_bcast) * 1e6), "unit": "GFLOP/s",
                        "note": "operand resident on rank 0 -> NCCL broadcast of B (3 arrays) + multiply; C is reduced on device "

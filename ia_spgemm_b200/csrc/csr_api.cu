@@ -399,6 +399,57 @@ static int row_products_scan(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B,
     return IAS_OK;
 }
 
+namespace {
+__global__ void __launch_bounds__(256) k_iota_ll(int n, int *out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = i;
+}
+// rows sorted by decreasing work are dealt in snake order (0 1 .. P-1 P-1 .. 1 0 0 1 ..): part `part` keeps its positions
+__global__ void __launch_bounds__(256) k_take_share(int n, int parts, int part, const int *__restrict__ sorted_rows, int *__restrict__ out)
+{
+    int k = blockIdx.x * blockDim.x + threadIdx.x;              // k-th row of this part = round k
+    int pos = (k & 1) ? k * parts + (parts - 1 - part) : k * parts + part;
+    if (pos < n) out[k] = sorted_rows[pos];
+}
+}  // namespace
+
+int ias_row_share(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int parts, int part, int *rows_dev, int *count)
+{
+    IAS_TRY(ensure_init());
+    IAS_TRY(check_operands(A, B, 0, A ? A->row : 0));
+    if (parts < 1 || part < 0 || part >= parts || !rows_dev || !count) return fail(IAS_E_ARG, "bad share request");
+    Ctx &c = ctx();
+    const int n = A->row;
+    *count = 0;
+    if (n == 0) return IAS_OK;
+    DBuf<long long> work, work_sorted;
+    DBuf<int> ids, ids_sorted;
+    IAS_TRY(work.alloc(n));
+    IAS_TRY(work_sorted.alloc(n));
+    IAS_TRY(ids.alloc(n));
+    IAS_TRY(ids_sorted.alloc(n));
+    IAS_LAUNCH(k_row_products, grid_for((long long)n * 32, 256), 256, 0, n, view(A), view(B), work.p);
+    IAS_LAUNCH(k_iota_ll, grid_for(n, 256), 256, 0, n, ids.p);
+    size_t tb = 0;
+    IAS_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, work.p, work_sorted.p, ids.p, ids_sorted.p, n, 0, 48, c.stream));
+    DBuf<char> tmp;
+    IAS_TRY(tmp.alloc(tb));
+    IAS_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp.p, tb, work.p, work_sorted.p, ids.p, ids_sorted.p, n, 0, 48, c.stream));
+    c.launches += 2;
+    int mine = 0;                                   // rounds k with a valid position
+    for (int k = 0;; ++k) {
+        long long pos = (k & 1) ? (long long)k * parts + (parts - 1 - part) : (long long)k * parts + part;
+        if ((long long)k * parts >= n) break;
+        if (pos < n) mine = k + 1;
+    }
+    // (a round whose position falls beyond n can only be the last one: the share is rounds 0 .. mine-1, all valid)
+    if (mine) IAS_LAUNCH(k_take_share, grid_for(mine, 256), 256, 0, n, parts, part, ids_sorted.p, rows_dev);
+    IAS_CUDA(cudaStreamSynchronize(c.stream));
+    *count = mine;
+    return IAS_OK;
+}
+
 int ias_getflop(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, long long *products)
 {
     IAS_TRY(ensure_init());

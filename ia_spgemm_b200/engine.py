@@ -117,7 +117,7 @@ ABI_SYMBOLS = [
     "ias_csr_is_canonical", "ias_copy", "ias_forget_operand",
     "ias_csr_mul_csr_dev64", "ias_csr_mul_csr_dev", "ias_csr_mul_csr_rows_dev64", "ias_csr_mul_csr_stream",
     "ias_csr_mul_csr_stream_cb", "ias_csr_mul_csr_rowlist_stream",
-    "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_touched_b_bytes", "ias_partition_rows", "ias_checksum",
+    "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_touched_b_bytes", "ias_partition_rows", "ias_row_share", "ias_checksum",
     "ias_structure_hash",
     "ias_csr_to_dia", "ias_dia_mul_dia_dev", "ias_dia_mul_dia_rows_dev", "ias_download_dia", "ias_free_dia_dev", "ias_dia_relayout",
     "ias_csr_to_ell", "ias_ell_mul_ell_dev", "ias_ell_mul_ell_dev64", "ias_download_ell", "ias_download_ell64", "ias_free_ell_dev", "ias_free_ell64_dev",
@@ -549,6 +549,15 @@ class Engine:
         b = (C.c_int * (parts + 1))()
         self._ck(self.lib.ias_partition_rows(C.byref(A.dev), C.byref(B.dev), C.c_int(parts), b))
         return list(b)
+
+    def row_share(self, A, B, parts, part):
+        """Device tensor (torch int32) with this part's rows: rows sorted by decreasing products, dealt in snake order."""
+        import torch
+        cap = (A.dev.row + parts - 1) // parts + 1
+        t = torch.empty(cap, dtype=torch.int32, device="cuda")
+        n = C.c_int()
+        self._ck(self.lib.ias_row_share(C.byref(A.dev), C.byref(B.dev), C.c_int(parts), C.c_int(part), C.c_void_p(t.data_ptr()), C.byref(n)))
+        return t[: n.value]
 
     def checksum_ptr(self, ptr, n):
         s = C.c_double()

@@ -242,6 +242,10 @@ int ias_getflop(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, long long *p
 int ias_touched_b_bytes(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int row_begin, int row_end, long long *bytes);
 /* work-balanced contiguous row blocks: bounds[0..parts] with equal shares of products */
 int ias_partition_rows(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int parts, int *bounds);
+/* work-balanced NON-contiguous share for ias_csr_mul_csr_rowlist_stream: the rows sorted by decreasing products are dealt
+ * to the parts in snake order; rows_dev (capacity ceil(rows/parts)) receives the rows of `part`, *count their number.
+ * (Un-permuted R-MAT: rows r, r+N, ... would not do -- the even rows hold three quarters of the entries.) */
+int ias_row_share(const IasCsrMatrixDev *A, const IasCsrMatrixDev *B, int parts, int part, int *rows_dev, int *count);
 /* getsum_csr, csr_dev:264-273 (verified_sum) */
 int ias_checksum(const double *values_dev, long long n, double *sum);
 /* order-independent structure hash of a CSR result (same function as the streaming consumer) */

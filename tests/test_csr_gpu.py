@@ -258,6 +258,14 @@ def test_row_list_streaming_equals_rows_of_the_full_product(eng, oracle):
         want_v = np.concatenate([v[rp[r]:rp[r + 1]] for r in rows])
         assert np.array_equal(got_ci, want_ci) and np.allclose(got_v, want_v, rtol=1e-13, atol=0)
         assert parts[0]["row_begin"] == 0 and parts[-1]["row_end"] == len(rows)
+    # work-balanced shares: a partition of the rows, products within a few percent of each other
+    lens = np.diff(A[2]).astype(np.int64)
+    cs = np.concatenate(([0], np.cumsum(lens[A[3]])))
+    per_row = cs[A[2][1:]] - cs[A[2][:-1]]
+    shares = [eng.row_share(dA, dA, 3, p).cpu().numpy() for p in range(3)]
+    assert sorted(np.concatenate(shares).tolist()) == list(range(n))
+    tot = [int(per_row[sh].sum()) for sh in shares]
+    assert max(tot) - min(tot) <= 0.05 * sum(tot) / 3 + per_row.max()
     from ia_spgemm_b200.engine import EngineError
     bad = torch.tensor([0, n], dtype=torch.int32).cuda()
     with pytest.raises(EngineError):
