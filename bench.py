@@ -794,6 +794,7 @@ def side_config(B, eng, kind, args, with_cpu, with_cusparse):
     try:
         kw = dict(grid=args.grid, world=1, n=args.n, scale=22)
         wname = workload_name(kind, **kw)
+        eng.trim_pool()                                      # every config starts from an empty device pool, like its own process
         dA = make_operand(eng, kind, **kw)
         products = eng.GetFlop(dA, dA)
         rows = dA.dev.row
@@ -801,6 +802,9 @@ def side_config(B, eng, kind, args, with_cpu, with_cusparse):
         if dia is not None:
             eng.free_dia(dia)
         out = {"workload": wname, "description": describe(kind, **kw), "selected_format": fmt, "rows": rows, "nnz_A": dA.dev.nnz}
+        if fmt == "ell":                                                 # the selector's path first
+            out["ell_path"] = B.ell_leg(dA, rows, products, 5, 3, wname)
+            eng.trim_pool()
         if kind == "rmat":
             leg = B.csr_leg(dA, 0, rows, 2, 1, True, 0, wname)           # 1.5e11 products per step: one warm-up, two timed steps
         else:
@@ -808,7 +812,9 @@ def side_config(B, eng, kind, args, with_cpu, with_cusparse):
         out.update({k: leg[k] for k in ("ms_per_step", "value", "unit", "products", "nnz_C", "roofline")})
         out["detail"] = leg["detail"]
         if fmt == "ell":
-            out["ell_path"] = B.ell_leg(dA, rows, products, 5, 3, wname)
+            out["csr_path"] = {k: out[k] for k in ("ms_per_step", "value", "unit", "roofline")}
+            out.update({k: out["ell_path"][k] for k in ("ms_per_step", "value", "unit", "roofline")})
+            out["note"] = "top-level figures: the selector's path (ELL); csr_path: the CSR pipeline on the same operand"
         if with_cusparse and kind != "rmat":
             out["cusparse"] = B.cusparse_leg(dA, products)
         host = dA.download() if with_cpu else None          # the device generator's operand, for the CPU sample below

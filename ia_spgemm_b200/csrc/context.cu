@@ -152,6 +152,14 @@ int ias_use_own_stream(void)
     return IAS_OK;
 }
 
+int ias_trim_pool(void)
+{
+    IAS_TRY(ensure_init());
+    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
+    IAS_CUDA(cudaMemPoolTrimTo(ctx().pool, 0));          // cached blocks of earlier problem sizes go back to the driver
+    return IAS_OK;
+}
+
 int ias_sync(void)
 {
     IAS_TRY(ensure_init());

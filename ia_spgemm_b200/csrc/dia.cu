@@ -312,15 +312,18 @@ int ias_dia_mul_dia_rows_dev(const IasDiaDev *A, const IasDiaDev *B, int r0, int
     DBuf<int> di, off, d_pstart;
     DBuf<DiaPair> d_pairs;
     DBuf<double> val;
-    IAS_TRY(di.alloc((size_t)std::max(span, 1)));
+    // diagonal_ind spans rows(A) + cols(B) - 1 entries whatever the row block: a block of a larger product (multi-GPU)
+    // does not carry it -- zeroing a gigabyte per multiply is what cost the 8-GPU weak-scaling run 25 %
+    const bool full = r0 == 0 && r1 == A->row;
+    if (full) IAS_TRY(di.alloc((size_t)std::max(span, 1)));
     IAS_TRY(off.alloc((size_t)std::max(c_nd, 1)));
     IAS_TRY(d_pstart.alloc(pstart.size()));
     IAS_TRY(d_pairs.alloc(std::max<size_t>(pab.size(), 1)));
     IAS_TRY(val.alloc((size_t)nrows * c_nd));
-    IAS_CUDA(cudaMemsetAsync(di.p, 0, sizeof(int) * (size_t)std::max(span, 1), s));
+    if (full) IAS_CUDA(cudaMemsetAsync(di.p, 0, sizeof(int) * (size_t)std::max(span, 1), s));
     if (c_nd) {
         IAS_CUDA(cudaMemcpyAsync(off.p, c_off.data(), sizeof(int) * c_nd, cudaMemcpyHostToDevice, s));
-        IAS_LAUNCH(k_scatter_diag_ind, grid_for(c_nd, 256), 256, 0, c_nd, A->row, off.p, di.p);     // dia:150-158
+        if (full) IAS_LAUNCH(k_scatter_diag_ind, grid_for(c_nd, 256), 256, 0, c_nd, A->row, off.p, di.p);     // dia:150-158
     }
     IAS_CUDA(cudaMemcpyAsync(d_pstart.p, pstart.data(), sizeof(int) * pstart.size(), cudaMemcpyHostToDevice, s));
     if (!pab.empty()) IAS_CUDA(cudaMemcpyAsync(d_pairs.p, pab.data(), sizeof(DiaPair) * pab.size(), cudaMemcpyHostToDevice, s));
@@ -367,7 +370,7 @@ int ias_dia_relayout(const IasDiaDev *in, int to_row_major, IasDiaDev *out)
     IAS_TRY(di.alloc((size_t)span));
     IAS_TRY(off.alloc((size_t)std::max(in->num_diagonals, 1)));
     IAS_TRY(val.alloc(n));
-    if (in->row + in->col - 1 > 0) IAS_CUDA(cudaMemcpyAsync(di.p, in->diagonal_ind_dev, sizeof(int) * (size_t)(in->row + in->col - 1), cudaMemcpyDeviceToDevice, c.stream));
+    if (in->row + in->col - 1 > 0 && in->diagonal_ind_dev) IAS_CUDA(cudaMemcpyAsync(di.p, in->diagonal_ind_dev, sizeof(int) * (size_t)(in->row + in->col - 1), cudaMemcpyDeviceToDevice, c.stream));
     if (in->num_diagonals) IAS_CUDA(cudaMemcpyAsync(off.p, in->diagonal_offsets_dev, sizeof(int) * (size_t)in->num_diagonals, cudaMemcpyDeviceToDevice, c.stream));
     if (n) {
         if (to_row_major) IAS_LAUNCH(k_dia_to_row_major, grid_for((long long)n, 256), 256, 0, in->row, in->num_diagonals, in->values_dev, val.p);
@@ -386,7 +389,7 @@ int ias_download_dia(const IasDiaDev *d, int *diagonal_ind, int *diagonal_offset
     if (!d->choice) return fail(IAS_E_GATE, "DIA matrix was rejected by the size gate");
     Ctx &c = ctx();
     int span = d->row + d->col - 1;
-    if (diagonal_ind && span > 0) IAS_CUDA(cudaMemcpyAsync(diagonal_ind, d->diagonal_ind_dev, sizeof(int) * span, cudaMemcpyDeviceToHost, c.stream));
+    if (diagonal_ind && span > 0 && d->diagonal_ind_dev) IAS_CUDA(cudaMemcpyAsync(diagonal_ind, d->diagonal_ind_dev, sizeof(int) * span, cudaMemcpyDeviceToHost, c.stream));
     if (diagonal_offsets && d->num_diagonals) IAS_CUDA(cudaMemcpyAsync(diagonal_offsets, d->diagonal_offsets_dev, sizeof(int) * d->num_diagonals, cudaMemcpyDeviceToHost, c.stream));
     size_t n = (size_t)d->row * d->num_diagonals;
     if (values_row_major && n) {

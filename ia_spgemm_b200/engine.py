@@ -111,7 +111,7 @@ BIN_NAMES = ["empty", "tiny", "warp", "cta_s", "cta_l", "global"]
 
 # every symbol include/iaspgemm.h declares (tests check the library exports all of them)
 ABI_SYMBOLS = [
-    "ias_init", "ias_set_stream", "ias_use_own_stream", "ias_sync", "ias_last_error", "ias_version", "ias_device_info",
+    "ias_init", "ias_set_stream", "ias_use_own_stream", "ias_sync", "ias_trim_pool", "ias_last_error", "ias_version", "ias_device_info",
     "ias_kernel_launches", "ias_set_option", "ias_get_option",
     "ias_upload_csr", "ias_free_csr_dev", "ias_free_csr64_dev", "ias_download_csr64", "ias_download_csr",
     "ias_csr_is_canonical", "ias_copy", "ias_forget_operand",
@@ -299,6 +299,9 @@ class Engine:
 
     def sync(self):
         self._ck(self.lib.ias_sync())
+
+    def trim_pool(self):
+        self._ck(self.lib.ias_trim_pool())
 
     def kernel_launches(self):
         return int(self.lib.ias_kernel_launches())

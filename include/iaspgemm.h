@@ -140,6 +140,7 @@ int ias_init(int device);                       /* binds the engine to a CUDA de
 int ias_set_stream(void *cuda_stream);          /* run on the caller's cudaStream_t; NULL is the legacy default stream */
 int ias_use_own_stream(void);                   /* back to the engine's own (non-blocking) stream, the default after ias_init */
 int ias_sync(void);
+int ias_trim_pool(void);                        /* returns the engine pool's cached (free) device memory to the driver */
 const char *ias_last_error(void);
 const char *ias_version(void);
 int ias_device_info(int *sm_count, size_t *smem_optin, size_t *free_bytes, size_t *total_bytes);
@@ -257,7 +258,7 @@ int ias_csr_to_dia(const IasCsrMatrixDev *A, double gate, IasDiaDev *out);
 /* DIA_MUL_DIA_DEV, GPU/detail/dia_dev/common_dia_dev.h:138-182 */
 int ias_dia_mul_dia_dev(const IasDiaDev *A, const IasDiaDev *B, IasDiaDev *C, double *elapsed_ms);
 /* rows [row_begin,row_end) of C only (multi-GPU row blocks): C->row = row_end-row_begin, values[slot*C->row + (i-row_begin)];
- * offsets and diagonal_ind are those of the whole product */
+ * offsets are those of the whole product; diagonal_ind_dev is NULL unless the block is the whole matrix */
 int ias_dia_mul_dia_rows_dev(const IasDiaDev *A, const IasDiaDev *B, int row_begin, int row_end, IasDiaDev *C,
                              double *elapsed_ms);
 int ias_download_dia(const IasDiaDev *dev, int *diagonal_ind, int *diagonal_offsets,
