@@ -501,7 +501,7 @@ class Bench:
                 sink = float(r.values[cells - 1]) if cells else 0.0                       # read the result on the host
                 return {"format": {1: "csr", 2: "dia", 3: "ell"}[r.format], "nnz": r.nnz, "h2d_bytes": r.h2d_bytes, "d2h_bytes": r.d2h_bytes,
                         "ms": {k: getattr(r, "ms_" + k) for k in ("h2d", "select", "convert", "multiply", "d2h", "wall")},
-                        "host_ms_at": [round(x, 3) for x in r.ms_host]}, sink
+                        "host_ms_at": [round(x, 3) for x in r.ms_host], "pipelined": bool(r.pipelined)}, sink
             rp, ci, v = C.POINTER(C.c_longlong)(), C.POINTER(C.c_int)(), C.POINTER(C.c_double)()
             nnz, st, h2d, d2h = C.c_longlong(), SpgemmStats(), C.c_double(), C.c_double()
             eng._ck(lib.ias_csr_mul_csr_host(C.byref(h), C.byref(h), C.byref(rp), C.byref(ci), C.byref(v), C.byref(nnz), C.byref(st),
@@ -525,7 +525,7 @@ class Bench:
         e_ms = max(ev0.elapsed_time(ev1), wall) / e_steps
         out = {"ms_per_step": e_ms, "h2d_bytes_per_step": int(r["h2d_bytes"]), "d2h_bytes_per_step": int(r["d2h_bytes"]),
                "result_format": r["format"], "phase_ms": {k: round(float(v), 3) for k, v in r["ms"].items()},
-               "host_ms_at": r.get("host_ms_at"), "per_call_ms": per_call,
+               "host_ms_at": r.get("host_ms_at"), "per_call_ms": per_call, "pipelined": r.get("pipelined"),
                "api": "ias_spgemm_auto_host (features -> selection -> conversion -> multiply -> host result)" if api == "auto"
                       else "ias_csr_mul_csr_host (CSR_MUL_CSR on host operands)"}
         eng.lib.ias_release_host()

@@ -29,6 +29,7 @@ struct Tuning {
     long long g_lpt = 1;              // global rows are handed out in order of decreasing work
     long long g_block = 1024;         // L2 bitmap kernel: threads per CTA (1024: one row per SM, 512: two)
     long long bulk_store = 1;         // shared -> global bulk copies (cp.async.bulk) for staged output tiles (0: per-thread stores)
+    long long e2e_pipeline = 1;       // ias_spgemm_auto_host: chunked upload / DIA multiply / download for banded A^2 (speculative, verified)
     long long dia_vec = 0;            // DIA x DIA: two adjacent rows per thread with 128-bit accesses -- measured SLOWER than the scalar
                                       // kernel on B200 (0.617 vs 0.542 ms on Poisson 4096^2), kept for the record
     long long ell_onepass = 1;        // ELL x ELL: one-pass register-sort kernel when a row's products fit (0: always the pipeline)
@@ -44,6 +45,8 @@ struct Ctx {
     size_t smem_optin = 227 * 1024;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;      // stream every engine kernel is launched on
+    cudaStream_t s_up = nullptr, s_down = nullptr;     // copy streams of the pipelined host path (non-blocking)
+    cudaEvent_t ev_pipe[96] = {};       // upload / compute / download events of its chunks (no timing)
     cudaMemPool_t pool = nullptr;
     cudaEvent_t ev[8] = {};
     cudaEvent_t ev_bin[32] = {};        // [2*bin], [2*bin+1]: symbolic bins 0..7, numeric bins 8..15
@@ -61,6 +64,11 @@ struct Ctx {
 };
 
 Ctx &ctx();
+int host_arena(size_t bytes, void **p);        // pinned host memory owned by the engine (grow only; ias_release_host frees it)
+int ensure_pipe_streams();
+// DIA helpers shared with the auto path (dia.cu)
+void dia_rows_major(int rows, int nd, const double *in_diag_major, double *out_row_major, cudaStream_t s);
+int auto_dia_pipelined(const IasCsrMatrix *A, double gate, IasAutoResult *out, IasCsrMatrixDev *dA, int *have_dA, int *done);
 int fail_cuda(cudaError_t e, const char *what, const char *file, int line);
 int fail(int code, const char *fmt, ...);
 int ensure_init();

@@ -33,6 +33,36 @@ int ensure_init()
     return ias_init(0);
 }
 
+int host_arena(size_t bytes, void **p)
+{
+    Ctx &c = g_ctx;
+    if (c.h_arena_bytes < bytes) {
+        if (c.h_arena) cudaFreeHost(c.h_arena);
+        c.h_arena = nullptr; c.h_arena_bytes = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMallocHost(&c.h_arena, want);
+        if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMallocHost(&c.h_arena, want); }      // without the growth slack
+        if (e != cudaSuccess) {
+            cudaGetLastError();
+            c.h_arena = nullptr;
+            return fail(IAS_E_NOMEM, "pinned host allocation of %zu bytes failed: %s", want, cudaGetErrorString(e));
+        }
+        c.h_arena_bytes = want;
+    }
+    *p = c.h_arena;
+    return IAS_OK;
+}
+
+int ensure_pipe_streams()
+{
+    Ctx &c = g_ctx;
+    if (!c.s_up) IAS_CUDA(cudaStreamCreateWithFlags(&c.s_up, cudaStreamNonBlocking));
+    if (!c.s_down) IAS_CUDA(cudaStreamCreateWithFlags(&c.s_down, cudaStreamNonBlocking));
+    for (int i = 0; i < 96; ++i)
+        if (!c.ev_pipe[i]) IAS_CUDA(cudaEventCreateWithFlags(&c.ev_pipe[i], cudaEventDisableTiming));
+    return IAS_OK;
+}
+
 }  // namespace ias
 
 using namespace ias;
@@ -62,6 +92,7 @@ static long long *option_slot(const char *name)
     if (!strcmp(name, "ell_onepass")) return &t.ell_onepass;
     if (!strcmp(name, "bulk_store")) return &t.bulk_store;
     if (!strcmp(name, "dia_vec")) return &t.dia_vec;
+    if (!strcmp(name, "e2e_pipeline")) return &t.e2e_pipeline;
     if (!strcmp(name, "g_v2")) return &t.g_v2;
     if (!strcmp(name, "g_tbl")) return &t.g_tbl;
     if (!strcmp(name, "g_lpt")) return &t.g_lpt;
@@ -88,6 +119,10 @@ int ias_init(int device)
         c.own_stream = nullptr;
         for (int i = 0; i < 8; ++i) { if (c.ev[i]) cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
         for (int i = 0; i < 32; ++i) { if (c.ev_bin[i]) cudaEventDestroy(c.ev_bin[i]); c.ev_bin[i] = nullptr; }
+        for (int i = 0; i < 96; ++i) { if (c.ev_pipe[i]) cudaEventDestroy(c.ev_pipe[i]); c.ev_pipe[i] = nullptr; }
+        if (c.s_up) cudaStreamDestroy(c.s_up);
+        if (c.s_down) cudaStreamDestroy(c.s_down);
+        c.s_up = c.s_down = nullptr;
         c.canon_ci = c.canon_rp = nullptr; c.canon_rows = c.canon_nnz = -1;
         c.ready = false;
         cudaGetLastError();
@@ -108,7 +143,7 @@ int ias_init(int device)
         if (!c.ev_bin[i]) IAS_CUDA(cudaEventCreate(&c.ev_bin[i]));
     if (!c.h_scalars) IAS_CUDA(cudaMallocHost((void **)&c.h_scalars, 64 * sizeof(long long)));
     static const char *const names[] = {"global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win", "g_coop", "gwin_takes_b2",
-                                        "trust_operand_cache", "g_ldca", "g_block", "ell_onepass", "g_v2", "g_tbl", "g_lpt", "bulk_store", "dia_vec", "g_scr", "g2_takes_b2"};
+                                        "trust_operand_cache", "g_ldca", "g_block", "ell_onepass", "g_v2", "g_tbl", "g_lpt", "bulk_store", "dia_vec", "g_scr", "g2_takes_b2", "e2e_pipeline"};
     for (const char *n : names) {                  // IAS_OPT_GWIN_WIN=4096 etc.
         char env[64] = "IAS_OPT_";
         size_t k = strlen(env);

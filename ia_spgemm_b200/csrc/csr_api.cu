@@ -247,22 +247,6 @@ int ias_structure_hash(const IasCsr64Dev *C, int row_base, unsigned long long *h
 }
 
 // ---------------------------------------------------------------- host operands (the e2e path)
-static int host_arena(size_t bytes, void **p)
-{
-    Ctx &c = ctx();
-    if (c.h_arena_bytes < bytes) {
-        if (c.h_arena) cudaFreeHost(c.h_arena);
-        c.h_arena = nullptr; c.h_arena_bytes = 0;
-        size_t want = bytes + bytes / 8;
-        cudaError_t e = cudaMallocHost(&c.h_arena, want);
-        if (e != cudaSuccess) { cudaGetLastError(); want = bytes; e = cudaMallocHost(&c.h_arena, want); }      // without the growth slack
-        if (e != cudaSuccess) { cudaGetLastError(); c.h_arena = nullptr; return fail(IAS_E_NOMEM, "pinned host allocation of %zu bytes failed: %s", want, cudaGetErrorString(e)); }
-        c.h_arena_bytes = want;
-    }
-    *p = c.h_arena;
-    return IAS_OK;
-}
-
 int ias_release_host(void)
 {
     Ctx &c = ctx();

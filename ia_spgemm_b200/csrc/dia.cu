@@ -183,6 +183,55 @@ __global__ void __launch_bounds__(256) k_dia_to_diag_major(int rows, int nd, con
     out[t] = in[i * nd + s];
 }
 
+// ---- kernels of the pipelined host path (row ranges of an operand that is still being uploaded)
+__global__ void __launch_bounds__(256) k_flag_diagonals_rows(int r0, int r1, int rows, const int *__restrict__ rp, const int *__restrict__ ci,
+                                                             int *__restrict__ flags)
+{
+    int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r1) return;
+    int pe = rp[i + 1];
+    for (int p = rp[i]; p < pe; ++p) {
+        int m = (rows - i) + ci[p];
+        if (!flags[m]) flags[m] = 1;
+    }
+}
+// fill rows [r0, r1) of a DIA operand whose diagonal set was taken from the first chunk: an entry on another diagonal
+// raises *bad (the speculation failed; the caller falls back to the unpipelined path)
+__global__ void __launch_bounds__(256) k_fill_dia_rows(int r0, int r1, int rows, const int *__restrict__ rp, const int *__restrict__ ci,
+                                                       const double *__restrict__ v, const int *__restrict__ spec_flags,
+                                                       const int *__restrict__ slot_of, double *__restrict__ values, int *__restrict__ bad)
+{
+    int i = r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= r1) return;
+    int pe = rp[i + 1];
+    for (int p = rp[i]; p < pe; ++p) {
+        int m = (rows - i) + ci[p];
+        if (!spec_flags[m]) { *bad = 1; continue; }
+        values[(size_t)slot_of[m] * rows + i] = v[p];
+    }
+}
+__global__ void __launch_bounds__(256) k_flags_differ(int n, const int *__restrict__ a, const int *__restrict__ b, int *__restrict__ out)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && (a[i] != 0) != (b[i] != 0)) out[1] = 1;
+}
+// tiled transpose diagonal-major -> row-major (both sides coalesced)
+__global__ void __launch_bounds__(256) k_dia_rows_major(int rows, int nd, const double *__restrict__ in, double *__restrict__ out)
+{
+    __shared__ double tile[32][33];
+    const int i0 = blockIdx.x * 32, s0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;            // 8 rows of 32 threads
+    for (int r = ty; r < 32; r += 8) {
+        const int s = s0 + r, i = i0 + tx;
+        if (s < nd && i < rows) tile[r][tx] = in[(size_t)s * rows + i];
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int i = i0 + r, s = s0 + tx;
+        if (i < rows && s < nd) out[(size_t)i * nd + s] = tile[tx][r];
+    }
+}
+
 int diag_census(const IasCsrMatrixDev *A, DBuf<int> &flags, DBuf<int> &slot_of, int *nd)
 {
     Ctx &c = ctx();
@@ -203,6 +252,208 @@ int diag_census(const IasCsrMatrixDev *A, DBuf<int> &flags, DBuf<int> &slot_of, 
 }
 
 }  // namespace
+
+namespace ias {
+
+void dia_rows_major(int rows, int nd, const double *in, double *out, cudaStream_t s)
+{
+    if (rows <= 0 || nd <= 0) return;
+    dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((nd + 31) / 32));
+    k_dia_rows_major<<<grid, 256, 0, s>>>(rows, nd, in, out);
+}
+
+// A^2 of a banded host operand with upload, multiply and download overlapped (PCIe is full duplex):
+//   the CSR arrays go up in row chunks on one stream; the diagonal set is taken from the FIRST chunk (speculation) so that
+//   chunk k can be converted to DIA and chunk k-1 multiplied (ias_dia_mul_dia_rows_dev: it needs the B rows within the
+//   band around its own rows, i.e. one chunk ahead) while later chunks are still in flight; each finished row block of C
+//   is transposed to the reference's row-major layout and goes down on a third stream into the pinned result.
+//   Afterwards the speculation is VERIFIED: the census of all rows must equal the first chunk's, no entry may have
+//   fallen outside it, and the selector run on the complete features must still say DIA -- otherwise *done stays 0 and
+//   the caller runs the plain path on the operand that is on the device by then (*have_dA).
+// A^2 needs all of B before the first row of C only when B's rows are referenced at random; a band references its
+// neighbourhood, and that is what makes the overlap legal here.
+int auto_dia_pipelined(const IasCsrMatrix *A, double gate, IasAutoResult *out, IasCsrMatrixDev *dA, int *have_dA, int *done)
+{
+    *done = 0; *have_dA = 0;
+    Ctx &c = ctx();
+    const int rows = A->row, cols = A->col;
+    const long long nnz = A->nnz;
+    if (rows != cols || rows < (1 << 16) || nnz <= 0) return IAS_OK;
+    IAS_TRY(ensure_pipe_streams());
+    cudaStream_t s = c.stream, s_up = c.s_up, s_down = c.s_down;
+    cudaEvent_t *ev_up = c.ev_pipe, *ev_c = c.ev_pipe + 32, *ev_d = c.ev_pipe + 64;
+    const int K = 16;
+    int chunk = ((rows + K - 1) / K + 1) & ~1;                      // even: keeps every block 16-byte aligned
+    const int nchunk = (rows + chunk - 1) / chunk;
+
+    // ---- device CSR arrays; uploads in row chunks on s_up
+    DBuf<int> rp, ci;
+    DBuf<double> v;
+    IAS_TRY(rp.alloc((size_t)rows + 1));
+    IAS_TRY(ci.alloc((size_t)nnz));
+    IAS_TRY(v.alloc((size_t)nnz));
+    const int span = rows + cols;
+    DBuf<int> flags_spec, flags_full, slot_of, bad, a_off;
+    IAS_TRY(flags_spec.alloc((size_t)span + 1));
+    IAS_TRY(flags_full.alloc((size_t)span + 1));
+    IAS_TRY(slot_of.alloc((size_t)span + 1));
+    IAS_TRY(bad.alloc(2));
+    IAS_CUDA(cudaMemsetAsync(flags_spec.p, 0, sizeof(int) * ((size_t)span + 1), s));
+    IAS_CUDA(cudaMemsetAsync(flags_full.p, 0, sizeof(int) * ((size_t)span + 1), s));
+    IAS_CUDA(cudaMemsetAsync(bad.p, 0, 2 * sizeof(int), s));
+    IAS_CUDA(cudaStreamSynchronize(s));                              // the buffers exist before another stream writes them
+    IAS_CUDA(cudaMemcpyAsync(rp.p, A->row_ind, sizeof(int) * ((size_t)rows + 1), cudaMemcpyHostToDevice, s_up));
+    for (int k = 0; k < nchunk; ++k) {
+        const int r0 = k * chunk, r1 = std::min(rows, r0 + chunk);
+        const size_t e0 = (size_t)A->row_ind[r0], e1 = (size_t)A->row_ind[r1];
+        if (e1 > e0) {
+            IAS_CUDA(cudaMemcpyAsync(ci.p + e0, A->col_ind + e0, sizeof(int) * (e1 - e0), cudaMemcpyHostToDevice, s_up));
+            IAS_CUDA(cudaMemcpyAsync(v.p + e0, A->values + e0, sizeof(double) * (e1 - e0), cudaMemcpyHostToDevice, s_up));
+        }
+        IAS_CUDA(cudaEventRecord(ev_up[k], s_up));
+    }
+    dA->choice = true; dA->row = rows; dA->col = cols; dA->nnz = (int)nnz;
+    dA->row_ind_dev = rp.p; dA->col_ind_dev = ci.p; dA->values_dev = v.p;
+    auto give_up = [&]() {                                            // hand the (completely uploaded) operand to the caller
+        cudaStreamSynchronize(s_up); cudaStreamSynchronize(s_down); cudaStreamSynchronize(s);
+        rp.release(); ci.release(); v.release();
+        *have_dA = 1;
+        return IAS_OK;
+    };
+
+    // ---- speculation: the diagonals of the first chunk
+    IAS_CUDA(cudaStreamWaitEvent(s, ev_up[0], 0));
+    const int c0_rows = std::min(rows, chunk);
+    IAS_LAUNCH(k_flag_diagonals_rows, grid_for(c0_rows, 256), 256, 0, 0, c0_rows, rows, rp.p, ci.p, flags_spec.p);
+    size_t tb = 0;
+    IAS_CUDA(cub::DeviceScan::ExclusiveSum(nullptr, tb, flags_spec.p, slot_of.p, span + 1, s));
+    DBuf<char> tmp;
+    IAS_TRY(tmp.alloc(tb));
+    IAS_CUDA(cub::DeviceScan::ExclusiveSum(tmp.p, tb, flags_spec.p, slot_of.p, span + 1, s));
+    c.launches += 2;
+    int nd = 0;
+    IAS_CUDA(cudaMemcpyAsync(&nd, slot_of.p + span, sizeof(int), cudaMemcpyDeviceToHost, s));
+    IAS_CUDA(cudaStreamSynchronize(s));
+    const bool plausible = nd > 0 && nd <= 4096 && ias_sizeof_dia(rows, cols, nd) < gate * ias_sizeof_csr(rows, nnz) &&
+                           (double)nnz / ((double)nd * rows) > 0.5;
+    if (!plausible) return give_up();
+    IasDiaDev a_dia;
+    memset(&a_dia, 0, sizeof a_dia);
+    a_dia.choice = true; a_dia.row = rows; a_dia.col = cols; a_dia.num_diagonals = nd;
+    DBuf<int> a_di;
+    DBuf<double> a_val;
+    IAS_TRY(a_off.alloc((size_t)nd));
+    IAS_TRY(a_di.alloc((size_t)std::max(span - 1, 1)));
+    IAS_TRY(a_val.alloc((size_t)rows * nd));
+    IAS_CUDA(cudaMemsetAsync(a_val.p, 0, sizeof(double) * (size_t)rows * nd, s));
+    IAS_LAUNCH(k_number_diagonals, grid_for(span, 256), 256, 0, span, rows, flags_spec.p, slot_of.p, a_off.p, a_di.p);
+    a_dia.diagonal_ind_dev = a_di.p; a_dia.diagonal_offsets_dev = a_off.p; a_dia.values_dev = a_val.p;
+    {
+        // block j is multiplied when block j+1 has been converted: the band must not reach further than one chunk
+        std::vector<int> h_aoff((size_t)nd);
+        IAS_CUDA(cudaMemcpyAsync(h_aoff.data(), a_off.p, sizeof(int) * (size_t)nd, cudaMemcpyDeviceToHost, s));
+        IAS_CUDA(cudaStreamSynchronize(s));
+        long long reach = 0;
+        for (int o : h_aoff) reach = std::max<long long>(reach, o);
+        if (2 * reach >= chunk) return give_up();                   // (B's rows i + oA, and C = A*B reaches oA + oB)
+    }
+
+    // ---- chunks: convert k, multiply k-1, send k-1 down
+    DBuf<double> stage[2];
+    int ndc = 0;
+    void *base = nullptr;
+    double *h_vals = nullptr;
+    int *h_off = nullptr, *h_ind = nullptr;
+    size_t o_off = 0, o_ind = 0;
+    auto multiply_block = [&](int j) -> int {
+        const int r0 = j * chunk, r1 = std::min(rows, r0 + chunk);
+        IasDiaDev cb;
+        double ms = 0;
+        IAS_TRY(ias_dia_mul_dia_rows_dev(&a_dia, &a_dia, r0, r1, &cb, &ms));
+        if (ndc == 0) {                                               // first block: the shape of C is known, size the result
+            ndc = cb.num_diagonals;
+            const size_t cells = (size_t)rows * ndc, cspan = (size_t)std::max(rows + cols - 1, 1);
+            o_off = (cells * 8 + 255) / 256 * 256; o_ind = o_off + ((size_t)std::max(ndc, 1) * 4 + 255) / 256 * 256;
+            int rc = host_arena(o_ind + cspan * 4 + 256, &base);
+            if (rc != IAS_OK) { ias_free_dia_dev(&cb); return rc; }
+            h_vals = (double *)base; h_off = (int *)((char *)base + o_off); h_ind = (int *)((char *)base + o_ind);
+            if (ndc) IAS_CUDA(cudaMemcpyAsync(h_off, cb.diagonal_offsets_dev, sizeof(int) * (size_t)ndc, cudaMemcpyDeviceToHost, s));
+            IAS_TRY(stage[0].alloc((size_t)chunk * std::max(ndc, 1)));
+            IAS_TRY(stage[1].alloc((size_t)chunk * std::max(ndc, 1)));
+        } else if (cb.num_diagonals != ndc) {
+            ias_free_dia_dev(&cb);
+            return fail(IAS_E_CUDA, "pipelined DIA path: block %d has %d diagonals, the first had %d", j, cb.num_diagonals, ndc);
+        }
+        if (j >= 2) IAS_CUDA(cudaStreamWaitEvent(s, ev_d[j - 2], 0));  // the staging buffer's previous block has left
+        dia_rows_major(r1 - r0, ndc, cb.values_dev, stage[j & 1].p, s);
+        c.launches++;
+        IAS_CUDA(cudaEventRecord(ev_c[j], s));
+        ias_free_dia_dev(&cb);                                        // stream-ordered: after the transpose
+        IAS_CUDA(cudaStreamWaitEvent(s_down, ev_c[j], 0));
+        if (r1 > r0 && ndc)
+            IAS_CUDA(cudaMemcpyAsync(h_vals + (size_t)r0 * ndc, stage[j & 1].p, sizeof(double) * (size_t)(r1 - r0) * ndc, cudaMemcpyDeviceToHost, s_down));
+        IAS_CUDA(cudaEventRecord(ev_d[j], s_down));
+        return IAS_OK;
+    };
+    int rc = IAS_OK;
+    for (int k = 0; k < nchunk && rc == IAS_OK; ++k) {
+        const int r0 = k * chunk, r1 = std::min(rows, r0 + chunk);
+        if ((rc = cudaStreamWaitEvent(s, ev_up[k], 0) == cudaSuccess ? IAS_OK : IAS_E_CUDA) != IAS_OK) break;
+        k_flag_diagonals_rows<<<grid_for(r1 - r0, 256), 256, 0, s>>>(r0, r1, rows, rp.p, ci.p, flags_full.p);
+        k_fill_dia_rows<<<grid_for(r1 - r0, 256), 256, 0, s>>>(r0, r1, rows, rp.p, ci.p, v.p, flags_spec.p, slot_of.p, a_val.p, bad.p);
+        c.launches += 2;
+        if (k >= 1) rc = multiply_block(k - 1);
+    }
+    if (rc == IAS_OK) rc = multiply_block(nchunk - 1);
+    if (rc != IAS_OK) { give_up(); *have_dA = 1; return rc; }
+
+    // ---- verification of the speculation, complete features, selection
+    // (flags_full == flags_spec entry by entry, no entry fell outside the speculated diagonals)
+    {
+        k_flags_differ<<<grid_for(span + 1, 256), 256, 0, s>>>(span + 1, flags_full.p, flags_spec.p, bad.p);   // sets bad[1]
+        c.launches++;
+    }
+    int h_bad[2] = {0, 0};
+    IAS_CUDA(cudaMemcpyAsync(h_bad, bad.p, sizeof h_bad, cudaMemcpyDeviceToHost, s));
+    IAS_CUDA(cudaStreamSynchronize(s));
+    if (h_bad[0] || h_bad[1]) return give_up();
+    double *f = out->features;
+    IAS_TRY(ias_getinfo1(dA, f));
+    memcpy(f + 9, f, 9 * sizeof(double));
+    ias_getinfo2(rows, cols, nd, f + 18);
+    ias_getinfo2(rows, cols, nd, f + 21);
+    int wa = 0;
+    IAS_TRY(ias_max_row_nnz(dA, &wa));
+    ias_getinfo3(rows, nnz, std::max(wa, 1), f + 24);
+    ias_getinfo3(rows, nnz, std::max(wa, 1), f + 25);
+    const bool ell_ok = ias_sizeof_ell(rows, wa) < gate * ias_sizeof_csr(rows, nnz);
+    if (ias_select_format(f, 1, ell_ok ? 1 : 0) != 2) return give_up();
+    // diagonal_ind of C (dia:150-158) and the last copies
+    {
+        const size_t cspan = (size_t)std::max(rows + cols - 1, 1);
+        DBuf<int> c_di, c_off;
+        IAS_TRY(c_di.alloc(cspan));
+        IAS_TRY(c_off.alloc((size_t)std::max(ndc, 1)));
+        IAS_CUDA(cudaMemsetAsync(c_di.p, 0, sizeof(int) * cspan, s));
+        if (ndc) {
+            IAS_CUDA(cudaMemcpyAsync(c_off.p, h_off, sizeof(int) * (size_t)ndc, cudaMemcpyHostToDevice, s));
+            IAS_LAUNCH(k_scatter_diag_ind, grid_for(ndc, 256), 256, 0, ndc, rows, c_off.p, c_di.p);
+        }
+        IAS_CUDA(cudaMemcpyAsync(h_ind, c_di.p, sizeof(int) * cspan, cudaMemcpyDeviceToHost, s));
+        IAS_CUDA(cudaStreamSynchronize(s));
+        out->d2h_bytes = (long long)((size_t)rows * ndc * 8 + (size_t)ndc * 4 + cspan * 4);
+    }
+    IAS_CUDA(cudaStreamSynchronize(s_down));
+    IAS_CUDA(cudaStreamSynchronize(s_up));
+    out->format = 2; out->row = rows; out->col = cols;
+    out->values = h_vals; out->diagonal_offsets = h_off; out->diagonal_ind = h_ind;
+    out->num_diagonals = ndc; out->nnz = (long long)rows * ndc;
+    out->h2d_bytes = (long long)(4 * ((size_t)rows + 1) + 12 * (size_t)nnz);
+    *done = 1;
+    return IAS_OK;                                                     // rp / ci / v and the DIA operand are released by their holders
+}
+
+}  // namespace ias
 
 extern "C" {
 

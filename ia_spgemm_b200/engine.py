@@ -76,7 +76,7 @@ class AutoResult(C.Structure):         # IasAutoResult
                 ("max_nnz_per_row", C.c_int), ("nnz_row", _I),
                 ("features", C.c_double * 26),
                 ("ms_h2d", C.c_double), ("ms_select", C.c_double), ("ms_convert", C.c_double), ("ms_multiply", C.c_double),
-                ("ms_d2h", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("ms_wall", C.c_double), ("ms_host", C.c_double * 6)]
+                ("ms_d2h", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong), ("ms_wall", C.c_double), ("ms_host", C.c_double * 6), ("pipelined", C.c_int)]
 
 
 STREAM_CONSUMER = C.CFUNCTYPE(C.c_int, C.POINTER(StreamBatch), C.c_void_p)
@@ -436,7 +436,7 @@ class Engine:
         out = {"format": {1: "csr", 2: "dia", 3: "ell"}[r.format], "row": r.row, "col": r.col, "nnz": r.nnz,
                "features": np.array(r.features), "h2d_bytes": r.h2d_bytes, "d2h_bytes": r.d2h_bytes,
                "ms": {k: getattr(r, "ms_" + k) for k in ("h2d", "select", "convert", "multiply", "d2h", "wall")},
-               "host_ms_at": [round(x, 3) for x in r.ms_host]}
+               "host_ms_at": [round(x, 3) for x in r.ms_host], "pipelined": bool(r.pipelined)}
         arr = np.ctypeslib.as_array
         if r.format == 1:
             out["row_ptr"] = arr(r.row_ptr, shape=(r.row + 1,))

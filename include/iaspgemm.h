@@ -152,7 +152,7 @@ long long ias_kernel_launches(void);            /* engine kernels launched since
  * "trust_operand_cache" (see ias_forget_operand), "ell_onepass" (1 = one-pass ELL x ELL kernel where a row's products fit a
  * warp's register sort, 0 = always the pipeline), "g_block" (1024 / 512 threads per CTA of the L2 kernel), "g_ldca", "g_v2" (1 = second generation of the L2 kernel: rank + emit
  * from shared memory, split tables), "g_tbl" (its split-table capacity), "g_lpt" (1 = global rows in order of decreasing work), "g_scr" (per-CTA global scratch, in ints, for the split
- * tables of rows with more than 1024 A entries), "g2_takes_b2" (rows of the large CTA hash go to that kernel), "bulk_store" (1 = cp.async.bulk copy-out of staged tiles),
+ * tables of rows with more than 1024 A entries), "g2_takes_b2" (rows of the large CTA hash go to that kernel), "e2e_pipeline" (see ias_spgemm_auto_host), "bulk_store" (1 = cp.async.bulk copy-out of staged tiles),
  * "dia_vec" (1 = 128-bit DIA kernel).  Also read from
  * IAS_OPT_<NAME> in the environment by ias_init.  Results do not depend on any of them. */
 int ias_set_option(const char *name, long long value);
@@ -348,7 +348,11 @@ int ias_select_format(const double *features26, int dia_ok, int ell_ok);
  *                     format 2 DIA   diagonal_ind[row+col-1], diagonal_offsets[num_diagonals],
  *                                    values[row][num_diagonals] row-major                  (DIA_mul_DIA, dia:101)
  *                     format 3 ELL   nnz_row[row], col_ind / values [row][max_nnz_per_row] (ELL_MUL_ELL, ell:80)
- * matnet: handle from ias_matnet_load (a 5-class net drives the dispatch) or NULL for the rule; gate: 20 (GPU release). */
+ * matnet: handle from ias_matnet_load (a 5-class net drives the dispatch) or NULL for the rule; gate: 20 (GPU release).
+ * For A*A of a banded operand (B aliases A, rule selection) the call overlaps the PCIe upload of A's row chunks, the DIA
+ * multiply of the blocks already there and the download of finished blocks of C: the diagonal set is taken from the
+ * first chunk and verified against the whole operand afterwards, with a fall-back to the plain sequence
+ * (option "e2e_pipeline" = 0 disables it). */
 typedef struct {
     int format;
     int row, col;
@@ -365,6 +369,7 @@ typedef struct {
     long long h2d_bytes, d2h_bytes;
     double ms_wall;                /* host wall clock of the whole call */
     double ms_host[6];             /* host wall clock at: upload done, selection done, conversion done, multiply done, download done, buffers released */
+    int pipelined;                 /* 1: upload, multiply and download were overlapped chunk by chunk (banded A^2; the ms_* phases are then 0) */
 } IasAutoResult;
 int ias_spgemm_auto_host(const IasCsrMatrix *A, const IasCsrMatrix *B, double gate, void *matnet, IasAutoResult *out);
 

@@ -505,3 +505,51 @@ def test_dia_vectorised_kernel_equals_scalar(eng, make, rows):
     assert np.array_equal(out[1]["diagonal_offsets"], out[0]["diagonal_offsets"])
     assert np.array_equal(out[1]["values"], out[0]["values"])
     eng.free_dia(d); dA.close()
+
+
+def test_auto_host_pipelined_banded_square(eng, oracle):
+    """ias_spgemm_auto_host on a banded A^2 overlaps upload / DIA multiply / download chunk by chunk, taking the diagonal
+    set from the first chunk and verifying it afterwards.  Same result as the plain sequence, bit for bit; an operand
+    that breaks the speculation (a stray entry in a later chunk, a band wider than a chunk) falls back and is still right."""
+    A = W.poisson2d(300)                                   # 90 000 rows: above the pipelining threshold
+    r1 = eng.spgemm_auto(A, A)
+    assert r1["format"] == "dia" and r1["pipelined"] and r1["num_diagonals"] == 13
+    v1, o1, i1 = r1["values"].copy(), r1["diagonal_offsets"].copy(), r1["diagonal_ind"].copy()
+    eng.set_option("e2e_pipeline", 0)
+    r0 = eng.spgemm_auto(A, A)
+    eng.set_option("e2e_pipeline", 1)
+    assert r0["format"] == "dia" and not r0["pipelined"]
+    assert np.array_equal(v1, r0["values"]) and np.array_equal(o1, r0["diagonal_offsets"]) and np.array_equal(i1, r0["diagonal_ind"])
+    wa = oracle.csr_to_dia(*A, gate=20.0)
+    want = oracle.dia_mul_dia(wa, wa)
+    assert np.array_equal(o1, want["diagonal_offsets"]) and np.array_equal(i1, want["diagonal_ind"])
+    absa = dict(wa, values=np.abs(wa["values"]))
+    assert _close(v1, want["values"], scale=oracle.dia_mul_dia(absa, absa)["values"])
+    assert np.allclose(r1["features"], oracle.features26(A, A, gate=20.0), rtol=1e-12)
+    # a stray entry far from the band in the last rows: not in the first chunk's diagonal set -> verified, refused, redone
+    rows, cols, rp, ci, v = A
+    rp2 = rp.copy(); rp2[-1] += 1
+    ci2 = np.concatenate((ci[:rp[-2]], [7], ci[rp[-2]:])).astype(np.int32)       # row rows-1 gets column 7 in front (sorted)
+    v2 = np.concatenate((v[:rp[-2]], [0.25], v[rp[-2]:]))
+    A2 = (rows, cols, rp2, ci2, v2)
+    r2 = eng.spgemm_auto(A2, A2)
+    assert not r2["pipelined"]
+    want2 = oracle.csr_mul_csr(rows, cols, rp2, ci2, v2, rp2, ci2, v2)
+    if r2["format"] == "csr":
+        assert_csr_parity((r2["row_ptr"].copy(), r2["col_ind"].copy(), r2["values"].copy()), want2, mag=abs_product(oracle, A2, A2))
+    else:
+        w2 = oracle.csr_to_dia(*A2, gate=20.0)
+        d2 = oracle.dia_mul_dia(w2, w2)
+        assert r2["format"] == "dia" and np.array_equal(r2["diagonal_offsets"], d2["diagonal_offsets"])
+        ab2 = dict(w2, values=np.abs(w2["values"]))
+        assert _close(r2["values"], d2["values"], scale=oracle.dia_mul_dia(ab2, ab2)["values"])
+    # a band wider than a chunk: plausible first chunk, but block k would need rows that are not converted yet
+    Wd = W.banded(70000, [-40000, 0, 3], seed=4)
+    r3 = eng.spgemm_auto(Wd, Wd)
+    assert not r3["pipelined"]
+    want3 = oracle.csr_mul_csr(Wd[0], Wd[1], Wd[2], Wd[3], Wd[4], Wd[2], Wd[3], Wd[4])
+    if r3["format"] == "csr":
+        assert_csr_parity((r3["row_ptr"].copy(), r3["col_ind"].copy(), r3["values"].copy()), want3)
+    else:
+        assert r3["format"] == "dia" and float(r3["values"].sum()) == pytest.approx(float(want3[2].sum()), rel=1e-11)
+    eng.lib.ias_release_host()
