@@ -3,6 +3,7 @@
 
 #include <vector>
 
+#define IAS_TU tu_csr
 #include "spgemm_host.cuh"
 
 using namespace ias;

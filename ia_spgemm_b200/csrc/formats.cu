@@ -14,6 +14,7 @@
 // followed by a row-index expansion of the result.
 #include <algorithm>
 
+#define IAS_TU tu_formats
 #include "spgemm_host.cuh"
 
 using namespace ias;
@@ -197,7 +198,8 @@ __global__ void __launch_bounds__(BLOCK) k_ell_mul_ell(int nrows, EllView A, Ell
 #pragma unroll
         for (int r = 0; r < IPL; ++r) {
             key[r] = cc[r] >= 0 ? (((KeyT)(unsigned)cc[r] << IDX_BITS) | (KeyT)(e0 + r)) : PAD;
-            svals[e0 + r] = av * vv[r];
+            svals[r * 32 + lane] = av * vv[r];         // slot e = lane * IPL + r lives at r * 32 + lane: conflict-free stores
+                                                       // (lane-major [e] made every store a 16-way bank conflict: ncu 2.3 G conflicts)
         }
         __syncwarp();
         warp_sort_runs<KeyT, IPL>(key, lane, sorted_runs ? (1 << log2_run) : 1);
@@ -227,7 +229,8 @@ __global__ void __launch_bounds__(BLOCK) k_ell_mul_ell(int nrows, EllView A, Ell
             const bool valid = key[r] != PAD;
             const KeyT prv = r > 0 ? key[r - 1] : prev_last;
             head[r] = valid && ((r == 0 && lane == 0) || (prv >> IDX_BITS) != (key[r] >> IDX_BITS));
-            v[r] = valid ? svals[(unsigned)(key[r] & IDX_MASK)] : 0.0;
+            const unsigned e = (unsigned)(key[r] & IDX_MASK);
+            v[r] = valid ? svals[(e % IPL) * 32 + e / IPL] : 0.0;
             tail_sum = head[r] ? v[r] : tail_sum + v[r];
             any_head |= head[r];
         }

@@ -10,6 +10,10 @@
 #include "spgemm_kernels.cuh"
 
 namespace ias {
+// Every translation unit that includes the pipeline gets its OWN copy of the kernels (IAS_TU is defined by the .cu file):
+// identical template instantiations in two units would otherwise be merged by the linker, and the phase-clock build
+// (make prof) would read the counters of the copy that lost.
+inline namespace IAS_TU {
 
 constexpr int TINY_BLOCK = 128;
 constexpr int G_BLOCK = 512;
@@ -633,4 +637,5 @@ int spgemm_materialise(const AV &av, const BV &bv, double avg_a_row, int ncols_b
     return IAS_OK;
 }
 
+}  // inline namespace IAS_TU
 }  // namespace ias

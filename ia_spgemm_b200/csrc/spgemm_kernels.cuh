@@ -34,6 +34,10 @@
 #include "common.cuh"
 
 namespace ias {
+// Every translation unit that includes the pipeline gets its OWN copy of the kernels (IAS_TU is defined by the .cu file):
+// identical template instantiations in two units would otherwise be merged by the linker, and the phase-clock build
+// (make prof) would read the counters of the copy that lost.
+inline namespace IAS_TU {
 
 enum { BIN_EMPTY = 0, BIN_T = 1, BIN_W = 2, BIN_B1 = 3, BIN_B2 = 4, BIN_G = 5, NBINS = 6 };
 
@@ -1454,6 +1458,24 @@ __global__ void __launch_bounds__(BLOCK) k_num_global(const int *__restrict__ ro
 //   * keeps the A row's entries (B row start, length, A value) in registers for rows of at most BLOCK entries.
 // Rows with more than BLOCK entries in A, or whose tables do not fit, take the per-window searches of the first
 // generation.  Dynamic shared memory: win doubles (accumulate tile, also the mark bitmap) + tbl_cap ints.
+// four independent binary searches per thread in lock step (a single search is a chain of dependent L2 loads; the
+// split tables need thousands of them per row): lo[u] = first index in [0, len[u]) of ci + b[u] with column >= c[u]
+template <class BV>
+__device__ __forceinline__ void lower_bound4(const BV &B, const typename BV::off_t (&b)[4], const int (&len)[4], const int (&c)[4], int (&lo)[4])
+{
+    int hi[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) { lo[u] = 0; hi[u] = len[u]; }
+    while ((lo[0] < hi[0]) | (lo[1] < hi[1]) | (lo[2] < hi[2]) | (lo[3] < hi[3])) {
+        int mid[4], k[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { mid[u] = (lo[u] + hi[u]) >> 1; k[u] = lo[u] < hi[u] ? __ldg(B.ci + b[u] + mid[u]) : 0; }
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (lo[u] < hi[u]) { if (k[u] < c[u]) lo[u] = mid[u] + 1; else hi[u] = mid[u]; }
+    }
+}
+
 constexpr int G2_MAX_BND = 512;          // window boundaries kept in shared memory (rows beyond read them from c_ci)
 
 template <class AV, class BV, int BLOCK>
@@ -1523,24 +1545,26 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
         auto long_table = [&](int K, auto boundary) {                 // gt[k * n_a + e], k = 0 .. K; boundary(k) = column of boundary k
             for (int e = tid; e < n_a; e += BLOCK) { gt[e] = 0; gt[(size_t)K * n_a + e] = __ldcg(glen + e); }
             const int items = n_a * (K - 1);
-            for (int it = tid; it < items; it += 2 * BLOCK) {
-                const int it1 = it + BLOCK;
-                const bool two = it1 < items;
-                const int k0 = it / n_a + 1, e0 = it - (k0 - 1) * n_a;
-                const int k1 = two ? it1 / n_a + 1 : k0, e1 = two ? it1 - (k1 - 1) * n_a : e0;
-                const int x0 = __ldcg(gx + e0), x1 = __ldcg(gx + e1);
-                const boff b0 = QB32 ? (boff)x0 : B.begin(x0), b1 = QB32 ? (boff)x1 : B.begin(x1);
-                const int c0 = boundary(k0), c1 = boundary(k1);
-                int lo0 = 0, hi0 = __ldcg(glen + e0), lo1 = 0, hi1 = two ? __ldcg(glen + e1) : 0;
-                while (lo0 < hi0 || lo1 < hi1) {
-                    const int m0 = (lo0 + hi0) >> 1, m1 = (lo1 + hi1) >> 1;
-                    const int v0 = lo0 < hi0 ? __ldg(B.ci + b0 + m0) : 0;
-                    const int v1 = lo1 < hi1 ? __ldg(B.ci + b1 + m1) : 0;
-                    if (lo0 < hi0) { if (v0 < c0) lo0 = m0 + 1; else hi0 = m0; }
-                    if (lo1 < hi1) { if (v1 < c1) lo1 = m1 + 1; else hi1 = m1; }
+            for (int it0 = tid; it0 < items; it0 += 4 * BLOCK) {
+                boff b[4];
+                int len[4], cc[4], lo[4];
+                size_t slot[4];
+                bool on[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int it = it0 + u * BLOCK;
+                    b[u] = 0; len[u] = 0; cc[u] = 0; slot[u] = 0; on[u] = it < items;
+                    if (on[u]) {
+                        const int k = it / n_a + 1, e = it - (k - 1) * n_a;
+                        const int x = __ldcg(gx + e);
+                        b[u] = QB32 ? (boff)x : B.begin(x);
+                        len[u] = __ldcg(glen + e); cc[u] = boundary(k); slot[u] = (size_t)k * n_a + e;
+                    }
                 }
-                gt[(size_t)k0 * n_a + e0] = lo0;
-                if (two) gt[(size_t)k1 * n_a + e1] = lo1;
+                lower_bound4(B, b, len, cc, lo);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (on[u]) gt[slot[u]] = lo[u];
             }
             __syncthreads();
         };
@@ -1569,13 +1593,22 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
             tile.incl[tid] = my_len;
             __syncthreads();
             const int items = n_a * (nsw - 1);
-            for (int it = tid; it < items; it += BLOCK) {
-                const int e = it / (nsw - 1), k = it - e * (nsw - 1) + 1;
-                const boff b = tile.rel[e];
-                const int c = (int)(k * span);
-                int lo = 0, hi = tile.incl[e];
-                while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(B.ci + b + mid) < c) lo = mid + 1; else hi = mid; }
-                tbl[e * mstride + k] = lo;
+            for (int it0 = tid; it0 < items; it0 += 4 * BLOCK) {
+                boff b[4];
+                int len[4], cc[4], lo[4], slot[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int it = it0 + u * BLOCK;
+                    b[u] = 0; len[u] = 0; cc[u] = 0; slot[u] = -1;
+                    if (it < items) {
+                        const int e = it / (nsw - 1), k = it - e * (nsw - 1) + 1;
+                        b[u] = tile.rel[e]; len[u] = tile.incl[e]; cc[u] = (int)(k * span); slot[u] = e * mstride + k;
+                    }
+                }
+                lower_bound4(B, b, len, cc, lo);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (slot[u] >= 0) tbl[slot[u]] = lo[u];
             }
             if (tid < n_a) { tbl[tid * mstride] = 0; tbl[tid * mstride + nsw] = my_len; }
             __syncthreads();
@@ -1708,13 +1741,22 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
             tile.incl[tid] = my_len;
             __syncthreads();
             const int items = n_a * (W - 1);
-            for (int it = tid; it < items; it += BLOCK) {
-                const int e = it / (W - 1), k = it - e * (W - 1) + 1;
-                const boff b = tile.rel[e];
-                const int c = s_bnd[k];
-                int lo = 0, hi = tile.incl[e];
-                while (lo < hi) { int mid = (lo + hi) >> 1; if (__ldg(B.ci + b + mid) < c) lo = mid + 1; else hi = mid; }
-                tbl[e * astride + k] = lo;
+            for (int it0 = tid; it0 < items; it0 += 4 * BLOCK) {
+                boff b[4];
+                int len[4], cc[4], lo[4], slot[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int it = it0 + u * BLOCK;
+                    b[u] = 0; len[u] = 0; cc[u] = 0; slot[u] = -1;
+                    if (it < items) {
+                        const int e = it / (W - 1), k = it - e * (W - 1) + 1;
+                        b[u] = tile.rel[e]; len[u] = tile.incl[e]; cc[u] = s_bnd[k]; slot[u] = e * astride + k;
+                    }
+                }
+                lower_bound4(B, b, len, cc, lo);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (slot[u] >= 0) tbl[slot[u]] = lo[u];
             }
             if (tid < n_a) { tbl[tid * astride] = 0; tbl[tid * astride + W] = my_len; }
         }
@@ -2195,4 +2237,5 @@ static __global__ void k_batch_bounds(int nrows, const long long *__restrict__ r
     *nb = (start >= nrows) ? b : -1;
 }
 
+}  // inline namespace IAS_TU
 }  // namespace ias
