@@ -306,9 +306,15 @@ class Bench:
         """W untimed steps, then exactly `steps` steps between CUDA events on the engine's stream, barrier +
         synchronize on both sides, max over ranks.  Returns (ms per step, list of per-step stats, launches, warm-ups run)."""
         torch, dist = self.torch, self.dist
-        t_warm, n_warm = time.perf_counter(), 0
-        while n_warm < warmup or (time.perf_counter() - t_warm < min_warm_s and n_warm < max_warm):
+        # warm-up: at least `warmup` steps and min_warm_s, and until two consecutive steps take the same time within 10 %
+        # (the first multiplies of a problem size grow the device pool; a step's C call returns synchronised)
+        t_warm, n_warm, prev, stable = time.perf_counter(), 0, None, False
+        while n_warm < warmup or ((time.perf_counter() - t_warm < min_warm_s or not stable) and n_warm < max_warm):
+            t1 = time.perf_counter()
             step()
+            dt = time.perf_counter() - t1
+            stable = prev is not None and abs(dt - prev) <= 0.1 * max(dt, prev)
+            prev = dt
             n_warm += 1
         torch.cuda.synchronize()
         if self.world > 1:
@@ -413,6 +419,7 @@ class Bench:
                 "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / self.peak,
                 "note": "rank 0's rows" if self.world > 1 else "the whole job"}
         cfg = {"streaming_batches": st.get("batches", 1), "warmup_steps_run": n_warm,
+               "engine_ms_per_call": [round(float(x.get("ms_total", 0.0)), 3) for x in stats],      # the C call's own event timing, every step
                "phase_ms": {k: float(np.mean([s.get(k, 0.0) for s in stats])) for k in ("ms_analyze", "ms_symbolic", "ms_scan", "ms_numeric")},
                "bins": BINS, "num_bin_rows": st.get("num_bin_rows"), "sym_bin_rows": st.get("sym_bin_rows"),
                "ms_bin_sym": [round(float(np.mean([s["ms_bin_sym"][b] for s in stats])), 4) for b in range(6)],
@@ -439,7 +446,8 @@ class Bench:
                 "frac": achieved / self.peak, "traffic": self.traffic(wname, "k_dia_mul_dia"), "peak_source": self.peak_src,
                 "kernel_ms": kern_ms, "algorithmic_bytes": alg_bytes, "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / self.peak}
         return {"ms_per_step": ms_step, "value": 2.0 * products / (ms_step * 1e6), "unit": "GFLOP/s", "products": products,
-                "c_diagonals": nd_c, "roofline": roof, "launches": launches_all, "detail": {"warmup_steps_run": n_warm}}
+                "c_diagonals": nd_c, "roofline": roof, "launches": launches_all,
+                "detail": {"warmup_steps_run": n_warm, "engine_ms_per_call": [round(float(x["ms_total"]), 3) for x in stats]}}
 
     def ell_leg(self, dA, rows, products, steps, warmup, wname):
         eng = self.eng
@@ -466,7 +474,7 @@ class Bench:
                 "algorithmic_bytes": alg_bytes, "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / self.peak}
         return {"ms_per_step": ms_step, "value": 2.0 * products / (ms_step * 1e6), "unit": "GFLOP/s", "products": products,
                 "nnz_C": st["nnz"], "c_width": st["c_width"], "trans_ms": trans_ms, "roofline": roof, "launches": launches,
-                "detail": {"warmup_steps_run": n_warm}}
+                "detail": {"warmup_steps_run": n_warm, "engine_ms_per_call": [round(float(x["ms_total"]), 3) for x in stats]}}
 
     # -- e2e ------------------------------------------------------------------------------------------
     def pinned_host_copy(self, dA):
@@ -656,6 +664,25 @@ def main():
         d = eng.wrap_device(rows, cols, int(t_ci.numel()), t_rp.data_ptr(), t_ci.data_ptr(), t_v.data_ptr())
         d._keep = (t_rp, t_ci, t_v)
         return d, float(t.item())
+
+    if args.impl == "cusparse":
+        # the same-box GPU library bar as its own arm: cusparseSpGEMM on the same device operand (one GPU)
+        if rank == 0:
+            kind = args.workload
+            kw = dict(grid=args.grid, world=1, n=args.n, scale=args.scale)
+            dA = make_operand(eng, kind, **kw)
+            products = eng.GetFlop(dA, dA)
+            r = B.cusparse_leg(dA, products, steps=max(2, min(args.steps, 5)))
+            dA.close()
+            sampler.stop()
+            emit({"impl": "cusparse", "metric": METRIC, "value": r.get("value"), "unit": "GFLOP/s", "n_gpus": 1, "steps": args.steps,
+                  "warmup": args.warmup, "ms_per_step": r.get("ms_per_step"), "higher_is_better": True, "scaling": "n/a (one GPU)",
+                  "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                  "config": {"workload": workload_name(kind, **kw), "description": describe(kind, **kw), "api": r.get("api"), "error": r.get("error")},
+                  "gpu_launches": 0})
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ================================================================== main leg
     kind = args.workload
