@@ -784,7 +784,9 @@ def main():
             also["uniform"] = side_config(B, eng, "uniform", args, with_cpu=not args.no_cpu, with_cusparse=not args.no_cusparse)
             also["rmat22"] = side_config(B, eng, "rmat", args, with_cpu=not args.no_cpu, with_cusparse=not args.no_cusparse)
         else:
+            sampler.pause()              # NVML polling of GPU 0 during a multi-rank timed leg would single out rank 0
             also["rmat22_strong"] = strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world)
+            sampler.resume()
 
     clocks = None
     if rank == 0:
