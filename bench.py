@@ -83,6 +83,12 @@ class ClockSampler:
         self.rows, self.proc, self.index = [], None, index
 
     def start(self):
+        self.mode = os.environ.get("IAS_BENCH_CLOCKS", "nvml")
+        if self.mode == "off":
+            return
+        if self.mode == "nvml" and self._start_nvml():
+            return
+        self.mode = "smi"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "100"],
@@ -96,20 +102,57 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append((time.perf_counter(), line.strip().split(", ")))
 
+    def _start_nvml(self):
+        """The same fields read in-process through NVML every 100 ms (what `nvidia-smi --query-gpu -lms 100` prints):
+        no child process attaching to the driver ten times a second beside the timed calls."""
+        try:
+            import pynvml as nv
+            import torch
+            nv.nvmlInit()
+            try:
+                h = nv.nvmlDeviceGetHandleByUUID("GPU-" + str(torch.cuda.get_device_properties(self.index).uuid))
+            except Exception:
+                h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            bits = (("hw_slowdown", nv.nvmlClocksThrottleReasonHwSlowdown), ("hw_thermal_slowdown", nv.nvmlClocksThrottleReasonHwThermalSlowdown),
+                    ("sw_thermal_slowdown", nv.nvmlClocksThrottleReasonSwThermalSlowdown), ("sw_power_cap", nv.nvmlClocksThrottleReasonSwPowerCap))
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+        except Exception:
+            return False
+        self.proc, self.paused, self.quit = "nvml", False, False
+
+        def poll():
+            while not self.quit:
+                if not self.paused:
+                    try:
+                        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                        row = [str(nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)), str(nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)),
+                               "%.1f" % (nv.nvmlDeviceGetPowerUsage(h) / 1000.0)] + ["Active" if r & b else "Not Active" for _, b in bits]
+                        self.rows.append((time.perf_counter(), row))
+                    except Exception:
+                        pass
+                time.sleep(0.1)
+        self.thread = threading.Thread(target=poll, daemon=True)
+        self.thread.start()
+        return True
+
     def mark(self):
         return time.perf_counter()
 
     def pause(self):
         """Stop polling while host-heavy legs run (e2e, CPU baseline): frequent NVML queries serialise with the many
         small driver calls of those paths; the clocks record is about the device-timed region."""
-        if self.proc:
+        if self.proc == "nvml":
+            self.paused = True
+        elif self.proc:
             try:
                 self.proc.send_signal(19)       # SIGSTOP
             except Exception:
                 pass
 
     def resume(self):
-        if self.proc:
+        if self.proc == "nvml":
+            self.paused = False
+        elif self.proc:
             try:
                 self.proc.send_signal(18)       # SIGCONT
             except Exception:
@@ -118,7 +161,7 @@ class ClockSampler:
     def summary(self, t0=None, t1=None):
         """Clocks seen between two marks (the whole run when omitted)."""
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["clock sampling unavailable or off"]}
         sm, mx, reasons = [], [], set()
         for t, r in list(self.rows):
             if (t0 is not None and t < t0) or (t1 is not None and t > t1):
@@ -131,10 +174,14 @@ class ClockSampler:
             except Exception:
                 pass
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "samples": len(sm), "reasons": sorted(reasons)}
+                "samples": len(sm), "reasons": sorted(reasons),
+                "source": "NVML in-process, 100 ms" if self.proc == "nvml" else "nvidia-smi --query-gpu -lms 100"}
 
     def stop(self):
-        if self.proc:
+        if self.proc == "nvml":
+            self.quit = True
+            self.thread.join(timeout=2)
+        elif self.proc:
             self.resume()
             self.proc.terminate()
             self.thread.join(timeout=2)

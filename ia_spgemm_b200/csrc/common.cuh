@@ -1,6 +1,9 @@
 // common.cuh -- engine context, error handling and small device helpers shared by all kernels.
 #pragma once
 #include <cuda_runtime.h>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
@@ -33,6 +36,8 @@ struct Tuning {
     long long dia_vec = 0;            // DIA x DIA: two adjacent rows per thread with 128-bit accesses -- measured SLOWER than the scalar
                                       // kernel on B200 (0.617 vs 0.542 ms on Poisson 4096^2), kept for the record
     long long ell_onepass = 1;        // ELL x ELL: one-pass register-sort kernel when a row's products fit (0: always the pipeline)
+    long long block_cache = 1;        // freed device blocks are kept per size class and handed out again without a driver call (0: every
+                                      // allocation goes to the stream-ordered pool, whose re-mapping blocks the caller for milliseconds)
     long long trust_operand_cache = 0; // 1: remember B's canonical flag per operand (pointers + shape) across calls; the caller
                                       // promises not to rewrite or re-allocate an operand without ias_forget_operand
 };
@@ -64,6 +69,10 @@ struct Ctx {
 };
 
 Ctx &ctx();
+int device_block(void **p, size_t bytes);       // stream-ordered device memory on ctx().stream: block cache first, then the pool
+void device_block_free(void *p);
+void block_cache_flush();                       // cached blocks go back to the pool (the caller synchronised the stream)
+size_t free_device_bytes();                     // what an allocation could get: free + the pool's idle reserve + cached blocks
 int host_arena(size_t bytes, void **p);        // pinned host memory owned by the engine (grow only; ias_release_host frees it)
 int ensure_pipe_streams();
 // DIA helpers shared with the auto path (dia.cu)
@@ -94,23 +103,31 @@ int ensure_init();
         if (le__ != cudaSuccess) return ias::fail_cuda(le__, #kernel, __FILE__, __LINE__); \
     } while (0)
 
+// IAS_HOST_TRACE=1: report (stderr) every allocation, free or stream wait that blocks the calling thread for more than 2 ms
+struct HostTrace {
+    const char *what; size_t bytes; std::chrono::steady_clock::time_point t0; bool on;
+    static bool enabled() { static int e = -1; if (e < 0) { const char *v = getenv("IAS_HOST_TRACE"); e = (v && *v && *v != '0') ? 1 : 0; } return e == 1; }
+    HostTrace(const char *w, size_t b) : what(w), bytes(b), on(enabled()) { if (on) t0 = std::chrono::steady_clock::now(); }
+    void done()
+    {
+        if (!on) return;
+        double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+        if (ms > 2.0) fprintf(stderr, "[ias host trace] %s (%zu bytes) blocked the caller for %.1f ms\n", what, bytes, ms);
+    }
+};
+
 // stream-ordered allocation from the engine pool (no cudaMalloc+cudaMemset per call like DevMalloc)
 template <class T>
 inline int dalloc(T **p, size_t n)
 {
     *p = nullptr;
     if (n == 0) n = 1;
-    cudaError_t e = cudaMallocFromPoolAsync((void **)p, n * sizeof(T), ctx().pool, ctx().stream);
-    if (e != cudaSuccess) {
-        cudaGetLastError();
-        return fail(IAS_E_NOMEM, "device allocation of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(e));
-    }
-    return IAS_OK;
+    return device_block((void **)p, n * sizeof(T));
 }
 template <class T>
 inline void dfree(T *p)
 {
-    if (p) cudaFreeAsync((void *)p, ctx().stream);
+    if (p) device_block_free((void *)p);
 }
 
 // RAII holder for temporaries inside one API call

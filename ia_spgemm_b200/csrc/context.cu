@@ -2,6 +2,11 @@
 #include <stdarg.h>
 #include <stdlib.h>
 
+#include <algorithm>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
 #include <cub/cub.cuh>
 
 #include "common.cuh"
@@ -53,6 +58,145 @@ int host_arena(size_t bytes, void **p)
     return IAS_OK;
 }
 
+// ---------------------------------------------------------------- device block cache
+// The stream-ordered pool alone is not enough: with differently sized requests in flight it re-maps physical memory
+// inside cudaMallocFromPoolAsync, and that blocks the calling thread for 2..700 ms at a time (IAS_HOST_TRACE=1 shows
+// it; profiles/r02_alloc_stalls.md).  A multiply repeats the same request sizes call after call, so freed blocks are
+// kept here per size class (4 mantissa bits: at most 6.25 % larger than asked) and handed out again without a driver
+// call.  Ordering is the stream's: every engine allocation and free belongs to ctx().stream (a block freed while its
+// last kernel is still queued is only ever given to work queued behind it on the same stream; ias_set_stream
+// synchronises when the stream changes).  Cached bytes are capped at half the device; when the pool cannot serve a
+// request the cache is emptied into it and the request retried.
+namespace {
+struct SizeClass {
+    std::vector<void *> idle;
+    unsigned long long last_use = 0;
+};
+struct BlockCache {
+    std::mutex mu;
+    std::unordered_map<size_t, SizeClass> classes;             // size class -> idle blocks of that size
+    std::unordered_map<void *, size_t> live;                   // block -> its size class (handed out or idle)
+    unsigned long long tick = 0;
+    size_t idle_bytes = 0;
+    size_t cap_bytes = 0;
+} g_blocks;
+
+size_t size_class(size_t bytes)
+{
+    if (bytes < 512) return 512;
+    int top = 63 - __builtin_clzll((unsigned long long)bytes);
+    size_t step = (size_t)1 << (top - 4);
+    return (bytes + step - 1) & ~(step - 1);
+}
+
+// idle blocks go back to the pool, least recently used size class first, until at most keep_bytes stay cached
+void evict_locked(size_t keep_bytes)
+{
+    BlockCache &b = g_blocks;
+    if (b.idle_bytes <= keep_bytes) return;
+    std::vector<std::pair<unsigned long long, size_t>> by_age;
+    for (std::unordered_map<size_t, SizeClass>::iterator it = b.classes.begin(); it != b.classes.end(); ++it)
+        if (!it->second.idle.empty()) by_age.push_back(std::make_pair(it->second.last_use, it->first));
+    std::sort(by_age.begin(), by_age.end());
+    for (size_t k = 0; k < by_age.size() && b.idle_bytes > keep_bytes; ++k) {
+        SizeClass &sc = b.classes[by_age[k].second];
+        while (!sc.idle.empty() && b.idle_bytes > keep_bytes) {
+            void *q = sc.idle.back();
+            sc.idle.pop_back();
+            b.live.erase(q);
+            b.idle_bytes -= by_age[k].second;
+            cudaFreeAsync(q, g_ctx.stream);
+        }
+    }
+}
+}  // namespace
+
+int device_block(void **p, size_t bytes)
+{
+    Ctx &c = g_ctx;
+    BlockCache &b = g_blocks;
+    const bool cached = c.tune.block_cache != 0;
+    const size_t cls = cached ? size_class(bytes) : bytes;
+    if (cached) {
+        std::lock_guard<std::mutex> g(b.mu);
+        std::unordered_map<size_t, SizeClass>::iterator it = b.classes.find(cls);
+        if (it != b.classes.end() && !it->second.idle.empty()) {
+            *p = it->second.idle.back();
+            it->second.idle.pop_back();
+            it->second.last_use = ++b.tick;
+            b.idle_bytes -= cls;
+            return IAS_OK;
+        }
+    }
+    HostTrace ht("cudaMallocFromPoolAsync", cls);
+    cudaError_t e = cudaMallocFromPoolAsync(p, cls, c.pool, c.stream);
+    if (e != cudaSuccess && b.idle_bytes) {                    // the memory may be sitting in the cache in other size classes
+        cudaGetLastError();
+        cudaStreamSynchronize(c.stream);
+        block_cache_flush();
+        e = cudaMallocFromPoolAsync(p, cls, c.pool, c.stream);
+    }
+    ht.done();
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        *p = nullptr;
+        return fail(IAS_E_NOMEM, "device allocation of %zu bytes failed: %s", bytes, cudaGetErrorString(e));
+    }
+    if (cached) {
+        std::lock_guard<std::mutex> g(b.mu);
+        b.live[*p] = cls;
+    }
+    return IAS_OK;
+}
+
+void device_block_free(void *p)
+{
+    if (!p) return;
+    Ctx &c = g_ctx;
+    BlockCache &b = g_blocks;
+    {
+        std::lock_guard<std::mutex> g(b.mu);
+        std::unordered_map<void *, size_t>::iterator it = b.live.find(p);
+        if (it != b.live.end()) {
+            if (c.tune.block_cache != 0) {
+                if (!b.cap_bytes) {
+                    size_t f = 0, t = 0;
+                    b.cap_bytes = cudaMemGetInfo(&f, &t) == cudaSuccess ? t / 2 : (size_t)64 << 30;
+                }
+                SizeClass &sc = b.classes[it->second];
+                sc.idle.push_back(p);
+                sc.last_use = ++b.tick;
+                b.idle_bytes += it->second;
+                if (b.idle_bytes > b.cap_bytes) evict_locked(b.cap_bytes);
+                return;
+            }
+            b.live.erase(it);
+        }
+    }
+    HostTrace ht("cudaFreeAsync", 0);
+    cudaFreeAsync(p, c.stream);
+    ht.done();
+}
+
+void block_cache_flush()
+{
+    std::lock_guard<std::mutex> g(g_blocks.mu);
+    evict_locked(0);
+}
+
+size_t free_device_bytes()
+{
+    size_t f = 0, t = 0;
+    if (cudaMemGetInfo(&f, &t) != cudaSuccess) { cudaGetLastError(); return 0; }
+    unsigned long long reserved = 0, used = 0;
+    if (g_ctx.pool && cudaMemPoolGetAttribute(g_ctx.pool, cudaMemPoolAttrReservedMemCurrent, &reserved) == cudaSuccess &&
+        cudaMemPoolGetAttribute(g_ctx.pool, cudaMemPoolAttrUsedMemCurrent, &used) == cudaSuccess && reserved > used)
+        f += (size_t)(reserved - used);
+    else
+        cudaGetLastError();
+    return f + g_blocks.idle_bytes;
+}
+
 int ensure_pipe_streams()
 {
     Ctx &c = g_ctx;
@@ -98,6 +242,7 @@ static long long *option_slot(const char *name)
     if (!strcmp(name, "g_lpt")) return &t.g_lpt;
     if (!strcmp(name, "g_scr")) return &t.g_scr;
     if (!strcmp(name, "g2_takes_b2")) return &t.g2_takes_b2;
+    if (!strcmp(name, "block_cache")) return &t.block_cache;
     return nullptr;
 }
 
@@ -114,7 +259,14 @@ int ias_init(int device)
     if (device < 0 || device >= n) return fail(IAS_E_ARG, "device %d out of range (have %d)", device, n);
     IAS_CUDA(cudaSetDevice(device));
     if (c.ready && c.device != device) {
-        // re-bound to another device: streams and events belong to the device they were created on
+        // re-bound to another device: streams, events and cached blocks belong to the device they were created on
+        {
+            int now = device;
+            cudaSetDevice(c.device);
+            cudaStreamSynchronize(c.stream);
+            block_cache_flush();
+            cudaSetDevice(now);
+        }
         if (c.own_stream) cudaStreamDestroy(c.own_stream);
         c.own_stream = nullptr;
         for (int i = 0; i < 8; ++i) { if (c.ev[i]) cudaEventDestroy(c.ev[i]); c.ev[i] = nullptr; }
@@ -143,7 +295,7 @@ int ias_init(int device)
         if (!c.ev_bin[i]) IAS_CUDA(cudaEventCreate(&c.ev_bin[i]));
     if (!c.h_scalars) IAS_CUDA(cudaMallocHost((void **)&c.h_scalars, 64 * sizeof(long long)));
     static const char *const names[] = {"global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win", "g_coop", "gwin_takes_b2",
-                                        "trust_operand_cache", "g_ldca", "g_block", "ell_onepass", "g_v2", "g_tbl", "g_lpt", "bulk_store", "dia_vec", "g_scr", "g2_takes_b2", "e2e_pipeline"};
+                                        "trust_operand_cache", "g_ldca", "g_block", "ell_onepass", "g_v2", "g_tbl", "g_lpt", "bulk_store", "dia_vec", "g_scr", "g2_takes_b2", "e2e_pipeline", "block_cache"};
     for (const char *n : names) {                  // IAS_OPT_GWIN_WIN=4096 etc.
         char env[64] = "IAS_OPT_";
         size_t k = strlen(env);
@@ -176,6 +328,7 @@ int ias_get_option(const char *name, long long *value)
 int ias_set_stream(void *s)
 {
     IAS_TRY(ensure_init());
+    if (ctx().stream != (cudaStream_t)s) IAS_CUDA(cudaStreamSynchronize(ctx().stream));     // cached blocks carry the old stream's ordering
     ctx().stream = (cudaStream_t)s;          // NULL is the legacy default stream (what torch's default stream handle is)
     return IAS_OK;
 }
@@ -183,6 +336,7 @@ int ias_set_stream(void *s)
 int ias_use_own_stream(void)
 {
     IAS_TRY(ensure_init());
+    if (ctx().stream != ctx().own_stream) IAS_CUDA(cudaStreamSynchronize(ctx().stream));
     ctx().stream = ctx().own_stream;
     return IAS_OK;
 }
@@ -190,6 +344,8 @@ int ias_use_own_stream(void)
 int ias_trim_pool(void)
 {
     IAS_TRY(ensure_init());
+    IAS_CUDA(cudaStreamSynchronize(ctx().stream));
+    block_cache_flush();
     IAS_CUDA(cudaStreamSynchronize(ctx().stream));
     IAS_CUDA(cudaMemPoolTrimTo(ctx().pool, 0));          // cached blocks of earlier problem sizes go back to the driver
     return IAS_OK;

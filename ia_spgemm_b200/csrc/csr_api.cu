@@ -67,9 +67,7 @@ static int stream_impl(const AV &av, double avg, bool same, const IasCsrMatrixDe
 
     // batch capacity in entries (12 B each): the budget, but never less than the largest row
     if (budget_bytes == 0) {
-        size_t f = 0, t = 0;
-        IAS_CUDA(cudaMemGetInfo(&f, &t));
-        budget_bytes = (size_t)(0.6 * (double)f);
+        budget_bytes = (size_t)(0.6 * (double)free_device_bytes());
     }
     long long cap = (long long)(budget_bytes / 12);
     cap = std::max<long long>(cap, (long long)B->col);       // nnz(C_i) <= cols: one row always fits

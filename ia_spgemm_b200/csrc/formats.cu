@@ -384,8 +384,7 @@ static int ell_mul_onepass(const IasEllDev *A, const IasEllDev *B, IasEll64Dev *
     int log2_run = 0;
     while ((1 << log2_run) < run) ++log2_run;
     const long long w_ub = std::min<long long>((long long)wa * wb, (long long)B->col);
-    size_t f = 0, t = 0;
-    IAS_CUDA(cudaMemGetInfo(&f, &t));
+    const size_t f = free_device_bytes();
     const double need = (double)A->row * (double)w_ub * 12.0;
     if (need > 0.45 * (double)f) return IAS_OK;              // the two-pass pipeline sizes C exactly
     int col_bits = 1;

@@ -133,7 +133,9 @@ inline int read_hist(RangeWork &rw, int n, long long *out)
 {
     Ctx &c = ctx();
     IAS_CUDA(cudaMemcpyAsync(c.h_scalars, rw.hist.p, sizeof(long long) * n, cudaMemcpyDeviceToHost, c.stream));
+    HostTrace ht("cudaStreamSynchronize after the analyze kernels", 0);
     IAS_CUDA(cudaStreamSynchronize(c.stream));
+    ht.done();
     for (int i = 0; i < n; ++i) out[i] = c.h_scalars[i];
     return IAS_OK;
 }
