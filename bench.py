@@ -833,6 +833,9 @@ def main():
         else:
             sampler.pause()              # NVML polling of GPU 0 during a multi-rank timed leg would single out rank 0
             also["rmat22_strong"] = strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world)
+            scale5 = int(os.environ.get("IAS_BENCH_STRONG_SCALE", "25"))       # BASELINE config 5: R-MAT scale 25 over the GPUs of the box
+            if scale5 > 0:
+                also["rmat%d_strong" % scale5] = strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world, scale=scale5, one_gpu=False)
             sampler.resume()
 
     clocks = None
@@ -914,7 +917,7 @@ def side_config(B, eng, kind, args, with_cpu, with_cusparse):
     return out
 
 
-def strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world):
+def strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world, scale=22, one_gpu=True):
     """R-MAT scale 22 (fixed problem) over the N GPUs: B broadcast once; the rows, sorted by decreasing products, are dealt
     to the ranks in snake order (ias_row_share) and every rank multiplies its share in ONE pass of the streaming pipeline
     (ias_csr_mul_csr_rowlist_stream): every rank gets its share of hub rows and of tail rows, and no launch tail is paid
@@ -922,8 +925,9 @@ def strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world):
     same box and run."""
     out = {}
     try:
-        wname = workload_name("rmat", scale=22)
-        dA, t_bcast = shared_operand("rmat", scale=22)
+        wname = workload_name("rmat", scale=scale)
+        eng.trim_pool()
+        dA, t_bcast = shared_operand("rmat", scale=scale)
         rows = dA.dev.row
         my_rows = eng.row_share(dA, dA, world, rank)          # rows by decreasing products, dealt in snake order
         n_mine = int(my_rows.numel())
@@ -931,7 +935,7 @@ def strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world):
         def step():
             return eng.csr_mul_csr_rowlist_stream(dA, dA, my_rows.data_ptr(), n_mine)
 
-        ms_step, stats, launches, n_warm = B.timed(step, 2, 1)
+        ms_step, stats, launches, n_warm = B.timed(step, 2 if one_gpu else 1, 1, max_warm=3 if one_gpu else 1)
         st = stats[-1]
         products, nnz_c = B.all_sum(st["products"], st["nnz"])
         busy = torch.zeros(world, dtype=torch.float64, device="cuda")
@@ -945,7 +949,17 @@ def strong_scaling_leg(B, eng, torch, dist, shared_operand, args, rank, world):
                        "note": "operand resident on rank 0 -> NCCL broadcast of B (3 arrays) + multiply; C is reduced on device "
                                "(nnz, checksum, structure hash), a few scalars come back"}}
         dist.barrier()
-        if rank == 0:
+        if rank == 0 and not one_gpu:
+            # the whole problem on one GPU takes minutes at this scale: the serial equivalent is the sum of the ranks'
+            # device times (what one GPU would spend on the N shares one after the other)
+            b = out["per_rank_busy_ms"]
+            out["one_gpu_same_run"] = None
+            out["serial_equivalent_ms"] = round(float(np.sum(b)), 1)
+            out["speedup_vs_serial_equivalent"] = float(np.sum(b)) / ms_step
+            out["efficiency"] = out["speedup_vs_serial_equivalent"] / world
+            out["limiter"] = "slowest rank %.0f ms vs mean %.0f ms of device time; step %.0f ms" % (max(b), float(np.mean(b)), ms_step)
+            out["steps"], out["warmup"] = 1, n_warm
+        if rank == 0 and one_gpu:
             world_saved, B.world = B.world, 1
             try:
                 one = B.csr_leg(dA, 0, rows, 1, 1, True, 0, wname)

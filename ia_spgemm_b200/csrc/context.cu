@@ -243,6 +243,9 @@ static long long *option_slot(const char *name)
     if (!strcmp(name, "g_scr")) return &t.g_scr;
     if (!strcmp(name, "g2_takes_b2")) return &t.g2_takes_b2;
     if (!strcmp(name, "block_cache")) return &t.block_cache;
+    if (!strcmp(name, "g_split")) return &t.g_split;
+    if (!strcmp(name, "g_split_ub")) return &t.g_split_ub;
+    if (!strcmp(name, "g_split_parts")) return &t.g_split_parts;
     return nullptr;
 }
 
@@ -295,7 +298,7 @@ int ias_init(int device)
         if (!c.ev_bin[i]) IAS_CUDA(cudaEventCreate(&c.ev_bin[i]));
     if (!c.h_scalars) IAS_CUDA(cudaMallocHost((void **)&c.h_scalars, 64 * sizeof(long long)));
     static const char *const names[] = {"global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win", "g_coop", "gwin_takes_b2",
-                                        "trust_operand_cache", "g_ldca", "g_block", "ell_onepass", "g_v2", "g_tbl", "g_lpt", "bulk_store", "dia_vec", "g_scr", "g2_takes_b2", "e2e_pipeline", "block_cache"};
+                                        "trust_operand_cache", "g_ldca", "g_block", "ell_onepass", "g_v2", "g_tbl", "g_lpt", "bulk_store", "dia_vec", "g_scr", "g2_takes_b2", "e2e_pipeline", "block_cache", "g_split", "g_split_ub", "g_split_parts"};
     for (const char *n : names) {                  // IAS_OPT_GWIN_WIN=4096 etc.
         char env[64] = "IAS_OPT_";
         size_t k = strlen(env);

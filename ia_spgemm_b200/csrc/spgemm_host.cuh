@@ -95,6 +95,8 @@ struct RangeWork {
     DBuf<unsigned> gwork;          // global-row workspace slots
     DBuf<int> gscr;                // k_num_global2: split-table scratch of the rows with more than 1024 A entries
     size_t gscr_ints = 0;
+    DBuf<int> split;               // k_num_global2: [0] = rows cut into parts, then one published count per part
+    size_t split_ints = 0;
     DBuf<int> cursor;
     int gslots = 0;
     long long products = 0;
@@ -532,8 +534,28 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
                 IAS_TRY(rw.gscr.alloc((size_t)grid * scr_cap));
                 rw.gscr_ints = (size_t)grid * scr_cap;
             }
+            // rows worth splitting over several CTAs (a prefix of the work-ordered list; counted on the device)
+            const GLayout lay = GLayout::make(ncols_b);
+            const int split_cap = 1024;
+            int split_words = 0;
+            if (c.tune.g_split != 0 && glist == wo.list.p && wo.list.p) {
+                const long long parts = std::min<long long>(2048, std::max<long long>(2, c.tune.g_split_parts));
+                long long sw = ((lay.words + parts - 1) / parts + 127) / 128 * 128;
+                sw = std::min<long long>(sw, std::min<long long>(2LL * win, 2LL * 1024 * 32));
+                const long long P = (lay.words + sw - 1) / sw;
+                if (P > 1) {
+                    split_words = (int)sw;
+                    if (rw.split_ints < (size_t)split_cap * P + 1) {
+                        IAS_TRY(rw.split.alloc((size_t)split_cap * P + 1));
+                        rw.split_ints = (size_t)split_cap * P + 1;
+                    }
+                    IAS_CUDA(cudaMemsetAsync(rw.split.p, 0, sizeof(int) * ((size_t)split_cap * P + 1), c.stream));
+                    IAS_LAUNCH(k_count_split_rows, 1, 1024, 0, wo.keys_sorted.p, m, c.tune.g_split_ub, (long long)1 << 22, grid, rw.split.p);
+                }
+            }
             IAS_LAUNCH(k, grid, 1024, sm, glist, m, r0, A, B, out, c_ci, c_v, rw.gwork.p,
-                       GLayout::make(ncols_b), rw.cursor.p, win, tbl_cap, ncols_b, rw.gscr.p, scr_cap);
+                       lay, rw.cursor.p, win, tbl_cap, ncols_b, rw.gscr.p, scr_cap,
+                       split_words ? rw.split.p : (int *)nullptr, split_cap, split_words, split_words ? rw.split.p + 1 : (int *)nullptr);
         } else {
             // 160 KB tile of fp64 partial sums per SM (192 KB would leave 28 KB of L1 for the B-row stream: ncu/clock64
             // showed the mark pass 1.6x slower); with two 512-thread CTAs per SM each gets half

@@ -1482,7 +1482,9 @@ template <class AV, class BV, int BLOCK>
 __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ rows, int nrows, int r0, AV A, BV B, OutMap out,
                                                        int *__restrict__ c_ci, double *__restrict__ c_v,
                                                        unsigned *__restrict__ work, GLayout L, int *__restrict__ cursor,
-                                                       int win, int tbl_cap, int ncols, int *__restrict__ gscr, int gscr_cap)
+                                                       int win, int tbl_cap, int ncols, int *__restrict__ gscr, int gscr_cap,
+                                                       const int *__restrict__ n_split_ptr, int split_cap, int split_words,
+                                                       int *__restrict__ part_cnt)
 {
     typedef typename AV::off_t aoff;
     typedef typename BV::off_t boff;
@@ -1495,7 +1497,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
     typedef cub::BlockScan<unsigned, BLOCK> Scan;
     __shared__ typename Scan::TempStorage scan_tmp;
     __shared__ int s_row, s_next;
-    __shared__ unsigned s_carry, s_swtot;
+    __shared__ unsigned s_carry, s_swtot, s_base;
     __shared__ unsigned s_blk[BLOCK];                                         // populations of a super-window's chunks of 128 words
     __shared__ int s_bnd[G2_MAX_BND + 1];
     __shared__ CtaTile<BV, BLOCK> tile;
@@ -1506,16 +1508,32 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
     const int swords = min(win * 2, 2 * BLOCK * 32);                           // a multiple of 128 (the host rounds win to 64)
     const long long span = (long long)swords * 32;
     const int nsw = (int)((ncols + span - 1) / span);
+    // Split rows.  The first n_split rows of the (work-ordered) list are cut into P parts by column range, one work item
+    // each: a part is the product of the A row with B restricted to the part's columns (the restriction is applied where
+    // the B rows' starts and lengths are loaded), marked and ranked in ONE bitmap pass of split_words words.  A part's
+    // place in the C row is the sum of the counts of the parts before it: every part publishes its count (part_cnt,
+    // zero = not yet) as soon as its bitmap is counted and waits for its predecessors' before it emits.  Items are drawn
+    // in order from the cursor, so the parts a CTA waits for were drawn earlier by CTAs that wait only for still earlier
+    // ones.  Without this a hub row is one CTA's work from start to end: at R-MAT scale 25 almost half of the kernel's
+    // time was tails behind single rows (profiles/r02_summary.md, section 6).
+    const int P = (QB32 && rows && n_split_ptr && split_words > 0) ? (L.words + split_words - 1) / split_words : 0;
+    const int n_split = P > 1 ? min(min(__ldg(n_split_ptr), split_cap), nrows) : 0;
+    const int n_items = n_split * P + (nrows - n_split);
     for (int w = tid; w < swords; w += BLOCK) bits[w] = 0;
     while (true) {
-        if (tid == 0) { s_row = atomicAdd(cursor, 1); s_carry = 0; }
+        if (tid == 0) { s_row = atomicAdd(cursor, 1); s_carry = 0; s_base = 0; }
         __syncthreads();
         const int idx = s_row;
-        if (idx >= nrows) break;
-        const int li = rows ? rows[idx] : idx;
+        if (idx >= n_items) break;
+        int part = -1, ridx = idx - n_split * P + n_split;
+        if (idx < n_split * P) { ridx = idx / max(P, 1); part = idx - ridx * P; }
+        const bool split = part >= 0;
+        const int row_lo = split ? part * split_words * 32 : 0;                                   // the item's column range
+        const int row_hi = split && part + 1 < P ? row_lo + split_words * 32 : 0x7fffffff;
+        const int li = rows ? rows[ridx] : ridx;
         const int i = r0 + li;
-        const long long gs = out.start(li);
-        const int n = out.count(li);
+        long long gs = out.start(li);                  // (a part: moved to its place in the row once the counts before it are known)
+        int n = out.count(li);
         const aoff pa = A.begin(i), pe = A.end(i);
         const int n_a = (int)min((aoff)0x7fffffff, pe - pa);
         const bool single_tile = pe - pa <= (aoff)BLOCK;
@@ -1524,7 +1542,10 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
         boff my_qb = 0;
         int my_len = 0;
         double my_av = 0.0;
-        if (single_tile) gwin_load<true>(A, B, pa, pe, my_qb, my_len, my_av);
+        if (single_tile) {
+            gwin_load<true>(A, B, pa, pe, my_qb, my_len, my_av);
+            if (split) ColumnWindow<BV>{B, row_lo, row_hi}(my_qb, my_len);
+        }
         // Rows with more than BLOCK entries in A (the hubs): the entries' B rows (start, length) and their split points
         // go to a per-CTA scratch in global memory (L2), boundary-major so that a window's tile reads them coalesced.
         // Every boundary of every B row is searched once (the upper bound of a window is the lower bound of the next),
@@ -1537,11 +1558,27 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
         if (long_cached) {
             for (int e = tid; e < n_a; e += BLOCK) {
                 const int j = __ldg(A.ci + pa + e);
-                gx[e] = QB32 ? (int)B.begin(j) : j;
-                glen[e] = B.len(j);
+                boff b = B.begin(j);
+                int l = B.len(j);
+                if (split) ColumnWindow<BV>{B, row_lo, row_hi}(b, l);            // (split implies QB32)
+                gx[e] = QB32 ? (int)b : j;
+                glen[e] = l;
             }
             __syncthreads();
         }
+        // one tile of a long row straight from the cached (start, length) pairs (a part's are already restricted)
+        auto cached_tile = [&](aoff base, bool need_values) {
+            const int e = (int)(base - pa) + tid;
+            boff qb = 0;
+            int len = 0;
+            double av = 0.0;
+            if (e < n_a) {
+                qb = (boff)__ldcg(gx + e);
+                len = __ldcg(glen + e);
+                if (need_values) av = __ldg(A.v + pa + e);
+            }
+            return need_values ? gwin_scan<true, BLOCK>(tile, qb, len, av) : gwin_scan<false, BLOCK>(tile, qb, len, 0.0);
+        };
         auto long_table = [&](int K, auto boundary) {                 // gt[k * n_a + e], k = 0 .. K; boundary(k) = column of boundary k
             for (int e = tid; e < n_a; e += BLOCK) { gt[e] = 0; gt[(size_t)K * n_a + e] = __ldcg(glen + e); }
             const int items = n_a * (K - 1);
@@ -1583,11 +1620,11 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
             }
             return need_values ? gwin_scan<true, BLOCK>(tile, qb, len, av) : gwin_scan<false, BLOCK>(tile, qb, len, 0.0);
         };
-        const bool use_gmtbl = long_cached && nsw > 1 && (long long)n_a * (nsw + 3) <= gscr_cap;
+        const bool use_gmtbl = !split && long_cached && nsw > 1 && (long long)n_a * (nsw + 3) <= gscr_cap;
         if (use_gmtbl) long_table(nsw, [&](int k) { return (int)(k * span); });
         // split table of the mark pass: where every B row crosses the super-window boundaries
         const int mstride = (nsw + 1) | 1;
-        const bool use_mtbl = single_tile && nsw > 1 && (long long)n_a * mstride <= tbl_cap;
+        const bool use_mtbl = !split && single_tile && nsw > 1 && (long long)n_a * mstride <= tbl_cap;
         if (use_mtbl) {
             tile.rel[tid] = my_qb;
             tile.incl[tid] = my_len;
@@ -1628,10 +1665,10 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
                 if (!(cur[u] & bit)) atomicOr(&bits[k[u] >> 5], bit);
             }
         };
-        for (int k = 0; k < nsw; ++k) {
-            const long long sw_lo = k * span;
+        for (int k = split ? part : 0; k < (split ? part + 1 : nsw); ++k) {
+            const long long sw_lo = split ? (long long)row_lo : k * span;
             const int c_lo = (int)sw_lo;
-            const int c_hi = k + 1 == nsw ? 0x7fffffff : (int)(sw_lo + span);
+            const int c_hi = split ? row_hi : k + 1 == nsw ? 0x7fffffff : (int)(sw_lo + span);
             bool any = false;
             if (single_tile) {
                 boff qb = my_qb;
@@ -1639,7 +1676,7 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
                 if (use_mtbl) {
                     const int o0 = tid < n_a ? tbl[tid * mstride + k] : 0, o1 = tid < n_a ? tbl[tid * mstride + k + 1] : 0;
                     qb = my_qb + o0; len = o1 - o0;
-                } else if (nsw > 1) gwin_restrict<BLOCK>(B, n_a, qb, len, tile, c_lo, c_hi);
+                } else if (!split && nsw > 1) gwin_restrict<BLOCK>(B, n_a, qb, len, tile, c_lo, c_hi);
                 const int total = gwin_scan<false, BLOCK>(tile, qb, len, 0.0);
                 if (total) {
                     any = true;
@@ -1648,7 +1685,9 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
                 __syncthreads();
             } else {
                 for (aoff base = pa; base < pe; base += BLOCK) {
-                    const int total = use_gmtbl ? long_tile(base, k, false) : gwin_build<false, BLOCK>(A, B, base, pe, tile, c_lo, c_hi);
+                    const int total = use_gmtbl ? long_tile(base, k, false)
+                                      : split && long_cached ? cached_tile(base, false)
+                                                             : gwin_build<false, BLOCK>(A, B, base, pe, tile, c_lo, c_hi);
                     if (total) {
                         any = true;
                         gwin_run<false, BLOCK>(tile, total, [&](const boff (&q)[PB], const double (&pv)[PB], unsigned valid) { mark(q, pv, valid, c_lo); });
@@ -1657,9 +1696,15 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
                 }
             }
             GP_ADD(34);
-            if (!any) continue;
+            if (!any) {
+                if (split) {                                          // an empty part: its count is zero, nothing to emit or accumulate
+                    n = 0;
+                    if (tid == 0) atomicExch(part_cnt + idx, 1);
+                }
+                continue;
+            }
             const int w0g = c_lo >> 5;                                // first global word of the super-window
-            const int nwords = min(swords, L.words - w0g);            // a multiple of 32 (L.words and swords are)
+            const int nwords = min(split ? split_words : swords, L.words - w0g);   // a multiple of 32 (L.words, swords and split_words are)
             // The bitmap is scanned in chunks of 128 words, four consecutive words per lane (one 128-bit shared-memory
             // load): one warp scan ranks 4096 columns.  (Ranking 32 words per warp scan cost more than the marking itself
             // on sparse rows: the dependent shuffle chain is paid per scan, not per entry.)  Words between nwords and
@@ -1677,9 +1722,27 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
                 unsigned excl, tot;
                 Scan(scan_tmp).ExclusiveSum(v0, excl, tot);
                 if (tid < nchunk) s_blk[tid] = excl;
-                if (tid == 0) { s_swtot = tot; s_next = 0; }
+                if (tid == 0) {
+                    s_swtot = tot; s_next = 0;
+                    if (split) atomicExch(part_cnt + idx, (int)tot + 1);      // published before the emit: the parts behind wait for it
+                }
             }
             __syncthreads();
+            if (split) {
+                // this part's place in the row: the counts of the parts before it
+                unsigned before = 0;
+                for (int t = tid; t < part; t += BLOCK) {
+                    const volatile int *slot = part_cnt + (idx - part + t);
+                    int v = *slot;
+                    while (v == 0) { __nanosleep(200); v = *slot; }
+                    before += (unsigned)(v - 1);
+                }
+                if (before) atomicAdd(&s_base, before);
+                __syncthreads();
+                gs += s_base;
+                n = (int)s_swtot;
+                GP_ADD(35);
+            }
             // cells + sorted columns of the super-window; the bitmap is left clean.  Chunks are drawn from a counter:
             // a chunk of hub columns (4096 entries) takes twenty times longer than a sparse one, and with a fixed
             // assignment the barrier behind this loop was the largest single stall of the kernel (ncu: 15 % of samples).
@@ -1762,16 +1825,17 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
         }
         __syncthreads();
         const bool use_gatbl = long_cached && W > 1 && bnd_in_smem && (long long)n_a * (W + 3) <= gscr_cap;
+        const bool cut = W > 1 || split;                              // the B rows must be restricted to the window's columns
         if (use_gatbl) long_table(W, [&](int k) { return s_bnd[k]; });
         GP_ADD(38);
         // 3. one window of `win` ranks at a time: accumulate in the shared-memory tile, then write it out
         for (int w = 0; w < W; ++w) {
             const int wbase = w * win;
             const int wn = min(win, n - wbase);
-            int c_lo = 0, c_hi = 0x7fffffff;
+            int c_lo = row_lo, c_hi = row_hi;
             if (W > 1) {
-                if (bnd_in_smem) { c_lo = w == 0 ? 0 : s_bnd[w]; c_hi = w + 1 < W ? s_bnd[w + 1] : 0x7fffffff; }
-                else { c_lo = w == 0 ? 0 : __ldcg(c_ci + gs + wbase); c_hi = w + 1 < W ? __ldcg(c_ci + gs + wbase + win) : 0x7fffffff; }
+                if (bnd_in_smem) { c_lo = w == 0 ? row_lo : s_bnd[w]; c_hi = w + 1 < W ? s_bnd[w + 1] : row_hi; }
+                else { c_lo = w == 0 ? row_lo : __ldcg(c_ci + gs + wbase); c_hi = w + 1 < W ? __ldcg(c_ci + gs + wbase + win) : row_hi; }
             }
             // (the tile is all zero here: the emit pass left the bitmap clean -- the same bytes -- and every write-out
             //  below zeroes what it has read)
@@ -1810,7 +1874,8 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
             } else {
                 for (aoff base = pa; base < pe; base += BLOCK) {
                     const int total = use_gatbl ? long_tile(base, w, true)
-                                                : gwin_build<true, BLOCK>(A, B, base, pe, tile, W > 1 ? c_lo : 0, W > 1 ? c_hi : 0x7fffffff);
+                                      : split && long_cached && W == 1 ? cached_tile(base, true)
+                                      : gwin_build<true, BLOCK>(A, B, base, pe, tile, cut ? c_lo : 0, cut ? c_hi : 0x7fffffff);
                     GP_ADD(38);
                     if (total) gwin_run<true, BLOCK>(tile, total, add);
                     __syncthreads();
@@ -1822,10 +1887,46 @@ __global__ void __launch_bounds__(BLOCK) k_num_global2(const int *__restrict__ r
             __syncthreads();
             GP_ADD(40);
         }
-        // 4. leave the slot clean for the next row (the tile, hence the bitmap, already is)
-        g_clear<BLOCK>(wp, summary, wsum, L);
+        // 4. leave the slot clean for the next row (the tile, hence the bitmap, already is); a part touched its own blocks only
+        if (split) {
+            const int b0 = (row_lo >> 5) >> 5, b1 = min(L.blocks, b0 + (split_words >> 5));
+            for (int b = b0 + tid; b < b1; b += BLOCK) {
+                const unsigned m = __ldcg(wsum + b);
+                if (!m) continue;
+                wsum[b] = 0;
+                uint2 *cell = wp + (size_t)b * 32;
+#pragma unroll
+                for (int x = 0; x < 32; ++x)
+                    if ((m >> x) & 1u) cell[x] = make_uint2(0, 0);
+            }
+        } else g_clear<BLOCK>(wp, summary, wsum, L);
         __syncthreads();
         GP_ADD(41);
+    }
+}
+
+// the first rows of a bin's work-ordered list that are worth splitting: rows with at least `fixed_threshold` products, or
+// (fixed_threshold == 0) with more than a quarter of one CTA's even share of the launch and at least `floor_products`
+static __global__ void __launch_bounds__(1024) k_count_split_rows(const unsigned *__restrict__ keys_desc, int n, long long fixed_threshold,
+                                                                  long long floor_products, int ctas, int *__restrict__ out)
+{
+    __shared__ unsigned long long s_sum;
+    if (threadIdx.x == 0) s_sum = 0;
+    __syncthreads();
+    unsigned long long threshold = (unsigned long long)fixed_threshold;
+    if (fixed_threshold <= 0) {
+        unsigned long long mine = 0;
+        for (int t = threadIdx.x; t < n; t += 1024) mine += keys_desc[t];
+        for (int o = 16; o; o >>= 1) mine += __shfl_xor_sync(0xffffffffu, mine, o);
+        if ((threadIdx.x & 31) == 0 && mine) atomicAdd(&s_sum, mine);
+        __syncthreads();
+        threshold = max((unsigned long long)floor_products, s_sum / (unsigned long long)(4 * max(ctas, 1)));
+    }
+    // keys are sorted by decreasing work: the rows at or above the threshold are a prefix
+    int lo = 0, hi = n;
+    if (threadIdx.x == 0) {
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if ((unsigned long long)keys_desc[mid] >= threshold) lo = mid + 1; else hi = mid; }
+        *out = lo;
     }
 }
 

@@ -400,7 +400,7 @@ def test_wide_column_space_uses_64bit_sort_keys(eng, oracle):
 
 # ---------------------------------------------------------------- global rows: windowed shared-memory kernels
 _GWIN_OPTS = ("global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win", "g_coop", "gwin_takes_b2",
-              "g_v2", "g_tbl", "g_lpt", "g_block", "g_scr")
+              "g_v2", "g_tbl", "g_lpt", "g_block", "g_scr", "g_split", "g_split_ub", "g_split_parts", "g2_takes_b2")
 
 
 @pytest.fixture
@@ -484,6 +484,52 @@ def test_global_rows_long_rows_use_global_split_tables(eng, oracle, options, g_w
     options("g_scr", g_scr)
     got, st = _check(eng, oracle, A, B, mag=False)
     assert st["num_bin_rows"][5] > 0
+
+
+@pytest.mark.parametrize("kind", ["few_a_entries", "mid_a_entries", "long_a_rows"])
+@pytest.mark.parametrize("g_win,parts,g_scr,g_tbl", [(16384, 128, 8 << 20, 8192), (64, 128, 8 << 20, 8192), (256, 3, 8 << 20, 0), (2048, 2, 0, 8192),
+                                                       (64, 7, 40000, 300), (1024, 128, 8 << 20, 8192)])
+def test_global_rows_split_over_ctas(eng, oracle, options, kind, g_win, parts, g_scr, g_tbl):
+    """k_num_global2 with every global row cut into column-range parts (g_split_ub = 1: any row qualifies), one work
+    item per part: parts publish their counts and wait for the counts before them.  Geometries: parts of one bitmap
+    chunk (4096 columns) up to half the column space, one or many rank windows per part, empty parts, long A rows with
+    and without the global scratch (restricted cached B rows vs. per-window searches)."""
+    A, B = _global_operands(kind)
+    options("global_rows_smem", 1)
+    options("gwin_swords", 32)
+    options("gwin_max_sw", 1)
+    options("g_v2", 1)
+    options("g_lpt", 1)
+    options("g_split", 1)
+    options("g_split_ub", 1)
+    options("g_split_parts", parts)
+    options("g_win", g_win)
+    options("g_scr", g_scr)
+    options("g_tbl", g_tbl)
+    got, st = _check(eng, oracle, A, B, mag=False)
+    assert st["num_bin_rows"][5] > 0
+    options("g_split", 0)                      # and the same C with one CTA per row
+    got1, st1 = _mul(eng, A, B)
+    assert np.array_equal(got[0], got1[0]) and np.array_equal(got[1], got1[1])
+    assert np.all(np.abs(got[2] - got1[2]) <= RTOL * np.maximum(np.abs(got[2]), np.abs(got1[2])))
+
+
+@pytest.mark.parametrize("parts,g_split_ub", [(4, 1), (2, 20000), (128, 0)])
+def test_global_rows_split_many_rows(eng, oracle, options, parts, g_split_ub):
+    """R-MAT scale 14 with the global rows on k_num_global2: hundreds of rows cut into parts at once (more work items
+    than CTAs, so parts wait for counts published by CTAs that drew the earlier items); a threshold in the middle of
+    the work-ordered list; the automatic threshold (no row qualifies at this size)."""
+    A = W.rmat(14, 16, seed=3)
+    options("global_rows_smem", 1)
+    options("gwin_swords", 32)
+    options("gwin_max_sw", 1)
+    options("g_v2", 1)
+    options("g_win", 1024)
+    options("g2_takes_b2", 1)                  # rows of 4097..12288 entries too: enough rows for every CTA
+    options("g_split_ub", g_split_ub)
+    options("g_split_parts", parts)
+    got, st = _check(eng, oracle, A, mag=False)
+    assert st["num_bin_rows"][5] > 20
 
 
 def test_global_rows_second_generation_many_boundaries(eng, oracle, options):
