@@ -153,7 +153,10 @@ long long ias_kernel_launches(void);            /* engine kernels launched since
  * warp's register sort, 0 = always the pipeline), "g_block" (1024 / 512 threads per CTA of the L2 kernel), "g_ldca", "g_v2" (1 = second generation of the L2 kernel: rank + emit
  * from shared memory, split tables), "g_tbl" (its split-table capacity), "g_lpt" (1 = global rows in order of decreasing work), "g_scr" (per-CTA global scratch, in ints, for the split
  * tables of rows with more than 1024 A entries), "g2_takes_b2" (rows of the large CTA hash go to that kernel), "e2e_pipeline" (see ias_spgemm_auto_host), "bulk_store" (1 = cp.async.bulk copy-out of staged tiles),
- * "dia_vec" (1 = 128-bit DIA kernel).  Also read from
+ * "dia_vec" (1 = 128-bit DIA kernel), "g_split" (1 = global rows with very many products are cut into column-range parts, one CTA
+ * each), "g_split_ub" (products from which a row is cut; 0 = automatic: a quarter of one CTA's even share of the launch, at least
+ * 4 Mi), "g_split_parts" (parts per cut row, default 128), "block_cache" (1 = freed device blocks are kept per size class and reused
+ * without a driver call; ias_trim_pool returns them).  Also read from
  * IAS_OPT_<NAME> in the environment by ias_init.  Results do not depend on any of them. */
 int ias_set_option(const char *name, long long value);
 int ias_get_option(const char *name, long long *value);
