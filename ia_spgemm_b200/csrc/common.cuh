@@ -29,7 +29,7 @@ struct Tuning {
     long long g_tbl = 8192;           // ... its split-table capacity (ints of shared memory)
     long long g_scr = 16 << 20;       // ... per-CTA global scratch (ints) for the split tables of rows with > 1024 A entries (0: off)
     long long g_split = 1;            // ... rows with very many products are cut into column-range parts, one CTA each (0: one CTA per row)
-    long long g_split_ub = 0;         // ... products from which a row is cut (0: a quarter of one CTA's even share of the launch, at least 4 Mi)
+    long long g_split_ub = 0;         // ... products from which a row is cut (0: a quarter of one CTA's even share of the launch, at least 256 Ki)
     long long g_split_parts = 128;    // ... parts per cut row (the column space in equal ranges, multiples of 4096 columns)
     long long g2_takes_b2 = 0;        // rows of the large CTA hash bin (nnz 4097..12288) go to the second-generation global-row kernel
     long long g_lpt = 1;              // global rows are handed out in order of decreasing work

@@ -550,7 +550,7 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
                         rw.split_ints = (size_t)split_cap * P + 1;
                     }
                     IAS_CUDA(cudaMemsetAsync(rw.split.p, 0, sizeof(int) * ((size_t)split_cap * P + 1), c.stream));
-                    IAS_LAUNCH(k_count_split_rows, 1, 1024, 0, wo.keys_sorted.p, m, c.tune.g_split_ub, (long long)1 << 22, grid, rw.split.p);
+                    IAS_LAUNCH(k_count_split_rows, 1, 1024, 0, wo.keys_sorted.p, m, c.tune.g_split_ub, (long long)1 << 18, grid, rw.split.p);
                 }
             }
             IAS_LAUNCH(k, grid, 1024, sm, glist, m, r0, A, B, out, c_ci, c_v, rw.gwork.p,

@@ -155,7 +155,7 @@ long long ias_kernel_launches(void);            /* engine kernels launched since
  * tables of rows with more than 1024 A entries), "g2_takes_b2" (rows of the large CTA hash go to that kernel), "e2e_pipeline" (see ias_spgemm_auto_host), "bulk_store" (1 = cp.async.bulk copy-out of staged tiles),
  * "dia_vec" (1 = 128-bit DIA kernel), "g_split" (1 = global rows with very many products are cut into column-range parts, one CTA
  * each), "g_split_ub" (products from which a row is cut; 0 = automatic: a quarter of one CTA's even share of the launch, at least
- * 4 Mi), "g_split_parts" (parts per cut row, default 128), "block_cache" (1 = freed device blocks are kept per size class and reused
+ * 256 Ki), "g_split_parts" (parts per cut row, default 128), "block_cache" (1 = freed device blocks are kept per size class and reused
  * without a driver call; ias_trim_pool returns them).  Also read from
  * IAS_OPT_<NAME> in the environment by ias_init.  Results do not depend on any of them. */
 int ias_set_option(const char *name, long long value);

@@ -518,7 +518,7 @@ def test_global_rows_split_over_ctas(eng, oracle, options, kind, g_win, parts, g
 def test_global_rows_split_many_rows(eng, oracle, options, parts, g_split_ub):
     """R-MAT scale 14 with the global rows on k_num_global2: hundreds of rows cut into parts at once (more work items
     than CTAs, so parts wait for counts published by CTAs that drew the earlier items); a threshold in the middle of
-    the work-ordered list; the automatic threshold (no row qualifies at this size)."""
+    the work-ordered list; the automatic threshold."""
     A = W.rmat(14, 16, seed=3)
     options("global_rows_smem", 1)
     options("gwin_swords", 32)
