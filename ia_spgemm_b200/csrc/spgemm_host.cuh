@@ -538,7 +538,7 @@ int numeric_rows(const AV &A, const BV &B, RangeWork &rw, int b0, int b1, int nc
             const GLayout lay = GLayout::make(ncols_b);
             const int split_cap = 1024;
             int split_words = 0;
-            if (c.tune.g_split != 0 && glist == wo.list.p && wo.list.p) {
+            if (c.tune.g_split != 0 && glist == wo.list.p && wo.list.p && ncols_b <= 0x7f000000) {      // (column ranges are ints)
                 const long long parts = std::min<long long>(2048, std::max<long long>(2, c.tune.g_split_parts));
                 long long sw = ((lay.words + parts - 1) / parts + 127) / 128 * 128;
                 sw = std::min<long long>(sw, std::min<long long>(2LL * win, 2LL * 1024 * 32));
