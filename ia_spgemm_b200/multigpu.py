@@ -33,6 +33,19 @@ def balanced_row_blocks(products_per_row, parts):
     return bounds
 
 
+def snake_row_share(products_per_row, parts, part):
+    """Rows of one rank for strong scaling: the rows sorted by decreasing products (stable: ties keep index order) are
+    dealt to the ranks in snake order -- round k gives position k*parts + part (k even) or k*parts + parts-1-part
+    (k odd) -- so every rank gets its share of hub rows and of tail rows.  Same rule as ias_row_share
+    (csrc/csr_api.cu: radix sort by work, k_take_share); returns row indices in the order they are dealt."""
+    work = np.asarray(products_per_row, dtype=np.int64)
+    n = len(work)
+    order = np.argsort(-work, kind="stable")
+    k = np.arange((n + parts - 1) // parts, dtype=np.int64)
+    pos = np.where(k % 2 == 0, k * parts + part, k * parts + (parts - 1 - part))
+    return order[pos[pos < n]].astype(np.int32)
+
+
 def broadcast_csr(dist, rows, cols, rp, ci, v, src=0, device="cpu"):
     """Broadcast a CSR operand from `src` to every rank.  On `src` pass the torch tensors; elsewhere pass
     None.  Returns (rows, cols, rp, ci, v) as torch tensors on `device`."""
