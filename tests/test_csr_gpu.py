@@ -264,6 +264,9 @@ def test_row_list_streaming_equals_rows_of_the_full_product(eng, oracle):
     per_row = cs[A[2][1:]] - cs[A[2][:-1]]
     shares = [eng.row_share(dA, dA, 3, p).cpu().numpy() for p in range(3)]
     assert sorted(np.concatenate(shares).tolist()) == list(range(n))
+    from ia_spgemm_b200.multigpu import snake_row_share            # the dealing rule restated in numpy (CPU multi-rank tests use it)
+    for p in range(3):
+        assert np.array_equal(shares[p], snake_row_share(per_row, 3, p))
     tot = [int(per_row[sh].sum()) for sh in shares]
     assert max(tot) - min(tot) <= 0.05 * sum(tot) / 3 + per_row.max()
     from ia_spgemm_b200.engine import EngineError
