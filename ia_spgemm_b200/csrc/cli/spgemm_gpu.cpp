@@ -9,7 +9,10 @@
 //            --transpose-b (B := A^T, what GPU/main.cu:261-269 computes), --write-c FILE (CSR result as .mtx),
 //            --matnet FILE.h5 (MatNet weights; default: ./NetWeights/Intel_weights.h5 and ./NetWeights/P100_weights.h5
 //            when present, the paths CPU/MatNet.py:81 and GPU/MatNet.py load), --no-matnet (rule on the features),
-//            --stream [GB] (CSR result produced in HBM-budgeted row batches; taken automatically when C does not fit)
+//            --stream [GB] (CSR result produced in HBM-budgeted row batches; taken automatically when C does not fit),
+//            --gpus N (Algorithm 2 over N GPUs of the box: one process per GPU, every process loads the operands, the rows
+//            of A sorted by decreasing products are dealt to the processes in snake order -- ias_row_share -- and each
+//            multiplies its share in one streamed pass -- ias_csr_mul_csr_rowlist_stream; no collective on the data path)
 //
 // Same stages as the reference main: Matrix-Market load -> density images ./imgs/img{1,2}.txt ->
 // 26 features -> MatNet format selection -> multiply -> report block (Appendix A of SURVEY.md: run_time,
@@ -23,7 +26,10 @@
 #include <stdlib.h>
 #include <string.h>
 #include <sys/stat.h>
+#include <sys/types.h>
+#include <sys/wait.h>
 #include <time.h>
+#include <unistd.h>
 
 #include <string>
 #include <vector>
@@ -93,6 +99,64 @@ static int append_batch(const IasStreamBatch *b, void *user)
     return ferror(w->f) ? IAS_E_IO : 0;
 }
 
+// ---------------------------------------------------------------- --gpus N: one process per GPU
+// What one process reports about its share of the rows of C (sent to the parent through a pipe).
+struct ShareResult {
+    int rc;                    // 0, or the engine's error code
+    int device, rows, batches;
+    long long nnz, products;
+    double checksum, ms;
+    char error[200];
+};
+
+// Multiply the rows of `rank` (of `parts`) of A*B on the device this process is bound to: the best of `runs - 1` passes
+// after one warm-up (runs > 1), or one cold pass.
+static void multiply_share(const IasCsrMatrixDev *dA, const IasCsrMatrixDev *dB, int parts, int rank, size_t budget_bytes, int runs, ShareResult *res)
+{
+    auto failed = [&](int rc) { res->rc = rc ? rc : IAS_E_CUDA; snprintf(res->error, sizeof(res->error), "%s", ias_last_error()); };
+    int *rows_dev = nullptr, count = 0;
+    const int cap = (dA->row + parts - 1) / parts;
+    int rc = ias_device_alloc((void **)&rows_dev, sizeof(int) * (size_t)(cap > 0 ? cap : 1));
+    if (rc) return failed(rc);
+    if ((rc = ias_row_share(dA, dB, parts, rank, rows_dev, &count)) != 0) { ias_device_free(rows_dev); return failed(rc); }
+    res->rows = count;
+    for (int r = 0; r < runs; ++r) {
+        IasSpgemmStats st;
+        if ((rc = ias_csr_mul_csr_rowlist_stream(dA, dB, rows_dev, count, budget_bytes, nullptr, nullptr, nullptr, &st)) != 0) {
+            ias_device_free(rows_dev);
+            return failed(rc);
+        }
+        if (r == (runs > 1 ? 1 : 0) || (r > 0 && st.ms_total < res->ms)) res->ms = st.ms_total;
+        res->nnz = st.nnz; res->products = st.products; res->checksum = st.checksum; res->batches = st.batches;
+    }
+    ias_device_free(rows_dev);
+}
+
+// A helper process (rank >= 1): binds to its GPU (a box with fewer devices than ranks shares device 0, so that the
+// path can be exercised anywhere), uploads the operands it inherited from the parent, multiplies its share, reports.
+static void helper_process(const IasCsrMatrix *A, const IasCsrMatrix *B, bool same, bool transpose_b, int parts, int rank,
+                           size_t budget_bytes, int runs, int fd)
+{
+    ShareResult res;
+    memset(&res, 0, sizeof(res));
+    res.device = rank;
+    auto failed = [&](int rc) { res.rc = rc ? rc : IAS_E_CUDA; snprintf(res.error, sizeof(res.error), "%s", ias_last_error()); };
+    IasCsrMatrixDev dA, dB;
+    int rc = ias_init(rank);
+    if (rc == IAS_E_ARG) { res.device = 0; rc = ias_init(0); }
+    if (rc) failed(rc);
+    else if ((rc = ias_upload_csr(A, &dA)) != 0) failed(rc);
+    else {
+        if (transpose_b) rc = ias_csr_transpose(&dA, &dB);
+        else if (same) dB = dA;
+        else rc = ias_upload_csr(B, &dB);
+        if (rc) failed(rc);
+        else multiply_share(&dA, &dB, parts, rank, budget_bytes, runs, &res);
+    }
+    ssize_t w = write(fd, &res, sizeof(res));
+    _exit(w == (ssize_t)sizeof(res) && res.rc == 0 ? 0 : 1);            // no stdio flush: the buffers are the parent's
+}
+
 int main(int argc, char **argv)
 {
     std::vector<std::string> pos;
@@ -100,15 +164,17 @@ int main(int argc, char **argv)
     double stream_gb = 0.0;
     std::string write_c, matnet_path;
     double gate = 20.0;
-    int repeat = 1;
+    int repeat = 1, gpus = 1;
     std::vector<std::pair<std::string, long long> > opts;       // --opt name=value -> ias_set_option
     for (int i = 1; i < argc; ++i) {
         std::string a = argv[i];
         if (a == "--help" || a == "-h") {
             printf("usage: spgemm-gpu A.mtx [B.mtx [testing_mode]] [--all] [--json] [--gate X] [--repeat N] [--transpose-b]\n"
-                   "                  [--write-c FILE.mtx] [--matnet WEIGHTS.h5 | --no-matnet] [--stream [GB]] [--opt NAME=VALUE ...]\n"
+                   "                  [--write-c FILE.mtx] [--matnet WEIGHTS.h5 | --no-matnet] [--stream [GB]] [--gpus N] [--opt NAME=VALUE ...]\n"
                    "  --matnet FILE      MatNet weights (default: ./NetWeights/Intel_weights.h5, ./NetWeights/P100_weights.h5 when present)\n"
                    "  --stream [GB]      CSR result in HBM-budgeted row batches (automatic when C does not fit the device)\n"
+                   "  --gpus N           Algorithm 2 (CSR) over N GPUs of the box, one process per GPU: rows of A dealt by decreasing work,\n"
+                   "                     every process multiplies its share in one streamed pass; report = slowest process, summed checksums\n"
                    "  --opt NAME=VALUE   kernel-selection knob of the engine (ias_set_option, include/iaspgemm.h), e.g.\n"
                    "                     global_rows_smem=0, gwin_max_sw=0; the result does not depend on it\n");
             return 0;
@@ -131,6 +197,7 @@ int main(int argc, char **argv)
         }
         else if (a == "--gate" && i + 1 < argc) gate = atof(argv[++i]);
         else if (a == "--repeat" && i + 1 < argc) repeat = atoi(argv[++i]);
+        else if (a == "--gpus" && i + 1 < argc) gpus = atoi(argv[++i]);
         else pos.push_back(a);
     }
     for (size_t o = 0; o < opts.size(); ++o)
@@ -139,6 +206,8 @@ int main(int argc, char **argv)
         printf("please use command like this : ./spgemm-gpu ./sample.mtx\n");
         return -1;
     }
+    if (gpus < 1 || gpus > 64) { printf("--gpus expects 1..64, got %d\n", gpus); return -6; }
+    if (gpus > 1 && !write_c.empty()) { printf("--write-c needs the whole result in one process: not with --gpus %d\n", gpus); return -6; }
     const std::string fa = pos[0], fb = pos.size() > 1 ? pos[1] : pos[0];
     int testing_mode = pos.size() > 2 ? atoi(pos[2].c_str()) : 0;
     printf("-------------- %s, %s --------------\n", fa.c_str(), fb.c_str());
@@ -154,6 +223,28 @@ int main(int argc, char **argv)
     printf("Activation Matrix (B): %dx%d: nnz = %d\n", B.row, B.col, B.nnz);
     if (testing_mode) { print_csr("A_csr", A); print_csr("B_csr", B); }
     if (!transpose_b && A.col > B.row) { printf("shape mismatch: A is %dx%d, B is %dx%d\n", A.row, A.col, B.row, B.col); return -5; }
+
+    // --gpus N: the helper processes start here, before this process touches CUDA (a forked child cannot use its parent's
+    // context); each one binds to its own GPU and works on its share while this process goes on as rank 0
+    const int runs_csr = repeat > 1 ? repeat + 1 : 1;
+    std::vector<int> helper_fd;
+    std::vector<pid_t> helper_pid;
+    fflush(stdout);
+    fflush(stderr);
+    for (int r = 1; r < gpus; ++r) {
+        int fd[2];
+        if (pipe(fd) != 0) { printf("pipe failed\n"); return -8; }
+        pid_t pid = fork();
+        if (pid < 0) { printf("fork failed\n"); return -8; }
+        if (pid == 0) {
+            close(fd[0]);
+            for (size_t k = 0; k < helper_fd.size(); ++k) close(helper_fd[k]);
+            helper_process(&A, &B, same, transpose_b, gpus, r, (size_t)(stream_gb * 1e9), runs_csr, fd[1]);
+        }
+        close(fd[1]);
+        helper_fd.push_back(fd[0]);
+        helper_pid.push_back(pid);
+    }
 
     if (ias_init(0)) return die("ias_init");
     IasCsrMatrixDev dA, dB;
@@ -240,7 +331,37 @@ int main(int argc, char **argv)
     // instead: checksum, nnz and the optional .mtx output come from the batch consumer.
     bool streamed = false;
     int stream_batches = 0;
-    if (want(1)) {
+    if (gpus > 1) {
+        // rank 0's share here, the others' from their processes; the report takes the slowest process (what a caller
+        // waits for), the summed checksum and the summed nnz
+        ShareResult mine;
+        memset(&mine, 0, sizeof(mine));
+        multiply_share(&dA, &dB, gpus, 0, (size_t)(stream_gb * 1e9), runs_csr, &mine);
+        if (mine.rc) { fprintf(stderr, "spgemm-gpu: share 0: %s\n", mine.error); return 1; }
+        long long nnz = mine.nnz, products = mine.products;
+        run[1] = mine.ms; sum[1] = mine.checksum;
+        printf("share 0 on device 0: %d rows, %lld products, nnz %lld, %.3f ms\n", mine.rows, mine.products, mine.nnz, mine.ms);
+        for (size_t k = 0; k < helper_fd.size(); ++k) {
+            ShareResult res;
+            size_t got = 0;
+            while (got < sizeof(res)) {
+                ssize_t n = read(helper_fd[k], (char *)&res + got, sizeof(res) - got);
+                if (n <= 0) break;
+                got += (size_t)n;
+            }
+            close(helper_fd[k]);
+            int status = 0;
+            waitpid(helper_pid[k], &status, 0);
+            if (got != sizeof(res)) { fprintf(stderr, "spgemm-gpu: the process of share %zu ended without a report\n", k + 1); return 1; }
+            if (res.rc) { fprintf(stderr, "spgemm-gpu: share %zu: %s\n", k + 1, res.error); return 1; }
+            printf("share %zu on device %d: %d rows, %lld products, nnz %lld, %.3f ms\n", k + 1, res.device, res.rows, res.products, res.nnz, res.ms);
+            nnz += res.nnz; products += res.products; sum[1] += res.checksum;
+            if (res.ms > run[1]) run[1] = res.ms;
+        }
+        size[1] = ias_sizeof_csr(dA.row, nnz);
+        if (products != flops) { fprintf(stderr, "spgemm-gpu: the shares cover %lld products, GetFlop says %lld\n", products, flops); return 1; }
+        printf("DONE CSR (rows dealt to %d processes, one per GPU)\n", gpus);
+    } else if (want(1)) {
         for (int r = 0; r < runs; ++r) {
             IasCsr64Dev C;
             IasSpgemmStats st;
@@ -338,8 +459,8 @@ int main(int argc, char **argv)
         printf("------------------------------\n");
     }
     if (json) {
-        printf("{\"file_a\": \"%s\", \"file_b\": \"%s\", \"rows\": %d, \"cols\": %d, \"nnz_a\": %d, \"products\": %lld, \"chosen\": %d, \"features\": [",
-               fa.c_str(), fb.c_str(), A.row, dB.col, A.nnz, flops, c + 1);
+        printf("{\"file_a\": \"%s\", \"file_b\": \"%s\", \"rows\": %d, \"cols\": %d, \"nnz_a\": %d, \"products\": %lld, \"chosen\": %d, \"gpus\": %d, \"features\": [",
+               fa.c_str(), fb.c_str(), A.row, dB.col, A.nnz, flops, c + 1, gpus);
         for (int i = 0; i < 26; ++i) printf("%s%.17g", i ? ", " : "", feat[i]);
         printf("], \"run_ms\": [%g, %g, %g, %g, %g], \"verified_sum\": [%.17g, %.17g, %.17g, %.17g, %.17g], \"memory_size\": [%.17g, %.17g, %.17g, %.17g, %.17g]}\n",
                run[0], run[1], run[2], run[3], run[4], sum[0], sum[1], sum[2], sum[3], sum[4], size[0], size[1], size[2], size[3], size[4]);

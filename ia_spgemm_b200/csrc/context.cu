@@ -455,6 +455,20 @@ int ias_copy(void *dst, const void *src, size_t bytes, int kind)
     return IAS_OK;
 }
 
+int ias_device_alloc(void **ptr, size_t bytes)
+{
+    IAS_TRY(ensure_init());
+    if (!ptr) return fail(IAS_E_ARG, "ias_device_alloc: NULL");
+    return device_block(ptr, bytes ? bytes : 1);
+}
+
+int ias_device_free(void *ptr)
+{
+    IAS_TRY(ensure_init());
+    device_block_free(ptr);
+    return IAS_OK;
+}
+
 // ---------------------------------------------------------------- verified_sum (csr_dev:258-273)
 // Deterministic: cub's reduction tree is fixed for a given n.
 int ias_checksum(const double *v, long long n, double *sum)

@@ -117,7 +117,7 @@ ABI_SYMBOLS = [
     "ias_csr_is_canonical", "ias_copy", "ias_forget_operand",
     "ias_csr_mul_csr_dev64", "ias_csr_mul_csr_dev", "ias_csr_mul_csr_rows_dev64", "ias_csr_mul_csr_stream",
     "ias_csr_mul_csr_stream_cb", "ias_csr_mul_csr_rowlist_stream",
-    "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_touched_b_bytes", "ias_partition_rows", "ias_row_share", "ias_checksum",
+    "ias_csr_mul_csr_host", "ias_release_host", "ias_getflop", "ias_touched_b_bytes", "ias_partition_rows", "ias_row_share", "ias_checksum", "ias_device_alloc", "ias_device_free",
     "ias_structure_hash",
     "ias_csr_to_dia", "ias_dia_mul_dia_dev", "ias_dia_mul_dia_rows_dev", "ias_download_dia", "ias_free_dia_dev", "ias_dia_relayout",
     "ias_csr_to_ell", "ias_ell_mul_ell_dev", "ias_ell_mul_ell_dev64", "ias_download_ell", "ias_download_ell64", "ias_free_ell_dev", "ias_free_ell64_dev",

@@ -173,6 +173,10 @@ int ias_download_csr(const IasCsrMatrixDev *dev, int *row_ptr, int *col_ind, dou
 /* raw copies on the engine stream, synchronous: kind 0 = host->device, 1 = device->host, 2 = device->device
  * (DevUpload / DevDownload, GPU/detail/common.h:79-97, without the exit(1)) */
 int ias_copy(void *dst, const void *src, size_t bytes, int kind);
+/* device scratch for the caller (DevMalloc, GPU/detail/common.h:62-77, without the memset and the exit(1)): a block of
+ * the engine's pool on the engine stream, e.g. the row list ias_row_share fills; released with ias_device_free */
+int ias_device_alloc(void **ptr, size_t bytes);
+int ias_device_free(void *ptr);
 /* With ias_set_option("trust_operand_cache", 1) the engine remembers, per B operand (pointers + shape), whether its
  * rows are canonical, so that repeated row-block multiplies against one B pay the 4 B/entry check once.  Off by
  * default: a caller that turns it on promises to call this before the next multiply whenever it rewrites an

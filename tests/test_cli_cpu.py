@@ -23,7 +23,7 @@ def _run(args, cwd):
 def test_help_lists_every_flag(tmp_path):
     r = _run(["--help"], str(tmp_path))
     assert r.returncode == 0
-    for flag in ("--all", "--json", "--gate", "--repeat", "--transpose-b", "--write-c", "--matnet", "--opt"):
+    for flag in ("--all", "--json", "--gate", "--repeat", "--transpose-b", "--write-c", "--matnet", "--opt", "--gpus", "--stream"):
         assert flag in r.stdout
 
 
@@ -46,6 +46,15 @@ def test_opt_flag_is_validated_before_any_work(tmp_path):
     assert r.returncode == 250 and "negative" in r.stdout
 
 
+def test_gpus_flag_is_validated_before_any_work(tmp_path):
+    r = _run(["--gpus", "0", "x.mtx"], str(tmp_path))
+    assert r.returncode == 250 and "--gpus expects" in r.stdout                          # -6
+    r = _run(["--gpus", "2", "--write-c", "c.mtx", "x.mtx"], str(tmp_path))
+    assert r.returncode == 250 and "--write-c" in r.stdout
+    r = _run(["--gpus", "2", str(tmp_path / "missing.mtx")], str(tmp_path))              # the loader runs before any process is started
+    assert r.returncode == 255 and "could not load" in r.stdout
+
+
 def test_shape_mismatch_is_reported_before_the_device_is_touched(mtx_dir, tmp_path):
     r = _run([os.path.join(mtx_dir, "sample.mtx"), os.path.join(mtx_dir, "Trec5.mtx")], str(tmp_path))    # 8x5 times 3x7: A has more columns than B has rows
     assert r.returncode == 251 and "shape mismatch" in r.stdout                          # -5
@@ -57,5 +66,8 @@ def test_no_cpu_fallback(mtx_dir, tmp_path):
     if torch.cuda.is_available():
         pytest.skip("a CUDA device is present")
     r = _run([os.path.join(mtx_dir, "dia.mtx")], str(tmp_path))
+    assert r.returncode != 0
+    assert "no CPU fallback" in r.stderr and "Algorithm" not in r.stdout
+    r = _run([os.path.join(mtx_dir, "dia.mtx"), "--gpus", "2"], str(tmp_path))          # nor with one process per GPU
     assert r.returncode != 0
     assert "no CPU fallback" in r.stderr and "Algorithm" not in r.stdout

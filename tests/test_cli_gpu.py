@@ -43,6 +43,24 @@ def test_cli_report_matches_reference_numbers(golden, mtx_dir, tmp_path, name):
     assert np.array_equal(np.loadtxt(os.path.join(tmp_path, "imgs", "img2.txt"), dtype=np.int64).reshape(128, 128), img1)
 
 
+@pytest.mark.parametrize("name", ["LFAT5", "Ragusa18"])
+def test_cli_gpus_flag_deals_the_rows_to_one_process_per_gpu(mtx_dir, tmp_path, name):
+    """--gpus 3: two helper processes plus the main one, each multiplying its snake-dealt share of the rows (on a box
+    with fewer devices the helpers share device 0): nnz (memory_size), products and verified_sum equal the one-GPU run."""
+    path = os.path.join(mtx_dir, name + ".mtx")
+    one = _run([path, "--json", "--no-matnet", "--all"], str(tmp_path))
+    three = _run([path, "--json", "--no-matnet", "--gpus", "3"], str(tmp_path))
+    assert one.returncode == 0 and three.returncode == 0, three.stdout + three.stderr
+    j1, j3 = json.loads(one.stdout.strip().splitlines()[-1]), json.loads(three.stdout.strip().splitlines()[-1])
+    assert j3["gpus"] == 3 and j1["gpus"] == 1
+    shares = re.findall(r"share (\d) on device (\d): (\d+) rows, (\d+) products, nnz (\d+)", three.stdout)
+    assert [s[0] for s in shares] == ["0", "1", "2"]
+    assert sum(int(s[2]) for s in shares) == j3["rows"] and sum(int(s[3]) for s in shares) == j3["products"] == j1["products"]
+    assert "DONE CSR (rows dealt to 3 processes" in three.stdout
+    assert j3["memory_size"][1] == j1["memory_size"][1]
+    assert j3["verified_sum"][1] == pytest.approx(j1["verified_sum"][1], rel=1e-12, abs=1e-9)
+
+
 def test_cli_dia_known_answer(mtx_dir, tmp_path):
     r = _run([os.path.join(mtx_dir, "dia.mtx"), "--all"], str(tmp_path))
     assert r.returncode == 0
