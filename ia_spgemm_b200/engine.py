@@ -319,7 +319,10 @@ class Engine:
         sw = max(32, (sw + 31) // 32 * 32)
         nsw = (words + sw - 1) // sw
         mx = self.get_option("gwin_max_sw")
-        return "k_num_gwin" if (mx == 0 or nsw <= mx) else "k_num_global"
+        if mx == 0 or nsw <= mx:
+            return "k_num_gwin"
+        second_generation = self.get_option("g_v2") != 0 and self.get_option("g_block") != 512
+        return "k_num_global2" if second_generation else "k_num_global"
 
     def get_option(self, name):
         v = C.c_longlong()
