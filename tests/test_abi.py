@@ -192,7 +192,8 @@ def test_options_round_trip_without_a_device(lib):
     """ias_set_option / ias_get_option are host-only bookkeeping: every documented knob exists, unknown names and
     negative values are refused (status 2 = IAS_E_ARG), and nothing needs a GPU."""
     names = ["global_rows_smem", "gwin_swords", "gwin_win", "gwin_sym_swords", "gwin_smem_kb", "gwin_max_sw", "g_win",
-             "g_coop", "gwin_takes_b2", "trust_operand_cache", "ell_onepass", "g_block", "g_ldca", "g_v2", "g_tbl", "g_lpt", "bulk_store", "dia_vec", "g_scr", "g2_takes_b2", "e2e_pipeline"]
+             "g_coop", "gwin_takes_b2", "trust_operand_cache", "ell_onepass", "g_block", "g_ldca", "g_v2", "g_tbl", "g_lpt", "bulk_store", "dia_vec", "g_scr", "g2_takes_b2", "e2e_pipeline",
+             "block_cache", "g_split", "g_split_ub", "g_split_parts"]
     header = open(os.path.join(ROOT, "include", "iaspgemm.h")).read()
     for n in names:
         assert '"%s"' % n in header, n            # documented where the entry point is declared
