@@ -465,6 +465,10 @@ class Bench:
                 "kernel_ms": dom_ms, "algorithmic_bytes": alg_bytes,
                 "step_frac": alg_bytes / (ms_step * 1e-3) / 1e9 / self.peak,
                 "note": "rank 0's rows" if self.world > 1 else "the whole job"}
+        # secondary diagnostic (not graded): the no-cache gather model -- every B entry re-fetched per product
+        gather_bytes = alg_bytes + 12 * int(st["products"])
+        roof["gather_model"] = {"bytes": gather_bytes, "step_frac": gather_bytes / (ms_step * 1e-3) / 1e9 / self.peak,
+                                "note": "bytes_alg + 12 B per intermediate product"}
         cfg = {"streaming_batches": st.get("batches", 1), "warmup_steps_run": n_warm,
                "engine_ms_per_call": [round(float(x.get("ms_total", 0.0)), 3) for x in stats],      # the C call's own event timing, every step
                "phase_ms": {k: float(np.mean([s.get(k, 0.0) for s in stats])) for k in ("ms_analyze", "ms_symbolic", "ms_scan", "ms_numeric")},
