@@ -110,3 +110,50 @@ def test_known_answer_from_the_reference_screenshots(lib, golden):
     cls, probs = net.predict(img1, img2, feats[:18])
     assert cls == 2 and probs[cls] > 0.9                               # GPU/2.jpg: Algorithm 3 (NSPARSE) is the fastest
     net.close()
+
+
+_FUZZ = r'''
+import ctypes as C, random, sys
+sys.path.insert(0, sys.argv[1])
+from ia_spgemm_b200 import engine as E
+lib = E.load_library()
+src = open(sys.argv[2], "rb").read()
+rng = random.Random(int(sys.argv[4]))
+loaded = 0
+for t in range(int(sys.argv[5])):
+    b = bytearray(src)
+    kind = rng.randrange(4)
+    if kind == 0:                                   # a few flipped bytes anywhere
+        for _ in range(rng.randrange(1, 8)): b[rng.randrange(len(b))] = rng.randrange(256)
+    elif kind == 1:                                 # truncated
+        b = b[:rng.randrange(len(b))]
+    elif kind == 2:                                 # the superblock / root group / heaps at the start
+        for _ in range(rng.randrange(1, 40)): b[rng.randrange(min(4096, len(b)))] = rng.randrange(256)
+    else:                                           # an 8-byte offset or length replaced by a random value
+        o = rng.randrange(len(b) // 8) * 8
+        b[o:o + 8] = rng.getrandbits(64).to_bytes(8, "little")
+    open(sys.argv[3], "wb").write(b)
+    h = C.c_void_p()
+    if lib.ias_matnet_load(sys.argv[3].encode(), C.byref(h)) == 0 and h.value:
+        loaded += 1
+        lib.ias_matnet_free(h)
+print("survived", loaded)
+'''
+
+
+@pytest.mark.timeout(300)
+def test_weight_reader_survives_corrupted_files(tmp_path):
+    """The HDF5 reader bounds-checks every offset and length it follows: 300 corrupted copies of a shipped weight file
+    (flipped bytes, truncation, random offsets) are refused or loaded, never a crash (run in a child process so that a
+    crash would be seen as one)."""
+    import subprocess
+    import sys
+    path = os.path.join(REF, FILES["Intel"][0])
+    if not os.path.exists(path):
+        pytest.skip("reference weights not present")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for seed in (11, 12):
+        r = subprocess.run([sys.executable, "-c", _FUZZ, root, path, str(tmp_path / "fuzz.h5"), str(seed), "150"],
+                           capture_output=True, text=True, timeout=280)
+        assert r.returncode == 0, "the reader crashed on a corrupted file (seed %d): %s" % (seed, r.stderr[-500:])
+        assert r.stdout.startswith("survived")

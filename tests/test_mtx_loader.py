@@ -143,3 +143,67 @@ def test_large_regular_file_uses_every_thread_and_keeps_file_order(lib, tmp_path
     new, old = _load(lib, p), _load(lib, p, "fscanf")
     assert _same(new, old)
     assert new[2][-1] == old[2][-1] > 0
+
+
+_FUZZ = r'''
+import ctypes as C, os, random, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+from ia_spgemm_b200 import engine as E
+lib = E.load_library()
+path, rng = sys.argv[2], random.Random(int(sys.argv[3]))
+TOKENS = ["1", "2", "3", "4", "5", "0", "-1", "+2", "99999999999", "1.5", "-2e3", "nan", "inf", "0x1p3", "abc", "%", "1e400", ".", "+", "-",
+          "1e", "\n", "\n\n", "\t", " ", "\r\n", "\f", "\v", "\0"]
+
+
+def load(mode):
+    if mode:
+        os.environ["IAS_MTX_LOADER"] = mode
+    else:
+        os.environ.pop("IAS_MTX_LOADER", None)
+    h = E.CsrMatrix()
+    rc = lib.ias_mtx_load(path.encode(), C.byref(h))
+    if rc:
+        return rc
+    out = (h.row, h.col, h.nnz, np.ctypeslib.as_array(h.row_ind, shape=(h.row + 1,)).tobytes(),
+           np.ctypeslib.as_array(h.col_ind, shape=(max(h.nnz, 1),))[:h.nnz].tobytes(),
+           np.ctypeslib.as_array(h.values, shape=(max(h.nnz, 1),))[:h.nnz].tobytes())
+    lib.ias_free_host_csr(C.byref(h))
+    return out
+
+
+for t in range(int(sys.argv[4])):
+    field = rng.choice(["real", "integer", "pattern"])
+    symm = rng.choice(["general", "symmetric", "hermitian", "skew-symmetric"])
+    m, n, nz = rng.randrange(0, 7), rng.randrange(0, 7), rng.randrange(0, 12)
+    body = []
+    for e in range(rng.randrange(0, 14)):
+        if rng.random() < 0.8:                       # an entry line, indices sometimes out of range
+            toks = [str(rng.randrange(0, 8)), str(rng.randrange(0, 8))]
+            if field == "real":
+                toks.append(rng.choice(["1.5", "-2", "3e1", "7"]))
+            elif field == "integer":
+                toks.append(str(rng.randrange(-9, 9)))
+            body.append(rng.choice([" ", "  ", "\t"]).join(toks) + rng.choice(["\n", "\n", "\r\n", " \n"]))
+        else:                                        # anything
+            body.append("".join(rng.choice(TOKENS) + rng.choice([" ", "", "\n"]) for _ in range(rng.randrange(1, 6))))
+    text = "%%%%MatrixMarket matrix coordinate %s %s\n%% c\n%d %d %d\n" % (field, symm, m, n, nz) + "".join(body)
+    open(path, "wb").write(text.encode("latin1"))
+    a, b = load(None), load("fscanf")
+    if a != b:
+        print("MISMATCH", repr(text))
+        sys.exit(3)
+print("agreed")
+'''
+
+
+@pytest.mark.timeout(300)
+def test_random_files_parse_like_the_fscanf_loop(tmp_path):
+    """Differential fuzz in a child process (a crash would be seen as one): regular entry lines mixed with arbitrary token
+    soup -- signs, hex floats, inf/nan, NUL bytes, form feeds, comments, numbers that overflow -- 600 files."""
+    import subprocess
+    for seed in (21, 22):
+        r = subprocess.run([sys.executable, "-c", _FUZZ, ROOT, str(tmp_path / "fuzz.mtx"), str(seed), "300"],
+                           capture_output=True, text=True, timeout=280)
+        assert r.returncode == 0, (r.stdout[-800:], r.stderr[-800:])
+        assert r.stdout.strip().endswith("agreed")
